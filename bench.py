@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- DBSCAN Mpts/s (config C2: 1M-point clustered cloud, eps 0.07, minPts 7) and ICP iters/s
+(config C3: 100k source vs 1M target, 50 iterations) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (CPU oracle port) on the host cores
+
+A step = one full DBSCAN pass (grid build -> core classification -> union-find -> labels) over one
+batch.  `value` is timed with CUDA events with the inputs resident in HBM (L2 flushed between steps,
+the flush is outside the timed region); `e2e` goes through the host-pointer C ABI (the call a P/Invoke
+user makes) with pinned host buffers, H2D and D2H inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+EPS, MIN_PTS = 0.07, 7
+DB_GRID, DB_N = 140, 1_000_000            # config C2
+ICP_M, ICP_N, ICP_ITERS = 1_000_000, 100_000, 50   # config C3
+DB_ALGO_BYTES_PER_PT = 21                  # 16 B read + 4 B cluster_id + 1 B is_key
+METRIC = "dbscan_mpts_per_s"
+UNIT = "Mpts/s"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [v for v in sm if v >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm (C++ port = oracle) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_dbscan_pass(oracle, mx, my, threads):
+    t0 = time.perf_counter()
+    oracle.dbscan(mx, my, EPS, MIN_PTS, 0, variant="grid", n_threads=threads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_py as oracle
+    from vtkcloudpoint_b200 import synth
+    oracle.lib()
+    cores = os.cpu_count() or 1
+    mx, my = synth.dbscan_cloud(0xC2, DB_GRID, n_total=DB_N)
+    for _ in range(min(args.warmup, 1)):
+        cpu_dbscan_pass(oracle, mx, my, cores)
+    times = [cpu_dbscan_pass(oracle, mx, my, cores) for _ in range(args.steps)]
+    total = sum(times)
+    value = DB_N * len(times) / total / 1e6
+    # ICP: bounded sample = 2 of the 50 iterations on the full C3 clouds
+    model, data, _, _ = synth.icp_clouds(0xC3, ICP_M, ICP_N)
+    t0 = time.perf_counter()
+    oracle.icp_rigid(model, data, -1.0, 2, use_grid=True, n_threads=cores)
+    icp_s = time.perf_counter() - t0
+    sample = f"full C2 cloud ({DB_N} pts), {len(times)} passes of the grid-accelerated C++ port of DBImproved.dbscan, {cores} threads for the region queries"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: DBSCAN 1M-point clustered cloud + noise, eps 0.07, minPts 7 (host CPU, reference algorithm)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "secondary": {"metric": "icp_iters_per_s", "value": 2 / icp_s, "unit": "iters/s",
+                      "sample": "2 iterations of C3 (100k vs 1M) incl. one grid build, grid-accelerated C++ port, all cores"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vtkcloudpoint_b200 import Context, synth
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = Context(local_rank)
+    peak_gbs, peak_src = load_peaks()
+
+    # ---- inputs: every rank owns one C2-sized cloud (weak scaling; slab exchange is in distributed.py)
+    mx, my = synth.dbscan_cloud(0xC2 + 1000 * rank, DB_GRID, n_total=DB_N)
+    h_x = torch.from_numpy(mx).pin_memory()
+    h_y = torch.from_numpy(my).pin_memory()
+    d_x, d_y = h_x.to(dev), h_y.to(dev)
+    out_dev = (torch.empty(DB_N, dtype=torch.int32, device=dev), torch.empty(DB_N, dtype=torch.uint8, device=dev),
+               torch.empty(DB_N, dtype=torch.uint8, device=dev), torch.empty(1, dtype=torch.int32, device=dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_dev():
+        ctx.dbscan_dev(d_x, d_y, EPS, MIN_PTS, 0, out=out_dev)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_dev()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()                      # L2 flush, outside the timed interval
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_dev()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = ctx.launch_count - launches0
+    dev_ms = max_over_ranks(dev_ms)
+    value = world * DB_N * args.steps / (dev_ms * 1e-3) / 1e6
+
+    # ---- e2e: host-pointer C ABI, pinned host buffers, H2D + D2H inside the timed region
+    from vtkcloudpoint_b200 import DbscanResult
+    res = DbscanResult(torch.empty(DB_N, dtype=torch.int32).pin_memory().numpy(), torch.empty(DB_N, dtype=torch.uint8).pin_memory().numpy(),
+                       torch.empty(DB_N, dtype=torch.uint8).pin_memory().numpy(), 0)
+    hx_np, hy_np = h_x.numpy(), h_y.numpy()
+    for _ in range(3):
+        ctx.dbscan(hx_np, hy_np, EPS, MIN_PTS, 0, out=res)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.dbscan(hx_np, hy_np, EPS, MIN_PTS, 0, out=res)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop()
+    e2e_value = world * DB_N * args.steps / e2e_s / 1e6
+
+    # ---- roofline: per-kernel CUDA-event times of the same step (separate profiled passes)
+    roofline, kernels = None, {}
+    if rank == 0:
+        ctx.profile(True)
+        for _ in range(max(3, min(args.steps, 10))):
+            flush.zero_()
+            step_dev()
+        rep = ctx.profile_report()
+        ctx.profile(False)
+        agg = {}
+        for name, ms in rep:
+            agg.setdefault(name, []).append(ms)
+        passes = max(3, min(args.steps, 10))
+        per_step = {k: sum(v) / passes for k, v in agg.items()}      # ms per step, all launches of that kernel
+        step_ms = sum(per_step.values())
+        top = max(per_step, key=per_step.get)
+        top_launch_ms = sum(agg[top]) / len(agg[top])
+        units_per_launch = DB_N
+        achieved = DB_ALGO_BYTES_PER_PT * units_per_launch / (top_launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                    "traffic": None, "peak_source": peak_src, "kernel_ms": top_launch_ms, "kernel_share_of_step": per_step[top] / step_ms,
+                    "pipeline_frac": DB_ALGO_BYTES_PER_PT * DB_N / (dev_ms / args.steps * 1e-3) / 1e9 / peak_gbs}
+        kernels = {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}
+
+    # ---- secondary metric: ICP iters/s (C3), rank 0 only
+    icp = None
+    if rank == 0 and not args.no_icp:
+        model, data, _, _ = synth.icp_clouds(0xC3, ICP_M, ICP_N)
+        hm, hd = torch.from_numpy(model).pin_memory(), torch.from_numpy(data).pin_memory()
+        dm, dd = hm.to(dev), hd.to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ctx.icp_set_model_dev(dm); e1.record(); torch.cuda.synchronize()
+        build_ms = e0.elapsed_time(e1)
+        outs = None
+        for _ in range(3):
+            outs = ctx.icp_rigid_dev(dd, -1.0, ICP_ITERS, out=outs)
+        torch.cuda.synchronize()
+        reps = max(3, min(args.steps, 10))
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0.record(); ctx.icp_rigid_dev(dd, -1.0, ICP_ITERS, out=outs); e1.record(); torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        it_s = ICP_ITERS * reps / (tot * 1e-3)
+        t0 = time.perf_counter()
+        r = ctx.icp_rigid(model, data, -1.0, ICP_ITERS)
+        icp_e2e_s = time.perf_counter() - t0
+        algo_bytes = 28 * ICP_N + 24 * ICP_M
+        icp = {"metric": "icp_iters_per_s", "value": it_s, "unit": "iters/s", "workload": "C3: 100k source vs 1M target, 50 iterations, fp64",
+               "ms_per_iter": 1e3 / it_s, "model_grid_build_ms": build_ms, "e2e_iters_per_s": ICP_ITERS / icp_e2e_s,
+               "roofline_frac": algo_bytes * it_s / 1e9 / peak_gbs, "rmse_last": r.rmse}
+
+    # ---- CPU baseline (oracle port) on this box's host cores, N = 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import oracle_py as oracle
+        cores = os.cpu_count() or 1
+        t = min(cpu_dbscan_pass(oracle, mx, my, cores) for _ in range(2))
+        cpu = {"value": DB_N / t / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"one pass over the full C2 cloud ({DB_N} pts), grid-accelerated C++ port of DBImproved.dbscan, best of 2"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7",
+                       "points_per_gpu": DB_N, "parallelism": "1 cloud per GPU" if world > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB write)",
+                       "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * DB_N, "d2h_bytes_per_step": 6 * DB_N + 4,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "secondary": icp,
+            "kernel_ms_per_step": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-icp", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/*
+ * vpc.h -- C ABI of libvpc.so: the B200-native (sm_100a) DBSCAN + ICP hot path of
+ * ZhiHuangHn/vtkCloudPoint, callable from the reference's C# through P/Invoke.
+ *
+ * The reference has no FFI for this path; the boundary is the public surface of its
+ * BaseClass algorithm classes.  Each export below names the
+ * reference method (file:line under vtkPointCloud/) it replaces.  INTEGRATION.md shows
+ * the [DllImport] stubs and the shim classes that keep the C# signatures.
+ *
+ * Conventions: extern "C", cdecl; every size is int64_t, every real is double (IEEE
+ * binary64, no FMA contraction inside the library); outputs are caller-allocated; no
+ * ownership crosses the boundary; host arrays need only stay valid for the call.
+ * Return value 0 = VPC_OK, negative = VPC_E_*; vpc_last_error() gives the message.
+ * Nothing throws across the boundary (the C# shim converts non-zero to MException,
+ * Matrix.cs:710-715).  There is NO CPU fallback: without a CUDA device vpc_create fails.
+ *
+ * Thread safety: a vpc_ctx serialises its calls with an internal mutex, so the
+ * reference's ThreadPool workers (FrmMain.cs:1356-1359) may share one context or use
+ * one context each.  No global mutable state.
+ */
+#ifndef VPC_H_
+#define VPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPC_OK 0
+#define VPC_E_BADARG (-1)   /* null pointer, negative size, m == 0 for ICP, eps == +inf */
+#define VPC_E_CUDA (-2)     /* CUDA runtime error (message has the cudaError string) */
+#define VPC_E_NOMEM (-3)    /* device or host allocation failed */
+#define VPC_E_NODEVICE (-4) /* no usable CUDA device: there is no CPU fallback */
+#define VPC_E_TOOBIG (-5)   /* n exceeds the 2^31-2 indexable points of one call */
+#define VPC_E_STATE (-6)    /* call sequence error (e.g. ICP model not set) */
+
+typedef struct vpc_ctx vpc_ctx;
+
+/* ---- context ------------------------------------------------------------------- */
+
+/* One context drives one GPU (device_ids[0]; device_ids == NULL means device 0).
+ * n_devices > 1 is reserved for the single-process multi-GPU mode; the multi-GPU path
+ * shipped today is one process per GPU (vtkcloudpoint_b200/distributed.py). */
+int vpc_create(vpc_ctx** out, const int* device_ids, int n_devices);
+void vpc_destroy(vpc_ctx* ctx);
+const char* vpc_last_error(const vpc_ctx* ctx);
+const char* vpc_version(void);
+/* Kernels launched by this context so far (bench.py's gpu_launches evidence). */
+int64_t vpc_launch_count(const vpc_ctx* ctx);
+
+/* Optional per-kernel timing: while enabled every kernel launch is bracketed by CUDA events on
+ * its own stream.  vpc_profile_report synchronises the device, writes one "kernel_name ms\n"
+ * line per launch since the last report into buf (NUL-terminated, truncated to cap) and returns
+ * the byte count.  Used by bench.py for the roofline figure; off by default. */
+int vpc_profile_enable(vpc_ctx* ctx, int on);
+int64_t vpc_profile_report(vpc_ctx* ctx, char* buf, int64_t cap);
+
+/* ---- DBSCAN --------------------------------------------------------------------- */
+
+/* Replaces `new DBImproved{cf = first_cluster_id}.dbscan(lst, e, minPts)`
+ * (BaseClass/DBImproved.cs:91-114 with isKeyPoint :33-54, expandCluster :56-90 and
+ * getDisP :14-25; call sites FrmMain.cs:1507-1516, :2785-2786, Tools.cs:591-592).
+ *   mx, my         motor_x / motor_y of lst[i]                       (in,  n doubles each)
+ *   cluster_id     Point3D.clusterId: 0 = noise, else first_cluster_id+1..  (out, n)
+ *   is_key         Point3D.isKeyPoint (core flag)                    (out, n bytes 0/1)
+ *   is_classed     Point3D.isClassed                                 (out, n bytes 0/1)
+ *   cluster_amount DBImproved.clusterAmount = first_cluster_id + #clusters (out, nullable)
+ * Result contract (identical to the C#, which callers always enter with clusterId = 0
+ * and isClassed = false): a point is core iff #{q : |dx|+|dy| <= eps} >= min_pts
+ * (itself included); clusters are numbered by ascending minimum core index; a
+ * non-core point within eps of core points takes the LARGEST adjacent cluster id (the
+ * C#'s unconditional relabel :87, last writer wins); everything else is 0.
+ * eps = +inf is rejected (VPC_E_BADARG); eps < 0 or NaN yields all-noise as in the C#. */
+int vpc_dbscan_l1_2d(vpc_ctx* ctx, const double* mx, const double* my, int64_t n, double eps,
+                     int32_t min_pts, int32_t first_cluster_id, int32_t* cluster_id,
+                     uint8_t* is_key, uint8_t* is_classed, int32_t* cluster_amount);
+
+/* Same, all pointers are DEVICE pointers on the context's GPU, work is enqueued on
+ * `stream` (a cudaStream_t; NULL = the legacy default stream) and the call returns
+ * without synchronising unless the workspace had to grow.  d_cluster_amount nullable. */
+int vpc_dbscan_l1_2d_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, int64_t n, double eps,
+                         int32_t min_pts, int32_t first_cluster_id, int32_t* d_cluster_id,
+                         uint8_t* d_is_key, uint8_t* d_is_classed, int32_t* d_cluster_amount,
+                         void* stream);
+
+/* ---- ICP ------------------------------------------------------------------------ */
+
+/* Point sets are PLANAR: xyz = x[0..k) y[0..k) z[0..k) (one H2D copy, coalesced). */
+
+/* Replaces ICP.FindClosestPointSet(model, data) (BaseClass/ICP.cs:224-250): for each
+ * data point the index of the nearest model point, d2 = (dx*dx + dy*dy) + dz*dz, ties
+ * to the LOWEST model index (strict '<' over ascending j, :240).  The C# returns the
+ * model points themselves and discards the index; order[] is that index.
+ * sqdist nullable.  m == 0 -> VPC_E_BADARG (the C# indexes model[0], :233). */
+int vpc_closest_point_set(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double* data_xyz,
+                          int64_t n, int32_t* order, double* sqdist);
+
+/* Replaces `new ICP().go_hell_ICP(model, data, R, T, e)` (BaseClass/ICP.cs:18-181; call
+ * site FrmMain.cs:2685-2690): nearest correspondences, centroids, cross-covariance,
+ * unit-quaternion solve (Besl-McKay / Horn; Matrix.ComputeEvJacobi's role), SSE, compose
+ * R <- R1*R, T <- R1*T + T1, re-transform the ORIGINAL data, until |d - pre_d| < e.
+ * R is Matrix(3,3).mat row-major, T is Matrix(3,1).mat (Matrix.cs:30-34); both are
+ * overwritten like the C# mutates them.  The five defects of the C# as written
+ * (integer 1/N, '+' for '-' on the mean product, delta[2], the Jacobi index bug, the
+ * eigenvector column) are NOT reproduced: this computes the intended
+ * least-squares rigid step, like the oracle.
+ *   max_iters   <= 0: run until convergence like the reference (it has no cap)
+ *   iters_done  rounds executed; sse_last = d of the last round; order_last (nullable,
+ *               n) = correspondences of the last round. */
+int vpc_icp_rigid(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double* data_xyz, int64_t n,
+                  double e, int32_t max_iters, double R[9], double T[3], int32_t* iters_done,
+                  double* sse_last, int32_t* order_last);
+
+/* Device-resident ICP in three steps: build the model's cell list once, then query or
+ * iterate any number of times.  All pointers are device pointers; work goes to `stream`. */
+int vpc_icp_set_model_dev(vpc_ctx* ctx, const double* d_model_xyz, int64_t m, void* stream);
+int vpc_closest_point_set_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, int32_t* d_order,
+                              double* d_sqdist, void* stream);
+/* d_state_out (device, 16 doubles): R[9], T[3], sse_last, iters_done, converged, 0.
+ * max_iters must be > 0 here (the whole loop is enqueued without host round trips). */
+int vpc_icp_rigid_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, double e, int32_t max_iters,
+                      double* d_state_out, int32_t* d_order_last, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,90 @@
+/*
+ * vpc_oracle.h -- CPU oracle for the vtkCloudPoint DBSCAN / ICP hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain C++ restatement of the reference's C#
+ * algorithm (vtkPointCloud/BaseClass/DBImproved.cs, ICP.cs, Matrix.cs).  It is the
+ * checker the CUDA path is compared with; it is never linked into, imported by or
+ * called from the product library (libvpc.so).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * PARITY STATUS: "parity unpinned" against an execution of the reference itself --
+ * the reference is C#/.NET 3.5 WinForms, no dotnet/mono/csc exists in the build image,
+ * and the reference ships no tests, golden vectors or known-answer data (SURVEY.md
+ * section 4 / 8c).  The oracle is pinned instead by (i) a line-by-line literal
+ * restatement, (ii) cross-checks against scikit-learn DBSCAN(metric='manhattan') and
+ * NumPy argmin / eigh / Kabsch-SVD in tests/, (iii) committed fixtures in tests/golden.
+ *
+ * All reals are IEEE binary64, compiled with -ffp-contract=off (the .NET x86 JIT the
+ * reference targets evaluates in 53-bit precision without FMA).
+ */
+#ifndef VPC_ORACLE_H_
+#define VPC_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPCO_OK 0
+#define VPCO_E_BADARG (-1)
+#define VPCO_E_REFERENCE_THROWS (-7) /* the as-written C# would throw here */
+
+/* DBImproved.dbscan, literal: DBImproved.cs:14-114.
+ * Θ(n²) region queries, FIFO `nei` with duplicates, unconditional relabel (:87).
+ * dedup_loop != 0 also executes the quadratic no-op de-dup scan (:70-83) so that the
+ * timing is faithful; it never changes the result.
+ * Unlike the C# method this resets clusterId/isClassed/isKeyPoint first -- every
+ * reference caller does so before the call (FrmMain.cs:1219-1223, 1512-1515;
+ * Tools.cs:584-590).  first_cluster_id is the pre-seeded `cf` (FrmMain.cs:1509).
+ * dist_evals (nullable) receives the getDisP call count (`iritatorNum`, :19). */
+int vpco_dbscan_l1_2d_literal(const double* mx, const double* my, int64_t n, double eps,
+                              int32_t min_pts, int32_t first_cluster_id,
+                              int32_t* cluster_id, uint8_t* is_key, uint8_t* is_classed,
+                              int32_t* cluster_amount, int dedup_loop, int64_t* dist_evals);
+
+/* Same control flow as the literal version (scan-order seeds, FIFO expansion, last
+ * writer wins) but isKeyPoint's O(n) scan is replaced by a cell-list query that
+ * returns the identical ascending index list.  n_threads > 1 precomputes the
+ * neighbour lists in parallel; the expansion itself stays sequential. */
+int vpco_dbscan_l1_2d_grid(const double* mx, const double* my, int64_t n, double eps,
+                           int32_t min_pts, int32_t first_cluster_id,
+                           int32_t* cluster_id, uint8_t* is_key, uint8_t* is_classed,
+                           int32_t* cluster_amount, int n_threads);
+
+/* ICP.FindClosestPointSet, literal: ICP.cs:224-250.  xyz arrays are planar:
+ * x[0..m) y[0..m) z[0..m).  order[i] = argmin_j, strict '<' so ties -> lowest j.
+ * sqdist nullable.  n_threads splits the data points. */
+int vpco_closest_point_set_literal(const double* model_xyz, int64_t m, const double* data_xyz,
+                                   int64_t n, int32_t* order, double* sqdist, int n_threads);
+/* Grid-accelerated, identical output (ring search continues while the unexplored
+ * region could still hold an equal-or-closer point). */
+int vpco_closest_point_set_grid(const double* model_xyz, int64_t m, const double* data_xyz,
+                                int64_t n, int32_t* order, double* sqdist, int n_threads);
+
+/* One rigid step from fixed correspondences: the *intended* Besl-McKay/Horn
+ * quaternion solve of ICP.cs:31-124 with the five defects corrected (see .cpp).
+ * P, Y planar n-point arrays.  R1 row-major 3x3, T1[3], sse = sum |P-Y|^2 (:126-133). */
+int vpco_rigid_step(const double* P_xyz, const double* Y_xyz, int64_t n, double R1[9],
+                    double T1[3], double* sse);
+
+/* ICP.go_hell_ICP: ICP.cs:18-181 control flow, corrected solve.  max_iters <= 0 means
+ * unbounded like the reference.  use_grid selects the NN routine.  order_last
+ * (nullable, n entries) = correspondences of the last round executed. */
+int vpco_icp_rigid(const double* model_xyz, int64_t m, const double* data_xyz, int64_t n,
+                   double e, int32_t max_iters, double R[9], double T[3], int32_t* iters_done,
+                   double* sse_last, int32_t* order_last, int use_grid, int n_threads);
+
+/* Matrix.ComputeEvJacobi with the commented-out indices (Matrix.cs:621-624, 644, 655-656,
+ * 664-665) restored.  a: n x n row-major symmetric, destroyed; v: eigenvectors in
+ * columns.  Returns 1 on convergence, 0 otherwise (like the C# bool). */
+int vpco_jacobi_eig(double* a, int n, double* eigval, double* v, int max_it, double eps);
+
+/* ICP.TransPoint: ICP.cs:195-219 (planar in/out). */
+int vpco_trans_points(const double* src_xyz, int64_t n, const double R[9], const double T[3],
+                      double* dst_xyz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,124 @@
+"""GPU parity: vpc_dbscan_l1_2d (through the C ABI) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from vtkcloudpoint_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, oracle, mx, my, eps, min_pts, cf0=0, variant="grid"):
+    got = ctx.dbscan(mx, my, eps, min_pts, cf0)
+    cid, key, cls, amount = oracle.dbscan(mx, my, eps, min_pts, cf0, variant=variant)
+    assert got.cluster_amount == amount
+    np.testing.assert_array_equal(got.is_key, key)
+    np.testing.assert_array_equal(got.is_classed, cls)
+    np.testing.assert_array_equal(got.cluster_id, cid)
+    return got
+
+
+def test_c1_literal(ctx, oracle):
+    # config C1: 10k-point cloud written with 3 decimals, eps 0.07, minPts 7 -- against the LITERAL oracle
+    mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000, decimals=3)
+    got = _check(ctx, oracle, mx, my, 0.07, 7, variant="literal")
+    assert got.cluster_amount == 196
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_random_uniform_small(ctx, oracle, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 3000))
+    mx = rng.uniform(0, 2.0, n)
+    my = rng.uniform(0, 2.0, n)
+    _check(ctx, oracle, mx, my, float(rng.uniform(0.02, 0.2)), int(rng.integers(1, 9)), int(rng.integers(0, 50)), variant="literal")
+
+
+def test_quantised_ties(ctx, oracle):
+    # lattice coordinates: many pairs sit exactly on |dx|+|dy| == eps (inclusive '<=')
+    rng = np.random.default_rng(7)
+    n = 4000
+    mx = rng.integers(0, 60, n) * 0.25
+    my = rng.integers(0, 60, n) * 0.25
+    for eps in (0.25, 0.5, 0.75):
+        for min_pts in (2, 4, 6):
+            _check(ctx, oracle, mx, my, eps, min_pts, variant="literal")
+
+
+def test_border_last_writer_wins(ctx, oracle):
+    # two dense groups and a NON-core point within eps of one member of each: it must take the LARGER id (:87)
+    t = np.arange(6) * 0.001
+    a = np.stack([-t, np.zeros(6)], axis=1)            # a[0] = (0, 0)
+    b = np.stack([0.2 + t, np.zeros(6)], axis=1)       # b[0] = (0.2, 0)
+    bridge = np.array([[0.1, 0.0]])
+    pts = np.vstack([a, bridge, b])
+    got = _check(ctx, oracle, pts[:, 0].copy(), pts[:, 1].copy(), 0.1, 6, variant="literal")
+    assert got.cluster_amount == 2
+    assert got.cluster_id[6] == 2 and got.is_key[6] == 0 and got.is_classed[6] == 1
+    # same cloud with the groups swapped in index order: the bridge still takes the larger id
+    pts = np.vstack([b, bridge, a])
+    got = _check(ctx, oracle, pts[:, 0].copy(), pts[:, 1].copy(), 0.1, 6, variant="literal")
+    assert got.cluster_id[6] == 2
+
+
+def test_edge_cases(ctx, oracle):
+    rng = np.random.default_rng(11)
+    mx = rng.uniform(0, 1, 500)
+    my = rng.uniform(0, 1, 500)
+    mx2, my2 = mx.copy(), my.copy()
+    mx2[[3, 77]] = np.nan
+    my2[[5]] = np.inf
+    mx2[[9]] = -np.inf
+    for (x, y) in ((mx, my), (mx2, my2)):
+        for eps, min_pts in ((0.05, 4), (0.05, 1), (0.05, 0), (0.05, -3), (-1.0, 3), (-1.0, 0), (float("nan"), 2), (0.0, 1), (0.0, 2),
+                             (5.0, 3), (1e-300, 1)):
+            _check(ctx, oracle, x, y, eps, min_pts, 7, variant="literal")
+    # duplicates count toward each other's density
+    d = np.repeat(rng.uniform(0, 1, 40), 5)
+    _check(ctx, oracle, d, d[::-1].copy(), 0.0, 5, variant="literal")
+    # n = 0 and n = 1
+    e = np.empty(0)
+    got = ctx.dbscan(e, e, 0.07, 7, 5)
+    assert got.cluster_amount == 5 and got.cluster_id.size == 0
+    _check(ctx, oracle, np.array([1.0]), np.array([2.0]), 0.07, 1, variant="literal")
+    _check(ctx, oracle, np.array([1.0]), np.array([2.0]), 0.07, 2, variant="literal")
+
+
+def test_huge_extent_and_offsets(ctx, oracle):
+    rng = np.random.default_rng(13)
+    n = 2000
+    mx = np.concatenate([rng.normal(0, 0.02, n // 2), rng.normal(1e9, 0.02, n // 2)])
+    my = np.concatenate([rng.normal(-1e12, 0.02, n // 2), rng.normal(5e11, 0.02, n // 2)])
+    _check(ctx, oracle, mx, my, 0.03, 5, variant="literal")
+    mx = rng.normal(0, 1e-3, n) + 1e6
+    my = rng.normal(0, 1e-3, n) - 1e6
+    _check(ctx, oracle, mx, my, 2e-4, 4, variant="literal")
+
+
+def test_eps_inf_rejected(ctx):
+    from vtkcloudpoint_b200 import VpcError
+    with pytest.raises(VpcError):
+        ctx.dbscan(np.zeros(3), np.zeros(3), float("inf"), 2)
+
+
+def test_c2_full_size_vs_grid_oracle(ctx, oracle):
+    # config C2: 1M points; oracle = grid variant (validated against the literal one in the CPU suite)
+    mx, my = synth.dbscan_cloud(0xC2, 140, n_total=1_000_000)
+    got = _check(ctx, oracle, mx, my, 0.07, 7)
+    assert got.cluster_amount >= 19_600
+    # idempotence / permutation property: relabelling is stable under a second run
+    again = ctx.dbscan(mx, my, 0.07, 7)
+    np.testing.assert_array_equal(again.cluster_id, got.cluster_id)
+
+
+def test_device_pointer_entry(ctx, oracle):
+    import torch
+    mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000)
+    tx = torch.from_numpy(mx).cuda()
+    ty = torch.from_numpy(my).cuda()
+    cid, key, cls, amount = ctx.dbscan_dev(tx, ty, 0.07, 7, 3)
+    torch.cuda.synchronize()
+    ocid, okey, ocls, oamount = oracle.dbscan(mx, my, 0.07, 7, 3)
+    assert int(amount.item()) == oamount
+    np.testing.assert_array_equal(cid.cpu().numpy(), ocid)
+    np.testing.assert_array_equal(key.cpu().numpy(), okey)
+    np.testing.assert_array_equal(cls.cpu().numpy(), ocls)

@@ -1,0 +1,56 @@
+"""ctypes binding of the C ABI declared in include/vpc.h.
+
+This is the same boundary the reference's C# would P/Invoke.  Loading
+fails loudly when the CUDA library is missing or cannot be built: there is no CPU
+fallback in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import lru_cache
+
+from . import _build
+
+VPC_OK = 0
+ERRORS = {-1: "VPC_E_BADARG", -2: "VPC_E_CUDA", -3: "VPC_E_NOMEM", -4: "VPC_E_NODEVICE",
+          -5: "VPC_E_TOOBIG", -6: "VPC_E_STATE"}
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_f64 = C.c_double
+
+# name -> (restype, argtypes); every symbol include/vpc.h declares
+SIGNATURES = {
+    "vpc_create": (C.c_int, [C.POINTER(_p), C.POINTER(C.c_int), C.c_int]),
+    "vpc_destroy": (None, [_p]),
+    "vpc_last_error": (C.c_char_p, [_p]),
+    "vpc_version": (C.c_char_p, []),
+    "vpc_launch_count": (_i64, [_p]),
+    "vpc_profile_enable": (C.c_int, [_p, C.c_int]),
+    "vpc_profile_report": (_i64, [_p, C.c_char_p, _i64]),
+    "vpc_dbscan_l1_2d": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p]),
+    "vpc_dbscan_l1_2d_dev": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p, _p]),
+    "vpc_closest_point_set": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p]),
+    "vpc_icp_rigid": (C.c_int, [_p, _p, _i64, _p, _i64, _f64, _i32, _p, _p, _p, _p, _p]),
+    "vpc_icp_set_model_dev": (C.c_int, [_p, _p, _i64, _p]),
+    "vpc_closest_point_set_dev": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
+    "vpc_icp_rigid_dev": (C.c_int, [_p, _p, _i64, _f64, _i32, _p, _p, _p]),
+}
+
+
+class VpcError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {message}")
+        self.code = code
+
+
+@lru_cache(maxsize=None)
+def lib() -> C.CDLL:
+    path = _build.build_lib()          # raises if nvcc is missing or the build fails
+    dll = C.CDLL(str(path))            # raises OSError if the library cannot be loaded
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(dll, name)        # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return dll

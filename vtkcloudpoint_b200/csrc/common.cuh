@@ -1,0 +1,194 @@
+// common.cuh -- shared device helpers for libvpc (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvpc is written for sm_100a (B200) only"
+#endif
+
+namespace vpc {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- order-preserving encoding of doubles for atomicMin/atomicMax -------------------
+__host__ __device__ inline unsigned long long ord_encode(double v) {
+#ifdef __CUDA_ARCH__
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+#else
+  unsigned long long b; memcpy(&b, &v, 8);
+#endif
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double ord_decode(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)b);
+#else
+  double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+
+__device__ __forceinline__ bool finite_d(double v) {
+  // exponent field all ones <=> inf or nan
+  return ((unsigned)(__double2hiint(v) >> 20) & 0x7ffu) != 0x7ffu;
+}
+
+// ---- streaming / cached vector loads --------------------------------------------------
+__device__ __forceinline__ double2 ldg_d2(const double2* p) { return __ldg(p); }
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_s32(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- warp reductions ---------------------------------------------------------------------
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// ---- single-pass exclusive scan (decoupled look-back) -------------------------------------
+// Scans `count` int32 items (count read from *n_ptr when n_ptr != nullptr, else n_static).
+// tile_state: one u64 per tile, zeroed before the launch; tile_counter: one int, zeroed.
+// total_out (nullable) receives the grand total.  in == out is allowed.
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanBlock * kScanItems;  // 4096 items per tile
+
+constexpr unsigned long long kTileAggregate = 1ull << 32;
+constexpr unsigned long long kTilePrefix = 2ull << 32;
+
+__global__ void __launch_bounds__(kScanBlock)
+k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr,
+                 int n_static, unsigned long long* tile_state, int* tile_counter, int* total_out) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[kScanBlock / kWarp];
+  __shared__ int s_excl;
+  const int n = n_ptr ? *n_ptr : n_static;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const long long base = (long long)tile * kScanTile;
+  if (base >= n) {
+    if (n <= 0 && tile == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile; vector loads
+  int v[kScanItems];
+  const long long t0 = base + (long long)threadIdx.x * kScanItems;
+  if (t0 + kScanItems <= n) {
+    const int4* p = reinterpret_cast<const int4*>(in + t0);
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+      int4 q = p[k];
+      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v[k] = (t0 + k < n) ? in[t0 + k] : 0;
+  }
+  int tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) tsum += v[k];
+  // block-wide exclusive scan of thread sums
+  int incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int warp_off = 0, block_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kScanBlock / kWarp; ++w) {
+    int s = s_warp[w];
+    if (w < warp) warp_off += s;
+    block_sum += s;
+  }
+  const int thread_excl = warp_off + incl - tsum;
+
+  // publish aggregate, look back for the exclusive prefix of this tile
+  if (warp == 0) {
+    if (tile == 0) {
+      if (lane == 0) { st_relaxed_u64(&tile_state[0], kTilePrefix | (unsigned)block_sum); s_excl = 0; }
+    } else {
+      if (lane == 0) st_relaxed_u64(&tile_state[tile], kTileAggregate | (unsigned)block_sum);
+      int excl = 0;
+      int look = tile - 1;
+      while (true) {
+        const int idx = look - lane;
+        unsigned long long st;
+        if (idx >= 0) {
+          do { st = ld_relaxed_u64(&tile_state[idx]); } while ((st >> 32) == 0);
+        } else {
+          st = kTilePrefix;  // virtual tile before tile 0: prefix 0
+        }
+        const unsigned mask = __ballot_sync(kFull, (st >> 32) == 2);
+        const int first = mask ? (__ffs(mask) - 1) : 31;
+        excl += warp_sum_i(lane <= first ? (int)(unsigned)st : 0);
+        if (mask) break;
+        look -= 32;
+      }
+      if (lane == 0) { st_relaxed_u64(&tile_state[tile], kTilePrefix | (unsigned)(excl + block_sum)); s_excl = excl; }
+    }
+  }
+  __syncthreads();
+  int run = s_excl + thread_excl;
+  if (total_out && base + kScanTile >= n && threadIdx.x == kScanBlock - 1) *total_out = s_excl + block_sum;
+  if (t0 + kScanItems <= n) {
+    int4* p = reinterpret_cast<int4*>(out + t0);
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+      int4 q;
+      q.x = run; run += v[4 * k];
+      q.y = run; run += v[4 * k + 1];
+      q.z = run; run += v[4 * k + 2];
+      q.w = run; run += v[4 * k + 3];
+      p[k] = q;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (t0 + k < n) out[t0 + k] = run;
+      run += v[k];
+    }
+  }
+}
+
+inline int scan_tiles(long long n) { return (int)((n + kScanTile - 1) / kScanTile); }
+
+}  // namespace vpc

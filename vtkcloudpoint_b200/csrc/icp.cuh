@@ -1,0 +1,440 @@
+// icp.cuh -- ICP nearest-correspondence search + per-iteration rigid solve.
+//
+// Replaces ICP.FindClosestPointSet (vtkPointCloud/BaseClass/ICP.cs:224-250),
+// CalculateMeanPoint3D (:255-273), the cross-covariance / quaternion solve of go_hell_ICP
+// (:35-124, CalculateRotation :274-285, Matrix.ComputeEvJacobi Matrix.cs:571-668), the SSE /
+// convergence / composition logic (:126-180) and TransPoint (:195-219).
+//
+// The model (target) cloud is static across iterations: it is binned once into a uniform
+// 3-D cell list (counting sort) and stored in cell order as 32-byte records
+// {x, y, z, original index}.  One iteration = two launches, no host round trip:
+//   k_icp_iter  : P = R*data + T, exact nearest model point by ring search (ties -> lowest
+//                 original index), per-block partial sums of {P, Y, P Y^T, |P-Y|^2}
+//   k_icp_solve : deterministic reduction of the partials, quaternion eigen solve, compose,
+//                 convergence test; the state lives in device memory.
+#pragma once
+
+#include "common.cuh"
+
+namespace vpc {
+
+struct IcpGridCtrl {
+  unsigned long long lo_k[3], hi_k[3];
+  double o[3], h, inv_h, slack_base;
+  int nc[3];
+  int ncells, ncells_p1;
+  int n_valid;           // finite model points (in the grid)
+  int model0_nan;        // model[0] has a NaN coordinate: every 'd < min' is false (ICP.cs:233,240)
+  unsigned blocks_done;
+  int scan_counter;
+  int valid_count;       // atomic counter during bounds
+};
+
+struct IcpState {
+  double R[9], T[3];
+  double pre_d, d;
+  int round, done, have_rt, converged;
+};
+
+struct IcpModel {
+  const double* xyz;  // planar, original order
+  int m;
+  int cell_cap;
+  IcpGridCtrl* ctrl;
+  int* cellkey;     // [m]
+  int* cell_count;  // [cell_cap+1]
+  int* cell_start;  // [cell_cap+1]
+  double4* spts;    // [m] {x,y,z,bits(idx)} in cell order
+  unsigned long long* tile_state;
+  int tiles;
+};
+
+constexpr int kIcpBlock = 128;
+constexpr int kIcpSums = 16;  // Px Py Pz | Yx Yy Yz | PxYx PxYy PxYz PyYx .. PzYz | sse
+
+__global__ void __launch_bounds__(256) k_icp_model_init(IcpModel g) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i <= g.cell_cap; i += nth) g.cell_count[i] = 0;
+  for (long long i = tid; i < g.tiles; i += nth) g.tile_state[i] = 0;
+  if (tid == 0) {
+    IcpGridCtrl* c = g.ctrl;
+    for (int d = 0; d < 3; ++d) { c->lo_k[d] = ~0ull; c->hi_k[d] = 0ull; }
+    c->blocks_done = 0; c->scan_counter = 0; c->valid_count = 0; c->n_valid = 0;
+    const double x = g.xyz[0], y = g.xyz[g.m], z = g.xyz[2 * (long long)g.m];
+    c->model0_nan = (x != x || y != y || z != z) ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ bool finite3(double x, double y, double z) { return finite_d(x) && finite_d(y) && finite_d(z); }
+
+__global__ void __launch_bounds__(256) k_icp_model_bounds(IcpModel g) {
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int cnt = 0;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.m; i += nth) {
+    const double v[3] = {__ldg(g.xyz + i), __ldg(g.xyz + g.m + i), __ldg(g.xyz + 2ll * g.m + i)};
+    if (finite3(v[0], v[1], v[2])) {
+      ++cnt;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { lo[d] = fmin(lo[d], v[d]); hi[d] = fmax(hi[d], v[d]); }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { lo[d] = warp_min_d(lo[d]); hi[d] = warp_max_d(hi[d]); }
+  cnt = warp_sum_i(cnt);
+  __shared__ bool s_last;
+  IcpGridCtrl* c = g.ctrl;
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { atomicMin(&c->lo_k[d], ord_encode(lo[d])); atomicMax(&c->hi_k[d], ord_encode(hi[d])); }
+    atomicAdd(&c->valid_count, cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&c->blocks_done, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  const int nv = ld_relaxed_s32(&c->valid_count);
+  double h = 1.0, o[3] = {0, 0, 0}, ext[3] = {0, 0, 0};
+  int nc[3] = {1, 1, 1};
+  if (nv > 0) {
+    double vol = 1.0; int nd = 0;
+    for (int d = 0; d < 3; ++d) {
+      o[d] = ord_decode(ld_relaxed_u64(&c->lo_k[d]));
+      ext[d] = fmin(ord_decode(ld_relaxed_u64(&c->hi_k[d])) - o[d], 1e300);
+      if (ext[d] > 0) { vol *= ext[d]; ++nd; }
+    }
+    if (nd > 0) {
+      const double per = vol / fmax(1.0, (double)nv * 0.5);  // about two points per cell
+      h = (nd == 3) ? cbrt(per) : (nd == 2 ? sqrt(per) : per);
+      if (!(h > 0.0) || !finite_d(h)) h = fmax(ext[0], fmax(ext[1], ext[2]));
+      if (!(h > 0.0) || !finite_d(h)) h = 1.0;
+    }
+    const double cap = (double)g.cell_cap;
+    for (int it = 0; it < 200; ++it) {
+      const double inv = 1.0 / h;
+      double f[3], tot = 1.0; bool ok = true;
+      for (int d = 0; d < 3; ++d) { f[d] = floor(ext[d] * inv) + 1.0; tot *= f[d]; ok = ok && f[d] < 2147483000.0; }
+      if (ok && tot <= cap) { for (int d = 0; d < 3; ++d) nc[d] = (int)f[d]; break; }
+      h *= 1.25;
+    }
+  }
+  for (int d = 0; d < 3; ++d) { c->o[d] = o[d]; c->nc[d] = nc[d]; }
+  c->h = h; c->inv_h = 1.0 / h;
+  c->ncells = nc[0] * nc[1] * nc[2]; c->ncells_p1 = c->ncells + 1;
+  c->n_valid = nv;
+  // absolute slack for the ring-search bound: 2^-40 of the largest coordinate magnitude in play
+  const double big = fabs(o[0]) + fabs(o[1]) + fabs(o[2]) + ext[0] + ext[1] + ext[2];
+  c->slack_base = big;
+}
+
+__device__ __forceinline__ int icp_cell1(double v, double o, double inv_h, int nc) {
+  const double q = floor((v - o) * inv_h);
+  if (!(q >= 0.0)) return 0;
+  if (q >= (double)nc) return nc - 1;
+  return (int)q;
+}
+
+__global__ void __launch_bounds__(256) k_icp_model_hist(IcpModel g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.m) return;
+  const IcpGridCtrl c = *g.ctrl;
+  const double x = __ldg(g.xyz + i), y = __ldg(g.xyz + g.m + i), z = __ldg(g.xyz + 2ll * g.m + i);
+  if (!finite3(x, y, z)) { g.cellkey[i] = -1; return; }
+  const int cx = icp_cell1(x, c.o[0], c.inv_h, c.nc[0]);
+  const int cy = icp_cell1(y, c.o[1], c.inv_h, c.nc[1]);
+  const int cz = icp_cell1(z, c.o[2], c.inv_h, c.nc[2]);
+  const int key = (cz * c.nc[1] + cy) * c.nc[0] + cx;
+  g.cellkey[i] = key;
+  atomicAdd(&g.cell_count[key], 1);
+}
+
+__global__ void __launch_bounds__(256) k_icp_model_scatter(IcpModel g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.m) return;
+  const int key = g.cellkey[i];
+  if (key < 0) return;
+  const int pos = g.cell_start[key] + atomicSub(&g.cell_count[key], 1) - 1;
+  double4 r;
+  r.x = __ldg(g.xyz + i); r.y = __ldg(g.xyz + g.m + i); r.z = __ldg(g.xyz + 2ll * g.m + i);
+  r.w = __longlong_as_double((long long)i);
+  g.spts[pos] = r;
+}
+
+// d2 with the association of ICP.cs:233,238: (dx*dx + dy*dy) + dz*dz  (library is built -fmad=false)
+__device__ __forceinline__ double icp_sqd(double ax, double ay, double az, double bx, double by, double bz) {
+  const double dx = ax - bx, dy = ay - by, dz = az - bz;
+  return (dx * dx + dy * dy) + dz * dz;
+}
+
+struct NnBest {
+  double d;
+  int i;
+  double x, y, z;
+};
+
+__device__ __forceinline__ void icp_scan_range(const double4* __restrict__ spts, int j0, int j1, double px, double py,
+                                               double pz, NnBest& b) {
+  for (int j = j0; j < j1; ++j) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(spts + j));
+    const double2 w = __ldg(reinterpret_cast<const double2*>(spts + j) + 1);
+    const double d2 = icp_sqd(px, py, pz, a.x, a.y, w.x);
+    const int i = (int)__double_as_longlong(w.y);
+    if (d2 < b.d || (d2 == b.d && i < b.i)) { b.d = d2; b.i = i; b.x = a.x; b.y = a.y; b.z = w.x; }
+  }
+}
+
+// Exact argmin_j d2(p, model[j]) with ties to the lowest j (ICP.cs:229-248) for a finite p over the
+// finite model points.  Rings of cells are searched outward until nothing outside the searched box can
+// be closer than, or as close as, the best so far.
+__device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl& c, double px, double py, double pz,
+                                            NnBest& b) {
+  b.d = INFINITY; b.i = 0x7fffffff; b.x = b.y = b.z = 0.0;
+  const double p[3] = {px, py, pz};
+  int cc[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) cc[d] = icp_cell1(p[d], c.o[d], c.inv_h, c.nc[d]);
+  const int rmax = max(c.nc[0], max(c.nc[1], c.nc[2]));
+  const double slack = ldexp(c.slack_base + fabs(px) + fabs(py) + fabs(pz), -40);
+  for (int r = 1; r <= rmax; ++r) {
+    int lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { lo[d] = max(cc[d] - r, 0); hi[d] = min(cc[d] + r, c.nc[d] - 1); }
+    for (int z = lo[2]; z <= hi[2]; ++z) {
+      for (int y = lo[1]; y <= hi[1]; ++y) {
+        const int row = (z * c.nc[1] + y) * c.nc[0];
+        const bool shell_row = (r == 1) || (abs(z - cc[2]) == r) || (abs(y - cc[1]) == r);
+        if (shell_row) {
+          icp_scan_range(g.spts, __ldg(g.cell_start + row + lo[0]), __ldg(g.cell_start + row + hi[0] + 1), px, py, pz, b);
+        } else {
+          if (cc[0] - r >= 0) icp_scan_range(g.spts, __ldg(g.cell_start + row + cc[0] - r), __ldg(g.cell_start + row + cc[0] - r + 1), px, py, pz, b);
+          if (cc[0] + r <= c.nc[0] - 1) icp_scan_range(g.spts, __ldg(g.cell_start + row + cc[0] + r), __ldg(g.cell_start + row + cc[0] + r + 1), px, py, pz, b);
+        }
+      }
+    }
+    bool all = true;
+    double lb = INFINITY;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (cc[d] - r > 0) { all = false; lb = fmin(lb, p[d] - (c.o[d] + (double)(cc[d] - r) * c.h)); }
+      if (cc[d] + r < c.nc[d] - 1) { all = false; lb = fmin(lb, (c.o[d] + (double)(cc[d] + r + 1) * c.h) - p[d]); }
+    }
+    if (all) break;
+    const double lbs = lb - slack;
+    if (b.i != 0x7fffffff && lbs > 0.0 && b.d < lbs * lbs * (1.0 - 9.094947017729282e-13)) break;
+  }
+}
+
+// Full reference semantics for one data point, including the non-finite corner cases of the
+// literal scan (min starts at d(i,0); 'd < min' is false for NaN).
+__device__ __forceinline__ void icp_match(const IcpModel& g, const IcpGridCtrl& c, double px, double py, double pz,
+                                          NnBest& b) {
+  bool searched = false;
+  if (!c.model0_nan && c.n_valid > 0 && finite3(px, py, pz)) {
+    icp_nearest(g, c, px, py, pz, b);
+    searched = (b.i != 0x7fffffff);
+  }
+  if (!searched) {
+    b.x = g.xyz[0]; b.y = g.xyz[g.m]; b.z = g.xyz[2ll * g.m];
+    b.i = 0; b.d = icp_sqd(px, py, pz, b.x, b.y, b.z);
+  }
+}
+
+// ---- standalone FindClosestPointSet ---------------------------------------------------------
+__global__ void __launch_bounds__(kIcpBlock)
+k_icp_closest(IcpModel g, const double* __restrict__ data, int n, int* __restrict__ order, double* __restrict__ sqdist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const IcpGridCtrl c = *g.ctrl;
+  NnBest b;
+  icp_match(g, c, __ldg(data + i), __ldg(data + n + i), __ldg(data + 2ll * n + i), b);
+  order[i] = b.i;
+  if (sqdist) sqdist[i] = b.d;
+}
+
+// ---- one ICP round, part 1: transform + correspondences + partial sums ----------------------
+__global__ void __launch_bounds__(kIcpBlock)
+k_icp_iter(IcpModel g, const double* __restrict__ data, int n, const IcpState* __restrict__ st, int* __restrict__ order,
+           double* __restrict__ partial) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s[kIcpSums];
+#pragma unroll
+  for (int k = 0; k < kIcpSums; ++k) s[k] = 0.0;
+  if (i < n) {
+    const IcpGridCtrl c = *g.ctrl;
+    double px = __ldg(data + i), py = __ldg(data + n + i), pz = __ldg(data + 2ll * n + i);
+    if (st->have_rt) {
+      // TransPoint, ICP.cs:195-219: r = R*p accumulated from 0.0 in k order (Matrix.cs:500-510), then + T
+      const double x = px, y = py, z = pz;
+      px = (((0.0 + st->R[0] * x) + st->R[1] * y) + st->R[2] * z) + st->T[0];
+      py = (((0.0 + st->R[3] * x) + st->R[4] * y) + st->R[5] * z) + st->T[1];
+      pz = (((0.0 + st->R[6] * x) + st->R[7] * y) + st->R[8] * z) + st->T[2];
+    }
+    NnBest b;
+    icp_match(g, c, px, py, pz, b);
+    order[i] = b.i;
+    s[0] = px; s[1] = py; s[2] = pz;
+    s[3] = b.x; s[4] = b.y; s[5] = b.z;
+    s[6] = px * b.x; s[7] = px * b.y; s[8] = px * b.z;
+    s[9] = py * b.x; s[10] = py * b.y; s[11] = py * b.z;
+    s[12] = pz * b.x; s[13] = pz * b.y; s[14] = pz * b.z;
+    const double ex = px - b.x, ey = py - b.y, ez = pz - b.z;
+    s[15] = ex * ex + ey * ey + ez * ez;  // ICP.cs:131
+  }
+  __shared__ double sm[kIcpBlock / kWarp][kIcpSums];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kIcpSums; ++k) {
+    const double v = warp_sum_d(s[k]);
+    if (lane == 0) sm[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kIcpSums) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kIcpBlock / kWarp; ++w) v += sm[w][threadIdx.x];
+    partial[(long long)blockIdx.x * kIcpSums + threadIdx.x] = v;
+  }
+}
+
+// Classical Jacobi for a symmetric 4x4 (the job of Matrix.ComputeEvJacobi, Matrix.cs:571-668):
+// zero the largest off-diagonal element until all are below eps.  v: eigenvectors in columns.
+__device__ inline void jacobi4(double a[4][4], double v[4][4], double eps, int max_it) {
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int it = 0; it < max_it; ++it) {
+    int p = 1, q = 0; double fm = 0.0;
+    for (int i = 1; i < 4; ++i) for (int j = 0; j < i; ++j) { const double d = fabs(a[i][j]); if (d > fm) { fm = d; p = i; q = j; } }
+    if (fm < eps) return;
+    const double x = -a[p][q], y = (a[q][q] - a[p][p]) / 2.0;
+    double omega = x / sqrt(x * x + y * y);
+    if (y < 0.0) omega = -omega;
+    double sn = 1.0 + sqrt(1.0 - omega * omega);
+    sn = omega / sqrt(2.0 * sn);
+    const double cn = sqrt(1.0 - sn * sn);
+    const double app = a[p][p], aqq = a[q][q], apq = a[p][q];
+    a[p][p] = app * cn * cn + aqq * sn * sn + apq * omega;
+    a[q][q] = app * sn * sn + aqq * cn * cn - apq * omega;
+    a[p][q] = 0.0; a[q][p] = 0.0;
+    for (int j = 0; j < 4; ++j) if (j != p && j != q) {
+      const double f = a[p][j];
+      a[p][j] = f * cn + a[q][j] * sn;
+      a[q][j] = -f * sn + a[q][j] * cn;
+    }
+    for (int i = 0; i < 4; ++i) if (i != p && i != q) {
+      const double f = a[i][p];
+      a[i][p] = f * cn + a[i][q] * sn;
+      a[i][q] = -f * sn + a[i][q] * cn;
+    }
+    for (int i = 0; i < 4; ++i) {
+      const double f = v[i][p];
+      v[i][p] = f * cn + v[i][q] * sn;
+      v[i][q] = -f * sn + v[i][q] * cn;
+    }
+  }
+}
+
+// ---- one ICP round, part 2: reduce, solve, compose, test ------------------------------------
+constexpr int kSolveBlock = 256;
+__global__ void __launch_bounds__(kSolveBlock)
+k_icp_solve(const double* __restrict__ partial, int n_blocks, int n, double e, int max_iters, IcpState* st) {
+  if (st->done) return;
+  __shared__ double sm[kIcpSums][kSolveBlock / kIcpSums + 1];
+  __shared__ double S[kIcpSums];
+  const int q = threadIdx.x % kIcpSums, slice = threadIdx.x / kIcpSums;
+  constexpr int kSlices = kSolveBlock / kIcpSums;
+  double acc = 0.0;
+  for (int b = slice; b < n_blocks; b += kSlices) acc += partial[(long long)b * kIcpSums + q];
+  sm[q][slice] = acc;
+  __syncthreads();
+  if (threadIdx.x < kIcpSums) {
+    double v = 0.0;
+    for (int k = 0; k < kSlices; ++k) v += sm[threadIdx.x][k];
+    S[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+
+  const double N = (double)n;
+  double mp[3], my[3];
+  for (int d = 0; d < 3; ++d) { mp[d] = S[d] / N; my[d] = S[3 + d] / N; }      // ICP.cs:255-273
+  const double inv_n = 1.0 / N;
+  double m[3][3], mT[3][3], A[3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) m[a][b] = S[6 + a * 3 + b] * inv_n - mp[a] * my[b];  // intended :53, :66
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) mT[b][a] = m[a][b];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) A[a][b] = m[a][b] - mT[a][b];  // :71-72
+  const double delta[3] = {A[1][2], A[2][0], A[0][1]};                             // intended :74-76
+  const double tr = (m[0][0] + m[1][1]) + m[2][2];                                   // :78
+  double Q[4][4], V[4][4];
+  Q[0][0] = tr;                                                                      // :88-104
+  for (int k = 0; k < 3; ++k) { Q[0][k + 1] = delta[k]; Q[k + 1][0] = delta[k]; }
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) Q[a + 1][b + 1] = (m[a][b] + mT[a][b]) - (a == b ? tr : 0.0);
+  double fro = 0.0;
+  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) fro += Q[a][b] * Q[a][b];
+  jacobi4(Q, V, fmax(sqrt(fro) * 1e-16, 2.2250738585072014e-308), 100);
+  int best = 0;
+  for (int k = 1; k < 4; ++k) if (Q[k][k] > Q[best][best]) best = k;                  // eigenvector of the largest eigenvalue
+  double qv[4] = {V[0][best], V[1][best], V[2][best], V[3][best]};
+  const double nq = sqrt(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2] + qv[3] * qv[3]);
+  if (nq > 0.0) for (int k = 0; k < 4; ++k) qv[k] = qv[k] / nq;
+  if (qv[0] < 0.0) for (int k = 0; k < 4; ++k) qv[k] = -qv[k];
+  double R1[9];                                                                       // ICP.cs:274-285
+  R1[0] = qv[0] * qv[0] + qv[1] * qv[1] - qv[2] * qv[2] - qv[3] * qv[3];
+  R1[1] = 2.0 * (qv[1] * qv[2] - qv[0] * qv[3]);
+  R1[2] = 2.0 * (qv[1] * qv[3] + qv[0] * qv[2]);
+  R1[3] = 2.0 * (qv[1] * qv[2] + qv[0] * qv[3]);
+  R1[4] = qv[0] * qv[0] - qv[1] * qv[1] + qv[2] * qv[2] - qv[3] * qv[3];
+  R1[5] = 2.0 * (qv[2] * qv[3] - qv[0] * qv[1]);
+  R1[6] = 2.0 * (qv[1] * qv[3] - qv[0] * qv[2]);
+  R1[7] = 2.0 * (qv[2] * qv[3] + qv[0] * qv[1]);
+  R1[8] = qv[0] * qv[0] - qv[1] * qv[1] - qv[2] * qv[2] + qv[3] * qv[3];
+  double T1[3];                                                                       // :114-124
+  for (int i = 0; i < 3; ++i) T1[i] = my[i] - (((0.0 + R1[i * 3] * mp[0]) + R1[i * 3 + 1] * mp[1]) + R1[i * 3 + 2] * mp[2]);
+
+  const double d = S[15];                                                             // :126-133
+  const double pre_d = st->d;                                                         // :25
+  st->pre_d = pre_d; st->d = d;
+  const int round = st->round + 1;                                                    // :134
+  st->round = round;
+  const bool go_on = fabs(d - pre_d) >= e;                                            // :149, :180
+  if (go_on) {
+    if (round == 1) {                                                                 // :151-162
+      for (int k = 0; k < 9; ++k) st->R[k] = R1[k];
+      for (int k = 0; k < 3; ++k) st->T[k] = T1[k];
+    } else {                                                                          // :163-177: R <- R1*R, T <- R1*T + T1
+      double tR[9], tT[3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) tR[i * 3 + j] = ((0.0 + R1[i * 3] * st->R[j]) + R1[i * 3 + 1] * st->R[3 + j]) + R1[i * 3 + 2] * st->R[6 + j];
+      for (int i = 0; i < 3; ++i) tT[i] = ((0.0 + R1[i * 3] * st->T[0]) + R1[i * 3 + 1] * st->T[1]) + R1[i * 3 + 2] * st->T[2];
+      for (int k = 0; k < 9; ++k) st->R[k] = tR[k];
+      for (int k = 0; k < 3; ++k) st->T[k] = tT[k] + T1[k];
+    }
+    st->have_rt = 1;                                                                  // :178 P = TransPoint(data, R, T)
+  } else {
+    st->converged = 1;
+  }
+  if (!go_on || (max_iters > 0 && round >= max_iters)) st->done = 1;
+}
+
+__global__ void k_icp_state_init(IcpState* st, const double* R0, const double* T0) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < 9; ++k) st->R[k] = R0 ? R0[k] : 0.0;
+  for (int k = 0; k < 3; ++k) st->T[k] = T0 ? T0[k] : 0.0;
+  st->pre_d = 0.0; st->d = 0.0; st->round = 0; st->done = 0; st->have_rt = 0; st->converged = 0;
+}
+
+// state -> 16 doubles for the caller: R[9] T[3] sse iters converged 0
+__global__ void k_icp_state_export(const IcpState* st, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < 9; ++k) out[k] = st->R[k];
+  for (int k = 0; k < 3; ++k) out[9 + k] = st->T[k];
+  out[12] = st->d; out[13] = (double)st->round; out[14] = (double)st->converged; out[15] = 0.0;
+}
+
+}  // namespace vpc

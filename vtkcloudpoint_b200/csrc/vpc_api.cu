@@ -1,0 +1,484 @@
+// vpc_api.cu -- C ABI of libvpc.so (see include/vpc.h).  Host-side orchestration only; the
+// arithmetic lives in dbscan.cuh / icp.cuh.  There is no CPU fallback anywhere in this file.
+
+#include "../../include/vpc.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "dbscan.cuh"
+#include "icp.cuh"
+
+using namespace vpc;
+
+namespace {
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+  void reset() { off = 0; }
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+inline size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
+
+}  // namespace
+
+struct vpc_ctx {
+  int device = 0;
+  std::mutex mu;
+  std::string err;
+  int64_t launches = 0;
+  cudaStream_t own_stream = nullptr;
+  Arena db;        // DBSCAN workspace
+  Arena io;        // device copies of host inputs / outputs (host-pointer entry points)
+  Arena icp_model; // model cell list (persists between calls)
+  Arena icp_work;  // per-call ICP workspace
+  // ICP model state
+  IcpModel model{};
+  bool model_set = false;
+  IcpState* icp_state = nullptr;
+  double* icp_partial = nullptr;
+  int icp_partial_blocks = 0;
+  int sm_count = 148;
+  // optional per-kernel CUDA-event timing (bench.py's roofline leg)
+  bool profile = false;
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+};
+
+namespace {
+
+#define VPC_CUDA(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                       \
+      return (_e == cudaErrorMemoryAllocation) ? VPC_E_NOMEM : VPC_E_CUDA;                   \
+    }                                                                                        \
+  } while (0)
+
+#define VPC_LAUNCH(ctx, kernel, grid, block, stream, ...)                                    \
+  do {                                                                                       \
+    cudaEvent_t _ea = nullptr, _eb = nullptr;                                                \
+    if ((ctx)->profile) {                                                                    \
+      cudaEventCreate(&_ea); cudaEventCreate(&_eb); cudaEventRecord(_ea, (stream));          \
+    }                                                                                        \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                   \
+    if ((ctx)->profile) {                                                                    \
+      cudaEventRecord(_eb, (stream)); (ctx)->prof.push_back({#kernel, _ea, _eb});            \
+    }                                                                                        \
+    (ctx)->launches++;                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#kernel) + ": " + cudaGetErrorString(_e);                     \
+      return VPC_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+int fail(vpc_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+// Grow-only device arena.  Growing synchronises the device (old buffer may be in flight).
+int arena_reserve(vpc_ctx* ctx, Arena& a, size_t bytes) {
+  a.reset();
+  if (bytes <= a.cap) return VPC_OK;
+  VPC_CUDA(ctx, cudaDeviceSynchronize());
+  if (a.base) VPC_CUDA(ctx, cudaFree(a.base));
+  a.base = nullptr; a.cap = 0;
+  size_t want = bytes + bytes / 8 + (1u << 20);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ctx->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+    return VPC_E_NOMEM;
+  }
+  a.base = static_cast<char*>(p); a.cap = want;
+  return VPC_OK;
+}
+
+inline int blocks_for(long long n, int block) { return (int)std::max<long long>(1, (n + block - 1) / block); }
+
+// ---------------------------------------------------------------------------------------
+// DBSCAN
+// ---------------------------------------------------------------------------------------
+int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, double eps, int32_t min_pts,
+                   int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
+                   int32_t* d_cluster_amount, cudaStream_t s) {
+  const int ni = (int)n;
+  const long long cap_ll = std::min<long long>(2ll * n + 1024, 2147483000ll);
+  const int cell_cap = (int)cap_ll;
+  const int tiles0 = scan_tiles((long long)cell_cap + 1), tiles1 = scan_tiles(std::max<long long>(n, 1));
+  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * 6 + al256(4ull * (cell_cap + 1ull)) * 2 + al256(16ull * n) +
+                 al256((size_t)n) + al256(8ull * tiles0) + al256(8ull * tiles1) + 4096;
+  int rc = arena_reserve(ctx, ctx->db, bytes);
+  if (rc) return rc;
+  Arena& w = ctx->db;
+  DbArgs a{};
+  a.x = d_x; a.y = d_y; a.n = ni; a.eps = eps; a.min_pts = min_pts; a.first_cluster_id = first_cluster_id;
+  a.cell_cap = cell_cap;
+  a.ctrl = w.take<DbCtrl>(1);
+  a.cellkey = w.take<int>(n);
+  a.cell_count = w.take<int>(cell_cap + 1ull);
+  a.cell_start = w.take<int>(cell_cap + 1ull);
+  a.sxy = w.take<double2>(n);
+  a.sidx = w.take<int>(n);
+  a.core = w.take<unsigned char>(n);
+  a.parent = w.take<int>(n);
+  a.compkey = w.take<int>(n);
+  a.flag = w.take<int>(n);
+  a.rank = w.take<int>(n);
+  a.tile_state0 = w.take<unsigned long long>(tiles0);
+  a.tile_state1 = w.take<unsigned long long>(tiles1);
+  a.tiles0 = tiles0; a.tiles1 = tiles1;
+  a.cluster_id = d_cluster_id; a.is_key = d_is_key; a.is_classed = d_is_classed; a.cluster_amount = d_cluster_amount;
+
+  const int gpts = blocks_for(n, kDbBlock);
+  const int gstride = std::min(gpts, ctx->sm_count * 8);
+  VPC_LAUNCH(ctx, k_db_init, std::min(blocks_for((long long)cell_cap + 1, kDbBlock), ctx->sm_count * 16), kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_db_bounds, gstride, kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_db_hist, gpts, kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_scan_exclusive, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0,
+             a.tile_state0, &a.ctrl->scan_counter[0], &a.ctrl->n_valid);
+  VPC_LAUNCH(ctx, k_db_scatter, gpts, kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_db_count, gpts, kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_db_union, gpts, kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_scan_exclusive, tiles1, kScanBlock, s, a.flag, a.rank, (const int*)nullptr, ni, a.tile_state1,
+             &a.ctrl->scan_counter[1], &a.ctrl->n_roots);
+  VPC_LAUNCH(ctx, k_db_label, gpts, kDbBlock, s, a);
+  return VPC_OK;
+}
+
+int dbscan_check(vpc_ctx* ctx, const void* mx, const void* my, int64_t n, double eps, const void* cid, const void* key,
+                 const void* cls) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0) return fail(ctx, VPC_E_BADARG, "n < 0");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2 points per call");
+  if (n > 0 && (!mx || !my || !cid || !key || !cls)) return fail(ctx, VPC_E_BADARG, "null array with n > 0");
+  if (std::isinf(eps) && eps > 0) return fail(ctx, VPC_E_BADARG, "eps = +inf is not supported");
+  return VPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// ICP
+// ---------------------------------------------------------------------------------------
+int icp_set_model(vpc_ctx* ctx, const double* d_model, int64_t m, cudaStream_t s) {
+  const long long cap_ll = std::min<long long>(2ll * m + 1024, 2147483000ll);
+  const int cell_cap = (int)cap_ll;
+  const int tiles = scan_tiles((long long)cell_cap + 1);
+  size_t bytes = al256(sizeof(IcpGridCtrl)) + al256(4ull * m) + al256(4ull * (cell_cap + 1ull)) * 2 + al256(32ull * m) +
+                 al256(8ull * tiles) + al256(sizeof(IcpState)) + 4096;
+  ctx->model_set = false;
+  int rc = arena_reserve(ctx, ctx->icp_model, bytes);
+  if (rc) return rc;
+  Arena& w = ctx->icp_model;
+  IcpModel g{};
+  g.xyz = d_model; g.m = (int)m; g.cell_cap = cell_cap;
+  g.ctrl = w.take<IcpGridCtrl>(1);
+  g.cellkey = w.take<int>(m);
+  g.cell_count = w.take<int>(cell_cap + 1ull);
+  g.cell_start = w.take<int>(cell_cap + 1ull);
+  g.spts = w.take<double4>(m);
+  g.tile_state = w.take<unsigned long long>(tiles);
+  g.tiles = tiles;
+  ctx->icp_state = w.take<IcpState>(1);
+  const int gpts = blocks_for(m, 256);
+  VPC_LAUNCH(ctx, k_icp_model_init, std::min(blocks_for((long long)cell_cap + 1, 256), ctx->sm_count * 16), 256, s, g);
+  VPC_LAUNCH(ctx, k_icp_model_bounds, std::min(gpts, ctx->sm_count * 8), 256, s, g);
+  VPC_LAUNCH(ctx, k_icp_model_hist, gpts, 256, s, g);
+  VPC_LAUNCH(ctx, k_scan_exclusive, tiles, kScanBlock, s, g.cell_count, g.cell_start, &g.ctrl->ncells_p1, 0, g.tile_state,
+             &g.ctrl->scan_counter, (int*)nullptr);
+  VPC_LAUNCH(ctx, k_icp_model_scatter, gpts, 256, s, g);
+  ctx->model = g;
+  ctx->model_set = true;
+  return VPC_OK;
+}
+
+int icp_reserve_work(vpc_ctx* ctx, int64_t n) {
+  const int nb = blocks_for(n, kIcpBlock);
+  int rc = arena_reserve(ctx, ctx->icp_work, al256(8ull * kIcpSums * nb) + al256(12 * 8) + 1024);
+  if (rc) return rc;
+  ctx->icp_partial = ctx->icp_work.take<double>((size_t)kIcpSums * nb);
+  ctx->icp_partial_blocks = nb;
+  return VPC_OK;
+}
+
+// enqueue `rounds` ICP rounds (each a no-op once the state says done)
+int icp_enqueue_rounds(vpc_ctx* ctx, const double* d_data, int64_t n, double e, int32_t max_iters, int rounds,
+                       int32_t* d_order, cudaStream_t s) {
+  const int nb = ctx->icp_partial_blocks;
+  for (int r = 0; r < rounds; ++r) {
+    VPC_LAUNCH(ctx, k_icp_iter, nb, kIcpBlock, s, ctx->model, d_data, (int)n, ctx->icp_state, d_order, ctx->icp_partial);
+    VPC_LAUNCH(ctx, k_icp_solve, 1, kSolveBlock, s, ctx->icp_partial, nb, (int)n, e, max_iters, ctx->icp_state);
+  }
+  return VPC_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* vpc_version(void) { return "vpc-b200 0.1 (sm_100a)"; }
+
+int vpc_create(vpc_ctx** out, const int* device_ids, int n_devices) {
+  if (!out) return VPC_E_BADARG;
+  *out = nullptr;
+  if (n_devices < 0 || n_devices > 1) return VPC_E_BADARG;  // single-process multi-GPU: reserved
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) { (void)cudaGetLastError(); return VPC_E_NODEVICE; }
+  const int dev = (device_ids && n_devices > 0) ? device_ids[0] : 0;
+  if (dev < 0 || dev >= count) return VPC_E_BADARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return VPC_E_CUDA;
+  if (prop.major < 10) return VPC_E_NODEVICE;  // kernels are sm_100a only
+  vpc_ctx* ctx = new (std::nothrow) vpc_ctx();
+  if (!ctx) return VPC_E_NOMEM;
+  ctx->device = dev;
+  ctx->sm_count = prop.multiProcessorCount;
+  DeviceGuard g(dev);
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VPC_E_CUDA; }
+  *out = ctx;
+  return VPC_OK;
+}
+
+void vpc_destroy(vpc_ctx* ctx) {
+  if (!ctx) return;
+  {
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (Arena* a : {&ctx->db, &ctx->io, &ctx->icp_model, &ctx->icp_work})
+      if (a->base) cudaFree(a->base);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  }
+  delete ctx;
+}
+
+const char* vpc_last_error(const vpc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t vpc_launch_count(const vpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vpc_profile_enable(vpc_ctx* ctx, int on) {
+  if (!ctx) return VPC_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->profile = (on != 0);
+  return VPC_OK;
+}
+
+int64_t vpc_profile_report(vpc_ctx* ctx, char* buf, int64_t cap) {
+  if (!ctx || !buf || cap <= 0) return VPC_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  std::string out;
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    char line[160];
+    snprintf(line, sizeof line, "%s %.6f\n", r.name, (double)ms);
+    out += line;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  const int64_t nbytes = std::min<int64_t>((int64_t)out.size(), cap - 1);
+  std::memcpy(buf, out.data(), (size_t)nbytes);
+  buf[nbytes] = 0;
+  return nbytes;
+}
+
+int vpc_dbscan_l1_2d_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, int64_t n, double eps, int32_t min_pts,
+                         int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
+                         int32_t* d_cluster_amount, void* stream) {
+  int rc = dbscan_check(ctx, d_mx, d_my, n, eps, d_cluster_id, d_is_key, d_is_classed);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return dbscan_enqueue(ctx, d_mx, d_my, n, eps, min_pts, first_cluster_id, d_cluster_id, d_is_key, d_is_classed,
+                        d_cluster_amount, static_cast<cudaStream_t>(stream));
+}
+
+int vpc_dbscan_l1_2d(vpc_ctx* ctx, const double* mx, const double* my, int64_t n, double eps, int32_t min_pts,
+                     int32_t first_cluster_id, int32_t* cluster_id, uint8_t* is_key, uint8_t* is_classed,
+                     int32_t* cluster_amount) {
+  int rc = dbscan_check(ctx, mx, my, n, eps, cluster_id, is_key, is_classed);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  if (n == 0) {  // DBImproved.cs:93 loop does not run; clusterAmount = cf (:112)
+    if (cluster_amount) *cluster_amount = first_cluster_id;
+    return VPC_OK;
+  }
+  cudaStream_t s = ctx->own_stream;
+  rc = arena_reserve(ctx, ctx->io, al256(8ull * n) * 2 + al256(4ull * n) + al256((size_t)n) * 2 + 1024);
+  if (rc) return rc;
+  double* d_x = ctx->io.take<double>(n);
+  double* d_y = ctx->io.take<double>(n);
+  int* d_cid = ctx->io.take<int>(n);
+  unsigned char* d_key = ctx->io.take<unsigned char>(n);
+  unsigned char* d_cls = ctx->io.take<unsigned char>(n);
+  int* d_amount = ctx->io.take<int>(1);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_x, mx, 8ull * n, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_y, my, 8ull * n, cudaMemcpyHostToDevice, s));
+  rc = dbscan_enqueue(ctx, d_x, d_y, n, eps, min_pts, first_cluster_id, d_cid, d_key, d_cls, d_amount, s);
+  if (rc) return rc;
+  int amount = 0;
+  VPC_CUDA(ctx, cudaMemcpyAsync(cluster_id, d_cid, 4ull * n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(is_key, d_key, (size_t)n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(is_classed, d_cls, (size_t)n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(&amount, d_amount, 4, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  if (cluster_amount) *cluster_amount = amount;
+  return VPC_OK;
+}
+
+int vpc_icp_set_model_dev(vpc_ctx* ctx, const double* d_model_xyz, int64_t m, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (m <= 0 || !d_model_xyz) return fail(ctx, VPC_E_BADARG, "model must have at least one point (ICP.cs:233 reads model[0])");
+  if (m > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "m exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return icp_set_model(ctx, d_model_xyz, m, static_cast<cudaStream_t>(stream));
+}
+
+int vpc_closest_point_set_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, int32_t* d_order, double* d_sqdist,
+                              void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || (n > 0 && (!d_data_xyz || !d_order))) return fail(ctx, VPC_E_BADARG, "bad data/order");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->model_set) return fail(ctx, VPC_E_STATE, "vpc_icp_set_model_dev has not been called");
+  if (n == 0) return VPC_OK;
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_icp_closest, blocks_for(n, kIcpBlock), kIcpBlock, static_cast<cudaStream_t>(stream), ctx->model,
+             d_data_xyz, (int)n, d_order, d_sqdist);
+  return VPC_OK;
+}
+
+int vpc_icp_rigid_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, double e, int32_t max_iters, double* d_state_out,
+                      int32_t* d_order_last, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n <= 0 || !d_data_xyz || !d_state_out || !d_order_last) return fail(ctx, VPC_E_BADARG, "bad data/state/order");
+  if (max_iters <= 0) return fail(ctx, VPC_E_BADARG, "vpc_icp_rigid_dev needs max_iters > 0");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->model_set) return fail(ctx, VPC_E_STATE, "vpc_icp_set_model_dev has not been called");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = icp_reserve_work(ctx, n);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_icp_state_init, 1, 32, s, ctx->icp_state, (const double*)nullptr, (const double*)nullptr);
+  rc = icp_enqueue_rounds(ctx, d_data_xyz, n, e, max_iters, max_iters, d_order_last, s);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_icp_state_export, 1, 32, s, ctx->icp_state, d_state_out);
+  return VPC_OK;
+}
+
+int vpc_closest_point_set(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double* data_xyz, int64_t n,
+                          int32_t* order, double* sqdist) {
+  if (!ctx) return VPC_E_BADARG;
+  if (m <= 0 || !model_xyz) return fail(ctx, VPC_E_BADARG, "model must have at least one point (ICP.cs:233 reads model[0])");
+  if (n < 0 || (n > 0 && (!data_xyz || !order))) return fail(ctx, VPC_E_BADARG, "bad data/order");
+  if (m > 2147483646ll || n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "size exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n == 0) return VPC_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->own_stream;
+  int rc = arena_reserve(ctx, ctx->io, al256(24ull * m) + al256(24ull * n) + al256(4ull * n) + al256(8ull * n) + 1024);
+  if (rc) return rc;
+  double* d_model = ctx->io.take<double>(3 * m);
+  double* d_data = ctx->io.take<double>(3 * n);
+  int* d_order = ctx->io.take<int>(n);
+  double* d_sq = ctx->io.take<double>(n);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_model, model_xyz, 24ull * m, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_data, data_xyz, 24ull * n, cudaMemcpyHostToDevice, s));
+  rc = icp_set_model(ctx, d_model, m, s);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_icp_closest, blocks_for(n, kIcpBlock), kIcpBlock, s, ctx->model, d_data, (int)n, d_order,
+             sqdist ? d_sq : (double*)nullptr);
+  VPC_CUDA(ctx, cudaMemcpyAsync(order, d_order, 4ull * n, cudaMemcpyDeviceToHost, s));
+  if (sqdist) VPC_CUDA(ctx, cudaMemcpyAsync(sqdist, d_sq, 8ull * n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->model_set = false;  // the model copy lives in the io arena of this call only
+  return VPC_OK;
+}
+
+int vpc_icp_rigid(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double* data_xyz, int64_t n, double e,
+                  int32_t max_iters, double R[9], double T[3], int32_t* iters_done, double* sse_last, int32_t* order_last) {
+  if (!ctx) return VPC_E_BADARG;
+  if (m <= 0 || !model_xyz) return fail(ctx, VPC_E_BADARG, "model must have at least one point (ICP.cs:233 reads model[0])");
+  if (n <= 0 || !data_xyz || !R || !T) return fail(ctx, VPC_E_BADARG, "bad data/R/T");
+  if (m > 2147483646ll || n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "size exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->own_stream;
+  int rc = arena_reserve(ctx, ctx->io, al256(24ull * m) + al256(24ull * n) + al256(4ull * n) + al256(16 * 8) * 2 + 1024);
+  if (rc) return rc;
+  double* d_model = ctx->io.take<double>(3 * m);
+  double* d_data = ctx->io.take<double>(3 * n);
+  int* d_order = ctx->io.take<int>(n);
+  double* d_rt = ctx->io.take<double>(16);
+  double* d_out = ctx->io.take<double>(16);
+  double rt[12];
+  std::memcpy(rt, R, 72); std::memcpy(rt + 9, T, 24);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_model, model_xyz, 24ull * m, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_data, data_xyz, 24ull * n, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_rt, rt, 96, cudaMemcpyHostToDevice, s));
+  rc = icp_set_model(ctx, d_model, m, s);
+  if (rc) return rc;
+  rc = icp_reserve_work(ctx, n);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_icp_state_init, 1, 32, s, ctx->icp_state, (const double*)d_rt, (const double*)(d_rt + 9));
+  double out[16];
+  if (max_iters > 0) {
+    rc = icp_enqueue_rounds(ctx, d_data, n, e, max_iters, max_iters, d_order, s);
+    if (rc) return rc;
+    VPC_LAUNCH(ctx, k_icp_state_export, 1, 32, s, ctx->icp_state, d_out);
+    VPC_CUDA(ctx, cudaMemcpyAsync(out, d_out, 128, cudaMemcpyDeviceToHost, s));
+    VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  } else {
+    // unbounded like the reference (ICP.cs:180): enqueue batches of rounds until the state converges
+    for (;;) {
+      rc = icp_enqueue_rounds(ctx, d_data, n, e, 0, 16, d_order, s);
+      if (rc) return rc;
+      VPC_LAUNCH(ctx, k_icp_state_export, 1, 32, s, ctx->icp_state, d_out);
+      VPC_CUDA(ctx, cudaMemcpyAsync(out, d_out, 128, cudaMemcpyDeviceToHost, s));
+      VPC_CUDA(ctx, cudaStreamSynchronize(s));
+      if (out[14] != 0.0) break;
+    }
+  }
+  std::memcpy(R, out, 72); std::memcpy(T, out + 9, 24);
+  if (sse_last) *sse_last = out[12];
+  if (iters_done) *iters_done = (int32_t)out[13];
+  if (order_last) {
+    VPC_CUDA(ctx, cudaMemcpyAsync(order_last, d_order, 4ull * n, cudaMemcpyDeviceToHost, s));
+    VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  ctx->model_set = false;
+  return VPC_OK;
+}
+
+}  // extern "C"
