@@ -48,45 +48,56 @@ def load_peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML from a background thread while the timed
+    regions run (the nvidia-smi query of B200_PROFILING.md, without the process start-up latency)."""
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
+    def __init__(self, gpu_index: int, period_s: float = 0.005):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = None
+        self._thr = None
 
     def start(self):
+        import threading
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001
+            self.reasons.add(f"nvml unavailable: {exc}")
+            return
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+                self._stop.wait(self.period)
+
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        hi = [v for v in sm if v >= 0.5 * max(sm)]
-        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons) or ["no samples"]}
+        hi = [v for v in self.samples if v >= 0.5 * max(self.samples)]
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 def dist_env():
@@ -267,13 +278,21 @@ def run_ours(args):
             e0.record(); ctx.icp_rigid_dev(dd, -1.0, ICP_ITERS, out=outs); e1.record(); torch.cuda.synchronize()
             tot += e0.elapsed_time(e1)
         it_s = ICP_ITERS * reps / (tot * 1e-3)
+        ctx.profile(True)
+        ctx.icp_rigid_dev(dd, -1.0, ICP_ITERS, out=outs)
+        agg = {}
+        for name, ms in ctx.profile_report():
+            agg.setdefault(name, []).append(ms)
+        ctx.profile(False)
+        icp_kernels = {k: round(sum(v) / len(v), 5) for k, v in agg.items()}
+        ctx.icp_rigid(model, data, -1.0, 2)          # warm the host-pointer path (allocations)
         t0 = time.perf_counter()
         r = ctx.icp_rigid(model, data, -1.0, ICP_ITERS)
         icp_e2e_s = time.perf_counter() - t0
         algo_bytes = 28 * ICP_N + 24 * ICP_M
         icp = {"metric": "icp_iters_per_s", "value": it_s, "unit": "iters/s", "workload": "C3: 100k source vs 1M target, 50 iterations, fp64",
                "ms_per_iter": 1e3 / it_s, "model_grid_build_ms": build_ms, "e2e_iters_per_s": ICP_ITERS / icp_e2e_s,
-               "roofline_frac": algo_bytes * it_s / 1e9 / peak_gbs, "rmse_last": r.rmse}
+               "roofline_frac": algo_bytes * it_s / 1e9 / peak_gbs, "rmse_last": r.rmse, "kernel_ms_per_launch": icp_kernels}
 
     # ---- CPU baseline (oracle port) on this box's host cores, N = 1 only
     cpu = None

@@ -1,4 +1,4 @@
-// dbscan.cuh -- DBSCAN (2-D, L1, inclusive eps) on a uniform eps-grid cell list.
+// dbscan.cuh -- DBSCAN (2-D, L1, inclusive eps) on a uniform cell list in ROTATED coordinates.
 //
 // Replaces DBImproved.dbscan / isKeyPoint / expandCluster / getDisP
 // (vtkPointCloud/BaseClass/DBImproved.cs:14-114).  The scan-order algorithm of the
@@ -6,13 +6,26 @@
 //   core[p]      <=> #{q : |dx|+|dy| <= eps} >= min_pts, self included        (:33-54)
 //   cluster of a core point = rank of its component's minimum ORIGINAL index   (:93-110)
 //   non-core p   -> max cluster id over core q within eps (last writer wins)   (:87)
-// Pipeline (all on one stream, no host round trip):
-//   k_db_init -> k_db_bounds -> k_db_hist -> scan(cells) -> k_db_scatter -> k_db_count
-//   -> k_db_union -> k_db_resolve -> scan(root flags) -> k_db_label
-// HBM layout: points are physically re-ordered by cell (counting sort) into sxy[] as
-// double2 (one 128-bit load per candidate) with sidx[] = original index; a row of three
-// neighbouring cells is one contiguous range of sxy[], so a region query reads three
-// contiguous ranges.
+//
+// Geometry.  With u = x + y, v = x - y the L1 distance is max(|du|, |dv|): the reference's
+// eps-diamond is an axis-aligned square in (u, v).  Points are binned on a (u, v) grid whose
+// cell side h sits a hair BELOW eps, so that
+//   * two points in the same cell are neighbours, whatever the rounding ("clique" cells):
+//     a cell with >= min_pts points is all core without one distance test, all core points of
+//     a cell belong to one cluster, and cluster connectivity is decided per cell pair;
+//   * every neighbour of p lies in the cells [cell(u-E), cell(u+E)] x [cell(v-E), cell(v+E)]
+//     (E = eps + rounding slack), i.e. the 3x3 block, occasionally 4 wide.
+// The binning only selects candidates; every accept/reject is the reference's own predicate
+// fl(|fl(dx)| + |fl(dy)|) <= eps on the original coordinates, so results are bit-exact.
+// If the grid has to be coarsened (cell budget, extreme coordinate ranges) the clique
+// shortcuts are switched off (ctrl.clique = 0) and the same kernels test every pair.
+//
+// Pipeline (one stream, no host round trip, no memsets):
+//   k_db_bounds -> k_db_hist -> scan(cells) -> k_db_scatter -> k_db_count -> k_db_union
+//   -> k_db_flatten -> k_db_resolve -> scan(self-keyed points) -> k_db_label
+// HBM layout: points are physically re-ordered by cell (counting sort) into sxy[] as double2
+// (one 128-bit load per candidate) with sidx[] = original index; cells of one grid row are
+// consecutive, so the candidates of a region query are <= 4 contiguous ranges of sxy[].
 #pragma once
 
 #include "common.cuh"
@@ -20,14 +33,14 @@
 namespace vpc {
 
 struct DbCtrl {
-  unsigned long long xmin_k, xmax_k, ymin_k, ymax_k;  // ordered encodings (atomicMin/Max)
-  double xmin, ymin, h, inv_h;
-  int ncx, ncy, ncells, ncells_p1;
-  int n_valid;   // points that take part in the grid (finite, eps >= 0)
+  unsigned long long umin_k, umax_k, vmin_k, vmax_k;  // ordered encodings (atomicMin/Max); self-resetting
+  double u0, v0, h, inv_h, E;
+  int ncu, ncv, ncells, ncells_p1;
+  int clique;    // 1: same-cell points are guaranteed to satisfy the reference predicate
+  int n_valid;   // points that take part in the grid
   int n_roots;   // number of clusters found
   unsigned blocks_done;
   int scan_counter[2];
-  int pad;
 };
 
 struct DbArgs {
@@ -41,17 +54,17 @@ struct DbArgs {
   // workspace
   DbCtrl* ctrl;
   int* cellkey;      // [n]  cell of original point i, -1 = not in the grid
-  int* cell_count;   // [cell_cap+1]
+  int* cell_count;   // [cell_cap+1]  zero on entry and on exit (k_db_scatter counts it back down)
   int* cell_start;   // [cell_cap+1]
   double2* sxy;      // [n]  coordinates in cell order
   int* sidx;         // [n]  original index of sorted position
   unsigned char* core;  // [n] by sorted position
   int* parent;       // [n]  union-find over sorted positions
+  int2* cinfo;       // [n]  .x at a cell's first slot: first core position of the cell; .y at a root: min original index
   int* compkey;      // [n]  by ORIGINAL index: min original core index of the point's cluster, -1 = noise
-  int* flag;         // [n]  by ORIGINAL index: 1 if i is the minimum core index of a component
-  int* rank;         // [n]  exclusive scan of flag
+  int* rank;         // [n]  exclusive scan of (compkey[i] == i)
   unsigned long long* tile_state0;  // scan states (cells)
-  unsigned long long* tile_state1;  // scan states (flags)
+  unsigned long long* tile_state1;  // scan states (points)
   int tiles0, tiles1;
   // outputs (device)
   int* cluster_id;
@@ -62,53 +75,57 @@ struct DbArgs {
 
 constexpr int kDbBlock = 256;
 
-// ---- k_db_init: zero the counters this invocation uses ------------------------------------
-__global__ void __launch_bounds__(kDbBlock) k_db_init(DbArgs a) {
+// one-time initialisation of a fresh workspace (cell_count must be all zero, ctrl keys armed)
+__global__ void __launch_bounds__(kDbBlock) k_db_ws_init(DbArgs a) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nth = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i <= a.cell_cap; i += nth) a.cell_count[i] = 0;
-  for (long long i = tid; i < a.n; i += nth) a.flag[i] = 0;
-  for (long long i = tid; i < a.tiles0; i += nth) a.tile_state0[i] = 0;
-  for (long long i = tid; i < a.tiles1; i += nth) a.tile_state1[i] = 0;
   if (tid == 0) {
     DbCtrl* c = a.ctrl;
-    c->xmin_k = ~0ull; c->ymin_k = ~0ull; c->xmax_k = 0ull; c->ymax_k = 0ull;
+    c->umin_k = ~0ull; c->vmin_k = ~0ull; c->umax_k = 0ull; c->vmax_k = 0ull;
     c->blocks_done = 0; c->scan_counter[0] = 0; c->scan_counter[1] = 0;
     c->n_valid = 0; c->n_roots = 0;
   }
 }
 
+// A point takes part in the grid when the reference predicate can ever be true for it:
+// finite coordinates and eps >= 0 (NaN/inf make every '<=' false, DBImproved.cs:41).
+// (x + y, x - y must be finite too: |x| + |y| < 1.79e308, documented limit.)
 __device__ __forceinline__ bool db_valid(double x, double y, bool eps_ok) {
-  return eps_ok && finite_d(x) && finite_d(y);
+  return eps_ok && finite_d(x) && finite_d(y) && finite_d(x + y) && finite_d(x - y);
 }
 
-// ---- k_db_bounds: bounding box of the participating points; last block derives the grid ----
+// ---- k_db_bounds: (u, v) bounding box; the last block derives the grid ------------------------
 __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
   const bool eps_ok = (a.eps >= 0.0);
-  double xmn = INFINITY, xmx = -INFINITY, ymn = INFINITY, ymx = -INFINITY;
+  double umn = INFINITY, umx = -INFINITY, vmn = INFINITY, vmx = -INFINITY;
   const long long nth = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += nth) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = tid; i < a.tiles0; i += nth) a.tile_state0[i] = 0;
+  for (long long i = tid; i < a.tiles1; i += nth) a.tile_state1[i] = 0;
+  for (long long i = tid; i < a.n; i += nth) {
     const double x = __ldg(a.x + i), y = __ldg(a.y + i);
     if (db_valid(x, y, eps_ok)) {
-      xmn = fmin(xmn, x); xmx = fmax(xmx, x);
-      ymn = fmin(ymn, y); ymx = fmax(ymx, y);
+      const double u = x + y, v = x - y;
+      umn = fmin(umn, u); umx = fmax(umx, u);
+      vmn = fmin(vmn, v); vmx = fmax(vmx, v);
     }
   }
-  xmn = warp_min_d(xmn); xmx = warp_max_d(xmx); ymn = warp_min_d(ymn); ymx = warp_max_d(ymx);
+  umn = warp_min_d(umn); umx = warp_max_d(umx); vmn = warp_min_d(vmn); vmx = warp_max_d(vmx);
   __shared__ double s[4][kDbBlock / kWarp];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s[0][warp] = xmn; s[1][warp] = xmx; s[2][warp] = ymn; s[3][warp] = ymx; }
+  if (lane == 0) { s[0][warp] = umn; s[1][warp] = umx; s[2][warp] = vmn; s[3][warp] = vmx; }
   __syncthreads();
   DbCtrl* c = a.ctrl;
   if (threadIdx.x == 0) {
     for (int w = 1; w < kDbBlock / kWarp; ++w) {
-      xmn = fmin(xmn, s[0][w]); xmx = fmax(xmx, s[1][w]);
-      ymn = fmin(ymn, s[2][w]); ymx = fmax(ymx, s[3][w]);
+      umn = fmin(umn, s[0][w]); umx = fmax(umx, s[1][w]);
+      vmn = fmin(vmn, s[2][w]); vmx = fmax(vmx, s[3][w]);
     }
-    if (xmn <= xmx) {
-      atomicMin(&c->xmin_k, ord_encode(xmn)); atomicMax(&c->xmax_k, ord_encode(xmx));
-      atomicMin(&c->ymin_k, ord_encode(ymn)); atomicMax(&c->ymax_k, ord_encode(ymx));
+    if (umn <= umx) {
+      atomicMin(&c->umin_k, ord_encode(umn)); atomicMax(&c->umax_k, ord_encode(umx));
+      atomicMin(&c->vmin_k, ord_encode(vmn)); atomicMax(&c->vmax_k, ord_encode(vmx));
     }
     __threadfence();
     s_last = (atomicAdd(&c->blocks_done, 1u) == gridDim.x - 1);
@@ -117,37 +134,50 @@ __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
   if (!s_last || threadIdx.x != 0) return;
   __threadfence();
   // ---- grid parameters (one thread) ----
-  const unsigned long long kx0 = ld_relaxed_u64(&c->xmin_k), kx1 = ld_relaxed_u64(&c->xmax_k);
-  const unsigned long long ky0 = ld_relaxed_u64(&c->ymin_k), ky1 = ld_relaxed_u64(&c->ymax_k);
-  double h = 1.0, x0 = 0.0, y0 = 0.0;
-  int ncx = 1, ncy = 1;
-  if (kx0 <= kx1) {
-    x0 = ord_decode(kx0); y0 = ord_decode(ky0);
-    double ex = ord_decode(kx1) - x0, ey = ord_decode(ky1) - y0;
-    ex = fmin(ex, 1e300); ey = fmin(ey, 1e300);
-    // Cell side a hair above eps: |dx| <= eps (as evaluated in fp64) then implies the two
-    // points' cell columns differ by at most one whatever the rounding of the products below.
-    h = a.eps * (1.0 + 1.0 / 65536.0);
-    h = fmax(h, fmax(ex, ey) * (1.0 / 1073741824.0));
-    if (!(h > 0.0) || !finite_d(h)) h = 1.0;
+  const unsigned long long ku0 = ld_relaxed_u64(&c->umin_k), ku1 = ld_relaxed_u64(&c->umax_k);
+  const unsigned long long kv0 = ld_relaxed_u64(&c->vmin_k), kv1 = ld_relaxed_u64(&c->vmax_k);
+  // re-arm the control block for the next invocation
+  c->umin_k = ~0ull; c->vmin_k = ~0ull; c->umax_k = 0ull; c->vmax_k = 0ull;
+  c->blocks_done = 0; c->scan_counter[0] = 0; c->scan_counter[1] = 0;
+  double h = 1.0, u0 = 0.0, v0 = 0.0, E = 0.0;
+  int ncu = 1, ncv = 1, clique = 0;
+  if (ku0 <= ku1) {
+    u0 = ord_decode(ku0); v0 = ord_decode(kv0);
+    const double u1 = ord_decode(ku1), v1 = ord_decode(kv1);
+    const double eu = fmin(u1 - u0, 1e300), ev = fmin(v1 - v0, 1e300);
+    // |fl(x+y) - (x+y)| <= 2^-53 |fl(x+y)|; err is twice that bound for the largest |u|, |v| present
+    const double amax = fmax(fmax(fabs(u0), fabs(u1)), fmax(fabs(v0), fabs(v1)));
+    const double err = amax * 2.220446049250313e-16 + 4.9e-324;
+    // predicate true  =>  |du|, |dv| <= eps (1 + 2^-50)  =>  |fl(u_p) - fl(u_q)| <= that + 2 err; one more
+    // err for rounding fl(u -+ E) itself.  Cell lookup is monotone, so [cell(u-E), cell(u+E)] covers q.
+    E = a.eps * (1.0 + 9.094947017729282e-13) + 4.0 * err;
+    // same cell  =>  |fl(u_p) - fl(u_q)| < h (1 + 2^-19)  =>  true L1 < h (1 + 2^-19) + 2 err, and the
+    // predicate's own rounding adds 2^-51 relative: h = (eps - 3 err)(1 - 2^-16) keeps it <= eps.
+    h = (a.eps - 3.0 * err) * (1.0 - 1.0 / 65536.0);
+    clique = 1;
+    if (!(h > 0.0) || !finite_d(h)) { h = E; clique = 0; }
+    const double h_floor = fmax(eu, ev) * (1.0 / 1073741824.0);
+    if (h < h_floor) { h = h_floor; clique = 0; }
+    if (!(h > 0.0) || !finite_d(h)) { h = 1.0; clique = 0; }
     const double cap = (double)a.cell_cap;
-    for (int it = 0; it < 64; ++it) {
+    for (int it = 0; it < 100; ++it) {
       const double inv = 1.0 / h;
-      const double fx = floor(ex * inv) + 1.0, fy = floor(ey * inv) + 1.0;
-      if (fx * fy <= cap && fx < 2147483000.0 && fy < 2147483000.0) { ncx = (int)fx; ncy = (int)fy; break; }
-      h = h * sqrt(fx * fy / cap) * 1.0009765625;  // coarsen: larger cells stay correct
+      const double fu = floor(eu * inv) + 1.0, fv = floor(ev * inv) + 1.0;  // = cell index of the max point + 1
+      if (fu * fv <= cap && fu < 2147483000.0 && fv < 2147483000.0) { ncu = (int)fu; ncv = (int)fv; break; }
+      h = h * sqrt(fu * fv / cap) * 1.0009765625;  // coarsen: candidates only, results stay exact
+      clique = 0;
+      if (it == 99) { h = fmax(eu, ev) * 2.0 + 1.0; ncu = 1; ncv = 1; }
     }
   }
-  c->xmin = x0; c->ymin = y0; c->h = h; c->inv_h = 1.0 / h;
-  c->ncx = ncx; c->ncy = ncy; c->ncells = ncx * ncy; c->ncells_p1 = ncx * ncy + 1;
+  c->u0 = u0; c->v0 = v0; c->h = h; c->inv_h = 1.0 / h; c->E = E;
+  c->ncu = ncu; c->ncv = ncv; c->ncells = ncu * ncv; c->ncells_p1 = ncu * ncv + 1;
+  c->clique = clique;
 }
 
-__device__ __forceinline__ void db_cell_of(const DbCtrl& c, double x, double y, int& cx, int& cy) {
-  // monotone in x: fl(x - xmin) * inv_h, floor; never exceeds ncx-1 (see k_db_bounds), clamped anyway
-  cx = (int)floor((x - c.xmin) * c.inv_h);
-  cy = (int)floor((y - c.ymin) * c.inv_h);
-  cx = min(max(cx, 0), c.ncx - 1);
-  cy = min(max(cy, 0), c.ncy - 1);
+// cell coordinate of a (possibly out-of-box) u or v value; monotone non-decreasing in t
+__device__ __forceinline__ int db_cell1(double t, double o, double inv_h, int nc) {
+  const double q = floor((t - o) * inv_h);
+  return (int)fmin(fmax(q, 0.0), (double)(nc - 1));
 }
 
 // ---- k_db_hist: cell key per point + occupancy histogram; settles points outside the grid ----
@@ -157,9 +187,9 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
   const DbCtrl c = *a.ctrl;
   const double x = __ldg(a.x + i), y = __ldg(a.y + i);
   if (db_valid(x, y, a.eps >= 0.0)) {
-    int cx, cy;
-    db_cell_of(c, x, y, cx, cy);
-    const int key = cy * c.ncx + cx;
+    const int cu = db_cell1(x + y, c.u0, c.inv_h, c.ncu);
+    const int cv = db_cell1(x - y, c.v0, c.inv_h, c.ncv);
+    const int key = cv * c.ncu + cu;
     a.cellkey[i] = key;
     atomicAdd(&a.cell_count[key], 1);
   } else {
@@ -170,11 +200,10 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
     const bool key_pt = (0 >= a.min_pts);
     a.is_key[i] = key_pt ? 1 : 0;
     a.compkey[i] = key_pt ? (int)i : -1;
-    if (key_pt) a.flag[i] = 1;
   }
 }
 
-// ---- k_db_scatter: physical reorder by cell ------------------------------------------------
+// ---- k_db_scatter: physical reorder by cell; leaves cell_count at zero again ----------------------
 __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
@@ -183,32 +212,46 @@ __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
   const int pos = a.cell_start[key] + atomicSub(&a.cell_count[key], 1) - 1;
   a.sxy[pos] = make_double2(__ldg(a.x + i), __ldg(a.y + i));
   a.sidx[pos] = (int)i;
+  a.cinfo[pos] = make_int2(0x7fffffff, 0x7fffffff);   // {first core position of the cell, min original index of the component}
 }
 
 // exact reference predicate: Math.Abs(dx) + Math.Abs(dy) <= e   (DBImproved.cs:16-21, :41)
-__device__ __forceinline__ bool db_near(double px, double py, double2 q, double eps) {
-  const double dx = px - q.x, dy = py - q.y;
+__device__ __forceinline__ bool db_near(double2 p, double2 q, double eps) {
+  const double dx = p.x - q.x, dy = p.y - q.y;
   return (fabs(dx) + fabs(dy)) <= eps;
 }
 
-struct DbRows {
-  int j0[3], j1[3];
+// the block of cells that can hold neighbours of p, and p's own cell.  ncols, nrows <= 4 by construction
+// (2E < 2.0001 h in clique mode, E <= h otherwise); the kernels clamp to 4 and loop if a range is longer.
+struct DbStencil {
+  int cu, cv, ulo, uhi, vlo, vhi;
 };
-// candidate ranges (three rows of three cells) of the point at (x, y)
-__device__ __forceinline__ void db_rows(const DbCtrl& c, const int* __restrict__ cell_start, double x, double y, DbRows& r) {
-  int cx, cy;
-  db_cell_of(c, x, y, cx, cy);
-  const int xa = max(cx - 1, 0), xb = min(cx + 1, c.ncx - 1);
+__device__ __forceinline__ DbStencil db_stencil(const DbCtrl& c, double2 p) {
+  const double u = p.x + p.y, v = p.x - p.y;
+  DbStencil s;
+  s.cu = db_cell1(u, c.u0, c.inv_h, c.ncu);
+  s.cv = db_cell1(v, c.v0, c.inv_h, c.ncv);
+  s.ulo = db_cell1(u - c.E, c.u0, c.inv_h, c.ncu);
+  s.uhi = db_cell1(u + c.E, c.u0, c.inv_h, c.ncu);
+  s.vlo = db_cell1(v - c.E, c.v0, c.inv_h, c.ncv);
+  s.vhi = db_cell1(v + c.E, c.v0, c.inv_h, c.ncv);
+  return s;
+}
+
+// number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight
+__device__ __forceinline__ int db_count_range(const double2* __restrict__ sxy, int j0, int j1, int s, int e, double2 me, double eps) {
+  int cnt = 0;
+  for (int j = j0; j < j1; j += 4) {
+    double2 q[4];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const int yy = cy + d - 1;
-    if (yy >= 0 && yy < c.ncy) {
-      r.j0[d] = __ldg(cell_start + yy * c.ncx + xa);
-      r.j1[d] = __ldg(cell_start + yy * c.ncx + xb + 1);
-    } else {
-      r.j0[d] = 0; r.j1[d] = 0;
+    for (int k = 0; k < 4; ++k) q[k] = ldg_d2(sxy + min(j + k, j1 - 1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int jj = j + k;
+      cnt += (jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps)) ? 1 : 0;
     }
   }
+  return cnt;
 }
 
 // ---- k_db_count: region query -> core flag (isKeyPoint, DBImproved.cs:33-54) ------------------
@@ -217,22 +260,43 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
   const DbCtrl c = *a.ctrl;
   if (p >= c.n_valid) return;
   const double2 me = a.sxy[p];
-  DbRows r;
-  db_rows(c, a.cell_start, me.x, me.y, r);
-  int cnt = 0;
+  const DbStencil st = db_stencil(c, me);
   const int need = a.min_pts;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    for (int j = r.j0[d]; j < r.j1[d]; ++j) {
-      cnt += db_near(me.x, me.y, ldg_d2(a.sxy + j), a.eps) ? 1 : 0;
-    }
-    if (cnt >= need) break;  // only 'count >= minPts' matters (:47)
+  const int own = st.cv * c.ncu + st.cu;
+  const int s = __ldg(a.cell_start + own), e = __ldg(a.cell_start + own + 1);
+  int cnt = 0, par = p;
+  bool dense = false;
+  int es = 0, ee = 0;                  // range excluded from the tests because it is already counted
+  if (c.clique) {
+    cnt = e - s;                       // every point of the own cell is a neighbour (self included)
+    es = s; ee = e;
+    if (cnt >= need) { dense = true; par = s; }   // dense cell: all core, one cluster, hung under its first point
   }
-  a.core[p] = (cnt >= need) ? 1 : 0;
-  a.parent[p] = p;
+  if (!dense) {
+    for (int rb = st.vlo; rb <= st.vhi && cnt < need; rb += 4) {
+      int j0[4], j1[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {    // all row ranges first: independent loads
+        const int row = rb + r;
+        const bool ok = row <= st.vhi;
+        j0[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.ulo) : 0;
+        j1[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.uhi + 1) : 0;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (cnt < need) cnt += db_count_range(a.sxy, j0[r], j1[r], es, ee, me, a.eps);
+    }
+  }
+  const bool core = cnt >= need;       // only 'count >= minPts' matters (:47)
+  a.core[p] = core ? 1 : 0;
+  a.parent[p] = par;
+  if (core && c.clique) {              // publish the first core position of the cell at the cell's first slot
+    if (dense) { if (p == s) a.cinfo[s].x = s; }
+    else atomicMin(&a.cinfo[s].x, p);
+  }
 }
 
-// ---- union-find over sorted positions; the root is the member with the smallest ORIGINAL index
+// ---- union-find over sorted positions; hooks point towards smaller positions -------------------
 __device__ __forceinline__ int uf_find(int* parent, int x) {
   int p = ld_relaxed_s32(parent + x);
   while (p != x) {
@@ -249,35 +313,85 @@ __device__ __forceinline__ int uf_find_ro(const int* parent, int x) {
   while (p != x) { x = p; p = ld_relaxed_s32(parent + x); }
   return x;
 }
-__device__ __forceinline__ void uf_unite(int* parent, const int* __restrict__ sidx, int a, int b) {
-  int ra = uf_find(parent, a), rb = uf_find(parent, b);
+// ra, rb: (possibly stale) roots.  Returns the root of the merged set as seen by this thread.
+__device__ __forceinline__ int uf_unite_roots(int* parent, int ra, int rb) {
   while (ra != rb) {
-    if (__ldg(sidx + ra) < __ldg(sidx + rb)) { const int t = ra; ra = rb; rb = t; }
-    // orig(ra) > orig(rb): hook ra under rb; parents always point to a smaller original index
-    const int old = atomicCAS(parent + ra, ra, rb);
-    if (old == ra) return;
+    if (ra < rb) { const int t = ra; ra = rb; rb = t; }
+    const int old = atomicCAS(parent + ra, ra, rb);   // hook the larger position under the smaller
+    if (old == ra) return rb;
     ra = uf_find(parent, ra);
     rb = uf_find(parent, rb);
   }
+  return ra;
 }
 
-// ---- k_db_union: core-core edges (expandCluster's reachability, DBImproved.cs:56-90) ---------
+// ---- k_db_union: core-core connectivity (expandCluster's reachability, DBImproved.cs:56-90) ----
 __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const DbCtrl c = *a.ctrl;
   if (p >= c.n_valid) return;
   if (!a.core[p]) return;
   const double2 me = a.sxy[p];
-  DbRows r;
-  db_rows(c, a.cell_start, me.x, me.y, r);
-  // each undirected edge once: only partners at a smaller sorted position (rows cy-1 and cy)
+  const DbStencil st = db_stencil(c, me);
+  int rp = uf_find(a.parent, p);
+  if (c.clique) {
+    const int own = st.cv * c.ncu + st.cu;
+    const int s = __ldg(a.cell_start + own);
+    // the core points of a cell are mutual neighbours: everybody joins the cell's first core point
+    const int lead = a.cinfo[s].x;
+    if (lead != p) rp = uf_unite_roots(a.parent, rp, uf_find(a.parent, lead));
+    // Each unordered pair of cells is handled from the cell with the larger key.  All core points of a
+    // cell share one cluster, so one root comparison dismisses a whole cell and one hit settles it.
+    for (int row = st.vlo; row <= st.cv; ++row) {
+      const int khi = (row == st.cv) ? st.cu - 1 : st.uhi;
+      const int base = row * c.ncu;
+      for (int kb = st.ulo; kb <= khi; kb += 4) {
+        int sB[5], lB[4], rB[4];
 #pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    const int j1 = min(r.j1[d], p);
-    for (int j = r.j0[d]; j < j1; ++j) {
-      if (a.core[j] && db_near(me.x, me.y, ldg_d2(a.sxy + j), a.eps)) uf_unite(a.parent, a.sidx, p, j);
+        for (int k = 0; k < 5; ++k) sB[k] = __ldg(a.cell_start + base + min(kb + k, khi + 1));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lB[k] = (kb + k <= khi && sB[k] < sB[k + 1]) ? a.cinfo[sB[k]].x : 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rB[k] = (lB[k] != 0x7fffffff) ? ld_relaxed_s32(a.parent + lB[k]) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (rB[k] < 0 || rB[k] == rp) continue;           // no core point there / parent is already our root
+          const int root = uf_find(a.parent, lB[k]);
+          if (root == rp) continue;
+          for (int j = lB[k]; j < sB[k + 1]; ++j)
+            if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) { rp = uf_unite_roots(a.parent, rp, root); break; }
+        }
+      }
+    }
+  } else {
+    for (int row = st.vlo; row <= st.cv; ++row) {
+      const int j0 = __ldg(a.cell_start + row * c.ncu + st.ulo);
+      const int j1 = min(__ldg(a.cell_start + row * c.ncu + st.uhi + 1), p);  // each edge once: partners before p
+      for (int j = j0; j < j1; ++j) {
+        if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) {
+          const int rj = uf_find(a.parent, j);
+          if (rj != rp) rp = uf_unite_roots(a.parent, rp, rj);
+        }
+      }
     }
   }
+}
+
+// ---- k_db_flatten: every core point learns its root; every root learns its minimum original index
+__global__ void __launch_bounds__(kDbBlock) k_db_flatten(DbArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_valid = a.ctrl->n_valid;
+  const bool active = (p < n_valid) && a.core[p];
+  int root = -1, orig = 0x7fffffff;
+  if (active) {
+    root = uf_find_ro(a.parent, p);
+    a.parent[p] = root;                    // readers racing with this store still see an ancestor
+    orig = __ldg(a.sidx + p);
+  }
+  // neighbours in sorted order mostly share a root: one atomic per distinct root per warp
+  const unsigned grp = __match_any_sync(kFull, root);
+  const int mn = __reduce_min_sync(grp, orig);
+  if (active && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicMin(&a.cinfo[root].y, mn);
 }
 
 // ---- k_db_resolve: component key per point, in ORIGINAL order ----------------------------------
@@ -288,22 +402,38 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
   const int me_i = a.sidx[p];
   int key;
   if (a.core[p]) {
-    const int root = uf_find_ro(a.parent, p);
-    key = a.sidx[root];
-    if (root == p) a.flag[me_i] = 1;
+    key = a.cinfo[a.parent[p]].y;
     a.is_key[me_i] = 1;
   } else {
     // border rule: the reference relabels unconditionally (:87), so the cluster expanded
     // last -- the one with the largest id = largest minimum core index -- wins.
     const double2 me = a.sxy[p];
-    DbRows r;
-    db_rows(c, a.cell_start, me.x, me.y, r);
+    const DbStencil st = db_stencil(c, me);
     key = -1;
+    for (int row = st.vlo; row <= st.vhi; ++row) {
+      const int base = row * c.ncu;
+      if (c.clique) {
+        for (int kb = st.ulo; kb <= st.uhi; kb += 4) {
+          int sB[5], lB[4], kB[4];
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-      for (int j = r.j0[d]; j < r.j1[d]; ++j)
-        if (a.core[j] && db_near(me.x, me.y, ldg_d2(a.sxy + j), a.eps))
-          key = max(key, __ldg(a.sidx + uf_find_ro(a.parent, j)));
+          for (int k = 0; k < 5; ++k) sB[k] = __ldg(a.cell_start + base + min(kb + k, st.uhi + 1));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) lB[k] = (kb + k <= st.uhi && sB[k] < sB[k + 1]) ? a.cinfo[sB[k]].x : 0x7fffffff;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) kB[k] = (lB[k] != 0x7fffffff) ? a.cinfo[a.parent[lB[k]]].y : -1;   // one cluster per cell
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (kB[k] <= key) continue;
+            for (int j = lB[k]; j < sB[k + 1]; ++j)
+              if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) { key = kB[k]; break; }
+          }
+        }
+      } else {
+        const int j0 = __ldg(a.cell_start + base + st.ulo), j1 = __ldg(a.cell_start + base + st.uhi + 1);
+        for (int j = j0; j < j1; ++j)
+          if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) key = max(key, a.cinfo[a.parent[j]].y);
+      }
+    }
     a.is_key[me_i] = 0;
   }
   a.compkey[me_i] = key;

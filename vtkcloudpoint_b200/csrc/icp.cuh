@@ -7,11 +7,12 @@
 //
 // The model (target) cloud is static across iterations: it is binned once into a uniform
 // 3-D cell list (counting sort) and stored in cell order as 32-byte records
-// {x, y, z, original index}.  One iteration = two launches, no host round trip:
+// {x, y, z, original index}.  One iteration = ONE launch, no host round trip:
 //   k_icp_iter  : P = R*data + T, exact nearest model point by ring search (ties -> lowest
-//                 original index), per-block partial sums of {P, Y, P Y^T, |P-Y|^2}
-//   k_icp_solve : deterministic reduction of the partials, quaternion eigen solve, compose,
-//                 convergence test; the state lives in device memory.
+//                 original index), per-block partial sums of {P, Y, P Y^T, |P-Y|^2}; the last
+//                 block to finish reduces the partials in a fixed order (deterministic), does the
+//                 quaternion eigen solve, composes R/T and tests convergence.  The state lives in
+//                 device memory, so the whole loop is enqueued without a host round trip.
 #pragma once
 
 #include "common.cuh"
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) k_icp_model_bounds(IcpModel g) {
       if (ext[d] > 0) { vol *= ext[d]; ++nd; }
     }
     if (nd > 0) {
-      const double per = vol / fmax(1.0, (double)nv * 0.5);  // about two points per cell
+      const double per = vol / fmax(1.0, (double)nv);  // about one point per cell
       h = (nd == 3) ? cbrt(per) : (nd == 2 ? sqrt(per) : per);
       if (!(h > 0.0) || !finite_d(h)) h = fmax(ext[0], fmax(ext[1], ext[2]));
       if (!(h > 0.0) || !finite_d(h)) h = 1.0;
@@ -177,31 +178,72 @@ struct NnBest {
   double x, y, z;
 };
 
+__device__ __forceinline__ void icp_consider(NnBest& b, double2 a, double2 w, double px, double py, double pz) {
+  const double d2 = icp_sqd(px, py, pz, a.x, a.y, w.x);
+  const int i = (int)__double_as_longlong(w.y);
+  if (d2 < b.d || (d2 == b.d && i < b.i)) { b.d = d2; b.i = i; b.x = a.x; b.y = a.y; b.z = w.x; }
+}
+
+// candidates [j0, j1) of the cell-ordered model; two records (four 128-bit loads) in flight
 __device__ __forceinline__ void icp_scan_range(const double4* __restrict__ spts, int j0, int j1, double px, double py,
                                                double pz, NnBest& b) {
-  for (int j = j0; j < j1; ++j) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(spts + j));
-    const double2 w = __ldg(reinterpret_cast<const double2*>(spts + j) + 1);
-    const double d2 = icp_sqd(px, py, pz, a.x, a.y, w.x);
-    const int i = (int)__double_as_longlong(w.y);
-    if (d2 < b.d || (d2 == b.d && i < b.i)) { b.d = d2; b.i = i; b.x = a.x; b.y = a.y; b.z = w.x; }
+  const double2* s2 = reinterpret_cast<const double2*>(spts);
+  for (int j = j0; j < j1; j += 2) {
+    const int j2 = min(j + 1, j1 - 1);
+    const double2 a0 = __ldg(s2 + 2 * j), w0 = __ldg(s2 + 2 * j + 1);
+    const double2 a1 = __ldg(s2 + 2 * j2), w1 = __ldg(s2 + 2 * j2 + 1);
+    icp_consider(b, a0, w0, px, py, pz);
+    icp_consider(b, a1, w1, px, py, pz);   // j2 == j repeats a record: harmless for an argmin
   }
 }
 
+// true when nothing outside the searched cell box [lo, hi] can be closer than, or as close as, the best so far
+__device__ __forceinline__ bool icp_box_done(const IcpGridCtrl& c, const double* p, const int* lo, const int* hi,
+                                             const NnBest& b, double slack) {
+  bool all = true;
+  double lb = INFINITY;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (lo[d] > 0) { all = false; lb = fmin(lb, p[d] - (c.o[d] + (double)lo[d] * c.h)); }
+    if (hi[d] < c.nc[d] - 1) { all = false; lb = fmin(lb, (c.o[d] + (double)(hi[d] + 1) * c.h) - p[d]); }
+  }
+  if (all) return true;
+  const double lbs = lb - slack;
+  return b.i != 0x7fffffff && lbs > 0.0 && b.d < lbs * lbs * (1.0 - 9.094947017729282e-13);
+}
+
 // Exact argmin_j d2(p, model[j]) with ties to the lowest j (ICP.cs:229-248) for a finite p over the
-// finite model points.  Rings of cells are searched outward until nothing outside the searched box can
-// be closer than, or as close as, the best so far.
+// finite model points.  Search order: the 2x2x2 block of cells nearest to p, then the 3x3x3 block, then
+// shells of cells outward -- each time until nothing outside the searched box can beat or tie the best.
 __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl& c, double px, double py, double pz,
                                             NnBest& b) {
   b.d = INFINITY; b.i = 0x7fffffff; b.x = b.y = b.z = 0.0;
   const double p[3] = {px, py, pz};
-  int cc[3];
+  int cc[3], lo[3], hi[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) cc[d] = icp_cell1(p[d], c.o[d], c.inv_h, c.nc[d]);
-  const int rmax = max(c.nc[0], max(c.nc[1], c.nc[2]));
+  for (int d = 0; d < 3; ++d) {
+    cc[d] = icp_cell1(p[d], c.o[d], c.inv_h, c.nc[d]);
+    const double mid = c.o[d] + ((double)cc[d] + 0.5) * c.h;
+    lo[d] = (p[d] < mid) ? max(cc[d] - 1, 0) : cc[d];
+    hi[d] = (p[d] < mid) ? cc[d] : min(cc[d] + 1, c.nc[d] - 1);
+  }
   const double slack = ldexp(c.slack_base + fabs(px) + fabs(py) + fabs(pz), -40);
+  {  // stage 1: nearest octant block, at most 4 row segments; all range loads first
+    int j0[4], j1[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int z = (r & 2) ? hi[2] : lo[2], y = (r & 1) ? hi[1] : lo[1];
+      const bool dup = ((r & 2) && hi[2] == lo[2]) || ((r & 1) && hi[1] == lo[1]);
+      const int row = (z * c.nc[1] + y) * c.nc[0];
+      j0[r] = dup ? 0 : __ldg(g.cell_start + row + lo[0]);
+      j1[r] = dup ? 0 : __ldg(g.cell_start + row + hi[0] + 1);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) icp_scan_range(g.spts, j0[r], j1[r], px, py, pz, b);
+    if (icp_box_done(c, p, lo, hi, b, slack)) return;
+  }
+  const int rmax = max(c.nc[0], max(c.nc[1], c.nc[2]));
   for (int r = 1; r <= rmax; ++r) {
-    int lo[3], hi[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) { lo[d] = max(cc[d] - r, 0); hi[d] = min(cc[d] + r, c.nc[d] - 1); }
     for (int z = lo[2]; z <= hi[2]; ++z) {
@@ -216,16 +258,7 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
         }
       }
     }
-    bool all = true;
-    double lb = INFINITY;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      if (cc[d] - r > 0) { all = false; lb = fmin(lb, p[d] - (c.o[d] + (double)(cc[d] - r) * c.h)); }
-      if (cc[d] + r < c.nc[d] - 1) { all = false; lb = fmin(lb, (c.o[d] + (double)(cc[d] + r + 1) * c.h) - p[d]); }
-    }
-    if (all) break;
-    const double lbs = lb - slack;
-    if (b.i != 0x7fffffff && lbs > 0.0 && b.d < lbs * lbs * (1.0 - 9.094947017729282e-13)) break;
+    if (icp_box_done(c, p, lo, hi, b, slack)) return;
   }
 }
 
@@ -256,10 +289,131 @@ k_icp_closest(IcpModel g, const double* __restrict__ data, int n, int* __restric
   if (sqdist) sqdist[i] = b.d;
 }
 
-// ---- one ICP round, part 1: transform + correspondences + partial sums ----------------------
-__global__ void __launch_bounds__(kIcpBlock)
-k_icp_iter(IcpModel g, const double* __restrict__ data, int n, const IcpState* __restrict__ st, int* __restrict__ order,
-           double* __restrict__ partial) {
+// One cyclic-Jacobi rotation on the symmetric 4x4 A (annihilates A[P][Q]) with static indices so that
+// A and V stay in registers.  V accumulates the eigenvectors in its columns.
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_rot(double (&A)[4][4], double (&V)[4][4]) {
+  const double apq = A[P][Q];
+  if (fabs(apq) < 1e-300) return;
+  const double theta = (A[Q][Q] - A[P][P]) / (2.0 * apq);
+  const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double cs = rsqrt(t * t + 1.0), sn = t * cs;
+  A[P][P] -= t * apq; A[Q][Q] += t * apq; A[P][Q] = 0.0; A[Q][P] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k != P && k != Q) {
+      const double akp = A[k][P], akq = A[k][Q];
+      A[k][P] = A[P][k] = cs * akp - sn * akq;
+      A[k][Q] = A[Q][k] = sn * akp + cs * akq;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double vkp = V[k][P], vkq = V[k][Q];
+    V[k][P] = cs * vkp - sn * vkq;
+    V[k][Q] = sn * vkp + cs * vkq;
+  }
+}
+
+// Symmetric 4x4 eigen-decomposition (the job of Matrix.ComputeEvJacobi, Matrix.cs:571-668): cyclic sweeps
+// until the off-diagonal mass is below 1e-16 of the Frobenius norm (quadratic convergence, <= 12 sweeps).
+__device__ __forceinline__ void jacobi4(double (&A)[4][4], double (&V)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  double fro = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fro += A[i][j] * A[i][j];
+  const double tol = fro * 1e-32;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[0][3] * A[0][3] + A[1][2] * A[1][2] + A[1][3] * A[1][3] + A[2][3] * A[2][3];
+    if (!(off > tol)) break;
+    jacobi_rot<0, 1>(A, V); jacobi_rot<2, 3>(A, V);
+    jacobi_rot<0, 2>(A, V); jacobi_rot<1, 3>(A, V);
+    jacobi_rot<0, 3>(A, V); jacobi_rot<1, 2>(A, V);
+  }
+}
+
+// The rigid step of one round from the 16 sums S (ICP.cs:31-180, intended algorithm): means, cross-covariance,
+// Horn's 4x4 matrix, quaternion of the largest eigenvalue, R1/T1, SSE, convergence test, composition.
+__device__ __forceinline__ void icp_solve_round(const double* S, int n, double e, int max_iters, IcpState* st) {
+  const double N = (double)n;
+  double mp[3], my[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { mp[d] = S[d] / N; my[d] = S[3 + d] / N; }            // ICP.cs:255-273
+  const double inv_n = 1.0 / N;
+  double m[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) m[a][b] = S[6 + a * 3 + b] * inv_n - mp[a] * my[b];      // intended :53, :66
+  const double tr = (m[0][0] + m[1][1]) + m[2][2];                                         // :78
+  double Q[4][4], V[4][4];
+  Q[0][0] = tr;                                                                            // :88-104
+  Q[0][1] = Q[1][0] = m[1][2] - m[2][1];                                                   // delta = (A23, A31, A12), A = m - m^T
+  Q[0][2] = Q[2][0] = m[2][0] - m[0][2];
+  Q[0][3] = Q[3][0] = m[0][1] - m[1][0];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) Q[a + 1][b + 1] = (m[a][b] + m[b][a]) - (a == b ? tr : 0.0);
+  jacobi4(Q, V);
+  double qv[4] = {V[0][0], V[1][0], V[2][0], V[3][0]};
+  double best = Q[0][0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (Q[k][k] > best) { best = Q[k][k]; qv[0] = V[0][k]; qv[1] = V[1][k]; qv[2] = V[2][k]; qv[3] = V[3][k]; }  // largest eigenvalue
+  const double nq = sqrt(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2] + qv[3] * qv[3]);
+  if (nq > 0.0) { qv[0] = qv[0] / nq; qv[1] = qv[1] / nq; qv[2] = qv[2] / nq; qv[3] = qv[3] / nq; }
+  if (qv[0] < 0.0) { qv[0] = -qv[0]; qv[1] = -qv[1]; qv[2] = -qv[2]; qv[3] = -qv[3]; }
+  double R1[9];                                                                            // ICP.cs:274-285
+  R1[0] = qv[0] * qv[0] + qv[1] * qv[1] - qv[2] * qv[2] - qv[3] * qv[3];
+  R1[1] = 2.0 * (qv[1] * qv[2] - qv[0] * qv[3]);
+  R1[2] = 2.0 * (qv[1] * qv[3] + qv[0] * qv[2]);
+  R1[3] = 2.0 * (qv[1] * qv[2] + qv[0] * qv[3]);
+  R1[4] = qv[0] * qv[0] - qv[1] * qv[1] + qv[2] * qv[2] - qv[3] * qv[3];
+  R1[5] = 2.0 * (qv[2] * qv[3] - qv[0] * qv[1]);
+  R1[6] = 2.0 * (qv[1] * qv[3] - qv[0] * qv[2]);
+  R1[7] = 2.0 * (qv[2] * qv[3] + qv[0] * qv[1]);
+  R1[8] = qv[0] * qv[0] - qv[1] * qv[1] - qv[2] * qv[2] + qv[3] * qv[3];
+  double T1[3];                                                                            // :114-124
+#pragma unroll
+  for (int i = 0; i < 3; ++i) T1[i] = my[i] - (((0.0 + R1[i * 3] * mp[0]) + R1[i * 3 + 1] * mp[1]) + R1[i * 3 + 2] * mp[2]);
+
+  const double d = S[15];                                                                  // :126-133
+  const double pre_d = st->d;                                                              // :25
+  st->pre_d = pre_d; st->d = d;
+  const int round = st->round + 1;                                                         // :134
+  st->round = round;
+  const bool go_on = fabs(d - pre_d) >= e;                                                 // :149, :180
+  if (go_on) {
+    if (round == 1) {                                                                      // :151-162
+      for (int k = 0; k < 9; ++k) st->R[k] = R1[k];
+      for (int k = 0; k < 3; ++k) st->T[k] = T1[k];
+    } else {                                                                               // :163-177: R <- R1*R, T <- R1*T + T1
+      double tR[9], tT[3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) tR[i * 3 + j] = ((0.0 + R1[i * 3] * st->R[j]) + R1[i * 3 + 1] * st->R[3 + j]) + R1[i * 3 + 2] * st->R[6 + j];
+      for (int i = 0; i < 3; ++i) tT[i] = ((0.0 + R1[i * 3] * st->T[0]) + R1[i * 3 + 1] * st->T[1]) + R1[i * 3 + 2] * st->T[2];
+      for (int k = 0; k < 9; ++k) st->R[k] = tR[k];
+      for (int k = 0; k < 3; ++k) st->T[k] = tT[k] + T1[k];
+    }
+    st->have_rt = 1;                                                                       // :178 P = TransPoint(data, R, T)
+  } else {
+    st->converged = 1;
+  }
+  if (!go_on || (max_iters > 0 && round >= max_iters)) st->done = 1;
+}
+
+// ---- one ICP round in ONE launch: transform + correspondences + block sums; the last block to finish
+// reduces the per-block partials in a fixed order (deterministic) and performs the rigid solve.
+constexpr int kIterBlock = 256;
+__global__ void __launch_bounds__(kIterBlock)
+k_icp_iter(IcpModel g, const double* __restrict__ data, int n, double e, int max_iters, IcpState* st,
+           int* __restrict__ order, double* __restrict__ partial, unsigned* ticket) {
   if (st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double s[kIcpSums];
@@ -286,69 +440,33 @@ k_icp_iter(IcpModel g, const double* __restrict__ data, int n, const IcpState* _
     const double ex = px - b.x, ey = py - b.y, ez = pz - b.z;
     s[15] = ex * ex + ey * ey + ez * ez;  // ICP.cs:131
   }
-  __shared__ double sm[kIcpBlock / kWarp][kIcpSums];
+  __shared__ double sm[kIcpSums][kIterBlock / kIcpSums + 1];
+  __shared__ double S[kIcpSums];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < kIcpSums; ++k) {
     const double v = warp_sum_d(s[k]);
-    if (lane == 0) sm[warp][k] = v;
+    if (lane == 0) sm[k][warp] = v;
   }
   __syncthreads();
   if (threadIdx.x < kIcpSums) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < kIcpBlock / kWarp; ++w) v += sm[w][threadIdx.x];
+    for (int w = 0; w < kIterBlock / kWarp; ++w) v += sm[threadIdx.x][w];
     partial[(long long)blockIdx.x * kIcpSums + threadIdx.x] = v;
+    __threadfence();
   }
-}
-
-// Classical Jacobi for a symmetric 4x4 (the job of Matrix.ComputeEvJacobi, Matrix.cs:571-668):
-// zero the largest off-diagonal element until all are below eps.  v: eigenvectors in columns.
-__device__ inline void jacobi4(double a[4][4], double v[4][4], double eps, int max_it) {
-  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int it = 0; it < max_it; ++it) {
-    int p = 1, q = 0; double fm = 0.0;
-    for (int i = 1; i < 4; ++i) for (int j = 0; j < i; ++j) { const double d = fabs(a[i][j]); if (d > fm) { fm = d; p = i; q = j; } }
-    if (fm < eps) return;
-    const double x = -a[p][q], y = (a[q][q] - a[p][p]) / 2.0;
-    double omega = x / sqrt(x * x + y * y);
-    if (y < 0.0) omega = -omega;
-    double sn = 1.0 + sqrt(1.0 - omega * omega);
-    sn = omega / sqrt(2.0 * sn);
-    const double cn = sqrt(1.0 - sn * sn);
-    const double app = a[p][p], aqq = a[q][q], apq = a[p][q];
-    a[p][p] = app * cn * cn + aqq * sn * sn + apq * omega;
-    a[q][q] = app * sn * sn + aqq * cn * cn - apq * omega;
-    a[p][q] = 0.0; a[q][p] = 0.0;
-    for (int j = 0; j < 4; ++j) if (j != p && j != q) {
-      const double f = a[p][j];
-      a[p][j] = f * cn + a[q][j] * sn;
-      a[q][j] = -f * sn + a[q][j] * cn;
-    }
-    for (int i = 0; i < 4; ++i) if (i != p && i != q) {
-      const double f = a[i][p];
-      a[i][p] = f * cn + a[i][q] * sn;
-      a[i][q] = -f * sn + a[i][q] * cn;
-    }
-    for (int i = 0; i < 4; ++i) {
-      const double f = v[i][p];
-      v[i][p] = f * cn + v[i][q] * sn;
-      v[i][q] = -f * sn + v[i][q] * cn;
-    }
-  }
-}
-
-// ---- one ICP round, part 2: reduce, solve, compose, test ------------------------------------
-constexpr int kSolveBlock = 256;
-__global__ void __launch_bounds__(kSolveBlock)
-k_icp_solve(const double* __restrict__ partial, int n_blocks, int n, double e, int max_iters, IcpState* st) {
-  if (st->done) return;
-  __shared__ double sm[kIcpSums][kSolveBlock / kIcpSums + 1];
-  __shared__ double S[kIcpSums];
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last block: partials -> S in a fixed order, then the solve ----
+  constexpr int kSlices = kIterBlock / kIcpSums;
   const int q = threadIdx.x % kIcpSums, slice = threadIdx.x / kIcpSums;
-  constexpr int kSlices = kSolveBlock / kIcpSums;
   double acc = 0.0;
-  for (int b = slice; b < n_blocks; b += kSlices) acc += partial[(long long)b * kIcpSums + q];
+  for (int b = slice; b < (int)gridDim.x; b += kSlices) acc += __ldcg(partial + (long long)b * kIcpSums + q);
   sm[q][slice] = acc;
   __syncthreads();
   if (threadIdx.x < kIcpSums) {
@@ -357,73 +475,15 @@ k_icp_solve(const double* __restrict__ partial, int n_blocks, int n, double e, i
     S[threadIdx.x] = v;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-
-  const double N = (double)n;
-  double mp[3], my[3];
-  for (int d = 0; d < 3; ++d) { mp[d] = S[d] / N; my[d] = S[3 + d] / N; }      // ICP.cs:255-273
-  const double inv_n = 1.0 / N;
-  double m[3][3], mT[3][3], A[3][3];
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b) m[a][b] = S[6 + a * 3 + b] * inv_n - mp[a] * my[b];  // intended :53, :66
-  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) mT[b][a] = m[a][b];
-  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) A[a][b] = m[a][b] - mT[a][b];  // :71-72
-  const double delta[3] = {A[1][2], A[2][0], A[0][1]};                             // intended :74-76
-  const double tr = (m[0][0] + m[1][1]) + m[2][2];                                   // :78
-  double Q[4][4], V[4][4];
-  Q[0][0] = tr;                                                                      // :88-104
-  for (int k = 0; k < 3; ++k) { Q[0][k + 1] = delta[k]; Q[k + 1][0] = delta[k]; }
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b) Q[a + 1][b + 1] = (m[a][b] + mT[a][b]) - (a == b ? tr : 0.0);
-  double fro = 0.0;
-  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) fro += Q[a][b] * Q[a][b];
-  jacobi4(Q, V, fmax(sqrt(fro) * 1e-16, 2.2250738585072014e-308), 100);
-  int best = 0;
-  for (int k = 1; k < 4; ++k) if (Q[k][k] > Q[best][best]) best = k;                  // eigenvector of the largest eigenvalue
-  double qv[4] = {V[0][best], V[1][best], V[2][best], V[3][best]};
-  const double nq = sqrt(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2] + qv[3] * qv[3]);
-  if (nq > 0.0) for (int k = 0; k < 4; ++k) qv[k] = qv[k] / nq;
-  if (qv[0] < 0.0) for (int k = 0; k < 4; ++k) qv[k] = -qv[k];
-  double R1[9];                                                                       // ICP.cs:274-285
-  R1[0] = qv[0] * qv[0] + qv[1] * qv[1] - qv[2] * qv[2] - qv[3] * qv[3];
-  R1[1] = 2.0 * (qv[1] * qv[2] - qv[0] * qv[3]);
-  R1[2] = 2.0 * (qv[1] * qv[3] + qv[0] * qv[2]);
-  R1[3] = 2.0 * (qv[1] * qv[2] + qv[0] * qv[3]);
-  R1[4] = qv[0] * qv[0] - qv[1] * qv[1] + qv[2] * qv[2] - qv[3] * qv[3];
-  R1[5] = 2.0 * (qv[2] * qv[3] - qv[0] * qv[1]);
-  R1[6] = 2.0 * (qv[1] * qv[3] - qv[0] * qv[2]);
-  R1[7] = 2.0 * (qv[2] * qv[3] + qv[0] * qv[1]);
-  R1[8] = qv[0] * qv[0] - qv[1] * qv[1] - qv[2] * qv[2] + qv[3] * qv[3];
-  double T1[3];                                                                       // :114-124
-  for (int i = 0; i < 3; ++i) T1[i] = my[i] - (((0.0 + R1[i * 3] * mp[0]) + R1[i * 3 + 1] * mp[1]) + R1[i * 3 + 2] * mp[2]);
-
-  const double d = S[15];                                                             // :126-133
-  const double pre_d = st->d;                                                         // :25
-  st->pre_d = pre_d; st->d = d;
-  const int round = st->round + 1;                                                    // :134
-  st->round = round;
-  const bool go_on = fabs(d - pre_d) >= e;                                            // :149, :180
-  if (go_on) {
-    if (round == 1) {                                                                 // :151-162
-      for (int k = 0; k < 9; ++k) st->R[k] = R1[k];
-      for (int k = 0; k < 3; ++k) st->T[k] = T1[k];
-    } else {                                                                          // :163-177: R <- R1*R, T <- R1*T + T1
-      double tR[9], tT[3];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) tR[i * 3 + j] = ((0.0 + R1[i * 3] * st->R[j]) + R1[i * 3 + 1] * st->R[3 + j]) + R1[i * 3 + 2] * st->R[6 + j];
-      for (int i = 0; i < 3; ++i) tT[i] = ((0.0 + R1[i * 3] * st->T[0]) + R1[i * 3 + 1] * st->T[1]) + R1[i * 3 + 2] * st->T[2];
-      for (int k = 0; k < 9; ++k) st->R[k] = tR[k];
-      for (int k = 0; k < 3; ++k) st->T[k] = tT[k] + T1[k];
-    }
-    st->have_rt = 1;                                                                  // :178 P = TransPoint(data, R, T)
-  } else {
-    st->converged = 1;
+  if (threadIdx.x == 0) {
+    *ticket = 0;
+    icp_solve_round(S, n, e, max_iters, st);
   }
-  if (!go_on || (max_iters > 0 && round >= max_iters)) st->done = 1;
 }
 
-__global__ void k_icp_state_init(IcpState* st, const double* R0, const double* T0) {
+__global__ void k_icp_state_init(IcpState* st, const double* R0, const double* T0, unsigned* ticket) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  *ticket = 0;
   for (int k = 0; k < 9; ++k) st->R[k] = R0 ? R0[k] : 0.0;
   for (int k = 0; k < 3; ++k) st->T[k] = T0 ? T0[k] : 0.0;
   st->pre_d = 0.0; st->d = 0.0; st->round = 0; st->done = 0; st->have_rt = 0; st->converged = 0;

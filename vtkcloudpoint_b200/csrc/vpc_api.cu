@@ -54,8 +54,10 @@ struct vpc_ctx {
   bool model_set = false;
   IcpState* icp_state = nullptr;
   double* icp_partial = nullptr;
+  unsigned* icp_ticket = nullptr;
   int icp_partial_blocks = 0;
   int sm_count = 148;
+  int64_t db_ws_n = -1;  // n the DBSCAN workspace is currently laid out and initialised for
   // optional per-kernel CUDA-event timing (bench.py's roofline leg)
   bool profile = false;
   struct ProfRec { const char* name; cudaEvent_t a, b; };
@@ -124,11 +126,14 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
                    int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
                    int32_t* d_cluster_amount, cudaStream_t s) {
   const int ni = (int)n;
-  const long long cap_ll = std::min<long long>(2ll * n + 1024, 2147483000ll);
+  // (u, v) cells of side ~eps: about 4 x (bounding area / eps^2); 8 per point covers clustered clouds,
+  // anything sparser is coarsened on the device (exactness is unaffected).
+  const long long cap_ll = std::min<long long>(8ll * n + 4096, 2147483000ll);
   const int cell_cap = (int)cap_ll;
   const int tiles0 = scan_tiles((long long)cell_cap + 1), tiles1 = scan_tiles(std::max<long long>(n, 1));
-  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * 6 + al256(4ull * (cell_cap + 1ull)) * 2 + al256(16ull * n) +
+  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * 5 + al256(8ull * n) + al256(4ull * (cell_cap + 1ull)) * 2 + al256(16ull * n) +
                  al256((size_t)n) + al256(8ull * tiles0) + al256(8ull * tiles1) + 4096;
+  const char* base_before = ctx->db.base;
   int rc = arena_reserve(ctx, ctx->db, bytes);
   if (rc) return rc;
   Arena& w = ctx->db;
@@ -136,15 +141,15 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   a.x = d_x; a.y = d_y; a.n = ni; a.eps = eps; a.min_pts = min_pts; a.first_cluster_id = first_cluster_id;
   a.cell_cap = cell_cap;
   a.ctrl = w.take<DbCtrl>(1);
-  a.cellkey = w.take<int>(n);
   a.cell_count = w.take<int>(cell_cap + 1ull);
   a.cell_start = w.take<int>(cell_cap + 1ull);
+  a.cellkey = w.take<int>(n);
   a.sxy = w.take<double2>(n);
   a.sidx = w.take<int>(n);
   a.core = w.take<unsigned char>(n);
   a.parent = w.take<int>(n);
+  a.cinfo = w.take<int2>(n);
   a.compkey = w.take<int>(n);
-  a.flag = w.take<int>(n);
   a.rank = w.take<int>(n);
   a.tile_state0 = w.take<unsigned long long>(tiles0);
   a.tile_state1 = w.take<unsigned long long>(tiles1);
@@ -153,18 +158,26 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
 
   const int gpts = blocks_for(n, kDbBlock);
   const int gstride = std::min(gpts, ctx->sm_count * 8);
-  VPC_LAUNCH(ctx, k_db_init, std::min(blocks_for((long long)cell_cap + 1, kDbBlock), ctx->sm_count * 16), kDbBlock, s, a);
+  // The control block and the cell counters clean up after themselves (k_db_bounds / k_db_scatter); they
+  // are initialised only when the workspace is new or its layout (n) changed.
+  if (base_before != ctx->db.base || ctx->db_ws_n != n) {
+    ctx->db_ws_n = -1;
+    VPC_LAUNCH(ctx, k_db_ws_init, std::min(blocks_for((long long)cell_cap + 1, kDbBlock), ctx->sm_count * 16), kDbBlock, s, a);
+  }
+  ctx->db_ws_n = -1;  // stays invalid if any launch below fails
   VPC_LAUNCH(ctx, k_db_bounds, gstride, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_hist, gpts, kDbBlock, s, a);
-  VPC_LAUNCH(ctx, k_scan_exclusive, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0,
+  VPC_LAUNCH(ctx, k_scan_exclusive<false>, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0,
              a.tile_state0, &a.ctrl->scan_counter[0], &a.ctrl->n_valid);
   VPC_LAUNCH(ctx, k_db_scatter, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_count, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_union, gpts, kDbBlock, s, a);
+  VPC_LAUNCH(ctx, k_db_flatten, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
-  VPC_LAUNCH(ctx, k_scan_exclusive, tiles1, kScanBlock, s, a.flag, a.rank, (const int*)nullptr, ni, a.tile_state1,
+  VPC_LAUNCH(ctx, k_scan_exclusive<true>, tiles1, kScanBlock, s, a.compkey, a.rank, (const int*)nullptr, ni, a.tile_state1,
              &a.ctrl->scan_counter[1], &a.ctrl->n_roots);
   VPC_LAUNCH(ctx, k_db_label, gpts, kDbBlock, s, a);
+  ctx->db_ws_n = n;
   return VPC_OK;
 }
 
@@ -205,7 +218,7 @@ int icp_set_model(vpc_ctx* ctx, const double* d_model, int64_t m, cudaStream_t s
   VPC_LAUNCH(ctx, k_icp_model_init, std::min(blocks_for((long long)cell_cap + 1, 256), ctx->sm_count * 16), 256, s, g);
   VPC_LAUNCH(ctx, k_icp_model_bounds, std::min(gpts, ctx->sm_count * 8), 256, s, g);
   VPC_LAUNCH(ctx, k_icp_model_hist, gpts, 256, s, g);
-  VPC_LAUNCH(ctx, k_scan_exclusive, tiles, kScanBlock, s, g.cell_count, g.cell_start, &g.ctrl->ncells_p1, 0, g.tile_state,
+  VPC_LAUNCH(ctx, k_scan_exclusive<false>, tiles, kScanBlock, s, g.cell_count, g.cell_start, &g.ctrl->ncells_p1, 0, g.tile_state,
              &g.ctrl->scan_counter, (int*)nullptr);
   VPC_LAUNCH(ctx, k_icp_model_scatter, gpts, 256, s, g);
   ctx->model = g;
@@ -214,10 +227,11 @@ int icp_set_model(vpc_ctx* ctx, const double* d_model, int64_t m, cudaStream_t s
 }
 
 int icp_reserve_work(vpc_ctx* ctx, int64_t n) {
-  const int nb = blocks_for(n, kIcpBlock);
+  const int nb = blocks_for(n, kIterBlock);
   int rc = arena_reserve(ctx, ctx->icp_work, al256(8ull * kIcpSums * nb) + al256(12 * 8) + 1024);
   if (rc) return rc;
   ctx->icp_partial = ctx->icp_work.take<double>((size_t)kIcpSums * nb);
+  ctx->icp_ticket = ctx->icp_work.take<unsigned>(1);
   ctx->icp_partial_blocks = nb;
   return VPC_OK;
 }
@@ -227,8 +241,8 @@ int icp_enqueue_rounds(vpc_ctx* ctx, const double* d_data, int64_t n, double e, 
                        int32_t* d_order, cudaStream_t s) {
   const int nb = ctx->icp_partial_blocks;
   for (int r = 0; r < rounds; ++r) {
-    VPC_LAUNCH(ctx, k_icp_iter, nb, kIcpBlock, s, ctx->model, d_data, (int)n, ctx->icp_state, d_order, ctx->icp_partial);
-    VPC_LAUNCH(ctx, k_icp_solve, 1, kSolveBlock, s, ctx->icp_partial, nb, (int)n, e, max_iters, ctx->icp_state);
+    VPC_LAUNCH(ctx, k_icp_iter, nb, kIterBlock, s, ctx->model, d_data, (int)n, e, max_iters, ctx->icp_state, d_order,
+               ctx->icp_partial, ctx->icp_ticket);
   }
   return VPC_OK;
 }
@@ -390,7 +404,7 @@ int vpc_icp_rigid_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, double 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc = icp_reserve_work(ctx, n);
   if (rc) return rc;
-  VPC_LAUNCH(ctx, k_icp_state_init, 1, 32, s, ctx->icp_state, (const double*)nullptr, (const double*)nullptr);
+  VPC_LAUNCH(ctx, k_icp_state_init, 1, 32, s, ctx->icp_state, (const double*)nullptr, (const double*)nullptr, ctx->icp_ticket);
   rc = icp_enqueue_rounds(ctx, d_data_xyz, n, e, max_iters, max_iters, d_order_last, s);
   if (rc) return rc;
   VPC_LAUNCH(ctx, k_icp_state_export, 1, 32, s, ctx->icp_state, d_state_out);
@@ -451,7 +465,7 @@ int vpc_icp_rigid(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double
   if (rc) return rc;
   rc = icp_reserve_work(ctx, n);
   if (rc) return rc;
-  VPC_LAUNCH(ctx, k_icp_state_init, 1, 32, s, ctx->icp_state, (const double*)d_rt, (const double*)(d_rt + 9));
+  VPC_LAUNCH(ctx, k_icp_state_init, 1, 32, s, ctx->icp_state, (const double*)d_rt, (const double*)(d_rt + 9), ctx->icp_ticket);
   double out[16];
   if (max_iters > 0) {
     rc = icp_enqueue_rounds(ctx, d_data, n, e, max_iters, max_iters, d_order, s);
