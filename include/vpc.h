@@ -84,6 +84,26 @@ int vpc_dbscan_l1_2d_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, i
                          uint8_t* d_is_key, uint8_t* d_is_classed, int32_t* d_cluster_amount,
                          void* stream);
 
+/* Replaces the blocked ("\u5206\u5757") multithreaded clustering's worker phase: every
+ * ThreadPool.QueueUserWorkItem(StartCode, cell) of MainForm.DoWork3 (FrmMain.cs:1356-1359), each of
+ * which runs `new DBImproved().dbscan(cell, eps, minPts)` (StartCode, FrmMain.cs:2782-2794), in ONE
+ * batched launch.  The cells of MainForm.getClusterFromMotor (FrmMain.cs:1214-1291) are given in CSR
+ * form: cell k owns points [cell_offsets[k], cell_offsets[k+1]) of mx/my; cell_offsets[0] = 0,
+ * cell_offsets[n_cells] = n.  Points of different cells never interact (the reference has no halo);
+ * cluster ids are CELL-LOCAL 1..k like the C#'s per-cell DBImproved (cf starts at 0);
+ * cluster_amount_per_cell[k] = that cell's DBImproved.clusterAmount (nullable).  The reference's racy
+ * statics (sumPts, threadCount, clusterSum, FrmMain.cs:2787-2789) are not reproduced: sum the per-cell
+ * counts in the caller. */
+int vpc_dbscan_l1_2d_cells(vpc_ctx* ctx, const double* mx, const double* my, int64_t n,
+                           const int64_t* cell_offsets, int32_t n_cells, double eps, int32_t min_pts,
+                           int32_t* cluster_id, uint8_t* is_key, uint8_t* is_classed,
+                           int32_t* cluster_amount_per_cell);
+/* Device-pointer variant; d_cell_offsets is int32 on the device and is trusted to be monotone. */
+int vpc_dbscan_l1_2d_cells_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, int64_t n,
+                               const int32_t* d_cell_offsets, int32_t n_cells, double eps, int32_t min_pts,
+                               int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
+                               int32_t* d_cluster_amount_per_cell, void* stream);
+
 /* ---- ICP ------------------------------------------------------------------------ */
 
 /* Point sets are PLANAR: xyz = x[0..k) y[0..k) z[0..k) (one H2D copy, coalesced). */

@@ -122,3 +122,25 @@ def test_device_pointer_entry(ctx, oracle):
     np.testing.assert_array_equal(cid.cpu().numpy(), ocid)
     np.testing.assert_array_equal(key.cpu().numpy(), okey)
     np.testing.assert_array_equal(cls.cpu().numpy(), ocls)
+
+
+def test_cells_batched_matches_per_cell_oracle(ctx, oracle):
+    # all StartCode work items (FrmMain.cs:2782-2794) in one launch: independent clouds, cell-local ids
+    rng = np.random.default_rng(21)
+    sizes = [0, 300, 1, 0, 777, 64, 1500, 0]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(offs[-1])
+    # overlapping extents on purpose: points of different cells must never interact
+    mx = rng.uniform(0, 1.0, n)
+    my = rng.uniform(0, 1.0, n)
+    for eps, min_pts in ((0.05, 4), (0.03, 2), (0.08, 7)):
+        got, per_cell = ctx.dbscan_cells(mx, my, offs, eps, min_pts)
+        for k in range(len(sizes)):
+            a, b = int(offs[k]), int(offs[k + 1])
+            cid, key, cls, amount = oracle.dbscan(mx[a:b], my[a:b], eps, min_pts, 0, variant="literal")
+            np.testing.assert_array_equal(got.cluster_id[a:b], cid)
+            np.testing.assert_array_equal(got.is_key[a:b], key)
+            np.testing.assert_array_equal(got.is_classed[a:b], cls)
+            assert per_cell[k] == amount
+    with pytest.raises(Exception):
+        ctx.dbscan_cells(mx, my, np.array([0, 5, 3, n]), 0.05, 4)

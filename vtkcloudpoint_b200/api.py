@@ -124,6 +124,20 @@ class Context:
         out.cluster_amount = int(amount.value)
         return out
 
+    def dbscan_cells(self, mx, my, cell_offsets, eps: float, min_pts: int):
+        """Batched per-cell DBSCAN (all StartCode work items of the blocked clustering in one launch).
+        Returns (DbscanResult with cell-local ids and cluster_amount = sum, cluster_amount_per_cell int32[n_cells])."""
+        mx = np.ascontiguousarray(mx, dtype=np.float64)
+        my = np.ascontiguousarray(my, dtype=np.float64)
+        off = np.ascontiguousarray(cell_offsets, dtype=np.int64)
+        n, n_cells = mx.shape[0], off.shape[0] - 1
+        out = DbscanResult(np.empty(n, np.int32), np.empty(n, np.uint8), np.empty(n, np.uint8), 0)
+        per_cell = np.zeros(max(n_cells, 0), np.int32)
+        self._check(self._lib.vpc_dbscan_l1_2d_cells(self._h, _ptr(mx), _ptr(my), n, _ptr(off), n_cells, float(eps), int(min_pts),
+                                                     _ptr(out.cluster_id), _ptr(out.is_key), _ptr(out.is_classed), _ptr(per_cell)))
+        out.cluster_amount = int(per_cell.sum())
+        return out, per_cell
+
     # ------------------------------------------------------------------ DBSCAN, device tensors
     def dbscan_dev(self, mx, my, eps: float, min_pts: int, first_cluster_id: int = 0, out=None):
         """mx, my: float64 CUDA tensors.  Returns (cluster_id i32, is_key u8, is_classed u8, amount i32[1]) tensors.

@@ -31,6 +31,8 @@ SIGNATURES = {
     "vpc_profile_report": (_i64, [_p, C.c_char_p, _i64]),
     "vpc_dbscan_l1_2d": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p]),
     "vpc_dbscan_l1_2d_dev": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p, _p]),
+    "vpc_dbscan_l1_2d_cells": (C.c_int, [_p, _p, _p, _i64, _p, _i32, _f64, _i32, _p, _p, _p, _p]),
+    "vpc_dbscan_l1_2d_cells_dev": (C.c_int, [_p, _p, _p, _i64, _p, _i32, _f64, _i32, _p, _p, _p, _p, _p]),
     "vpc_closest_point_set": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p]),
     "vpc_icp_rigid": (C.c_int, [_p, _p, _i64, _p, _i64, _f64, _i32, _p, _p, _p, _p, _p]),
     "vpc_icp_set_model_dev": (C.c_int, [_p, _p, _i64, _p]),

@@ -60,6 +60,13 @@ struct DbArgs {
   int* sidx;         // [n]  original index of sorted position
   unsigned char* core;  // [n] by sorted position
   int* parent;       // [n]  union-find over sorted positions
+  // segmented mode (vpc_dbscan_l1_2d_cells): independent clouds in one launch, points of a segment are
+  // contiguous in the input (CSR offsets); neighbours must share the segment, ids are segment-local
+  const int* seg_off;   // [n_seg+1] device, nullptr = one cloud
+  int n_seg;
+  int* segof;           // [n] segment of original point i
+  int* sseg;            // [n] segment of sorted position
+  int* seg_amount;      // [n_seg] out: clusters per segment (nullable)
   int2* cinfo;       // [n]  .x at a cell's first slot: first core position of the cell; .y at a root: min original index
   int* compkey;      // [n]  by ORIGINAL index: min original core index of the point's cluster, -1 = noise
   int* rank;         // [n]  exclusive scan of (compkey[i] == i)
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
   }
   c->u0 = u0; c->v0 = v0; c->h = h; c->inv_h = 1.0 / h; c->E = E;
   c->ncu = ncu; c->ncv = ncv; c->ncells = ncu * ncv; c->ncells_p1 = ncu * ncv + 1;
-  c->clique = clique;
+  c->clique = (a.seg_off != nullptr) ? 0 : clique;   // cells may mix segments: test every pair
 }
 
 // cell coordinate of a (possibly out-of-box) u or v value; monotone non-decreasing in t
@@ -186,6 +193,11 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
   if (i >= a.n) return;
   const DbCtrl c = *a.ctrl;
   const double x = __ldg(a.x + i), y = __ldg(a.y + i);
+  if (a.seg_off) {   // largest s with seg_off[s] <= i
+    int lo = 0, hi = a.n_seg;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(a.seg_off + mid) <= (int)i) lo = mid; else hi = mid; }
+    a.segof[i] = lo;
+  }
   if (db_valid(x, y, a.eps >= 0.0)) {
     const int cu = db_cell1(x + y, c.u0, c.inv_h, c.ncu);
     const int cv = db_cell1(x - y, c.v0, c.inv_h, c.ncv);
@@ -212,6 +224,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
   const int pos = a.cell_start[key] + atomicSub(&a.cell_count[key], 1) - 1;
   a.sxy[pos] = make_double2(__ldg(a.x + i), __ldg(a.y + i));
   a.sidx[pos] = (int)i;
+  if (a.seg_off) a.sseg[pos] = a.segof[i];
   a.cinfo[pos] = make_int2(0x7fffffff, 0x7fffffff);   // {first core position of the cell, min original index of the component}
 }
 
@@ -239,7 +252,8 @@ __device__ __forceinline__ DbStencil db_stencil(const DbCtrl& c, double2 p) {
 }
 
 // number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight
-__device__ __forceinline__ int db_count_range(const double2* __restrict__ sxy, int j0, int j1, int s, int e, double2 me, double eps) {
+__device__ __forceinline__ int db_count_range(const double2* __restrict__ sxy, int j0, int j1, int s, int e, double2 me, double eps,
+                                              const int* __restrict__ sseg, int myseg) {
   int cnt = 0;
   for (int j = j0; j < j1; j += 4) {
     double2 q[4];
@@ -248,7 +262,7 @@ __device__ __forceinline__ int db_count_range(const double2* __restrict__ sxy, i
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int jj = j + k;
-      cnt += (jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps)) ? 1 : 0;
+      cnt += (jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj] == myseg)) ? 1 : 0;
     }
   }
   return cnt;
@@ -264,6 +278,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
   const int need = a.min_pts;
   const int own = st.cv * c.ncu + st.cu;
   const int s = __ldg(a.cell_start + own), e = __ldg(a.cell_start + own + 1);
+  const int myseg = a.seg_off ? a.sseg[p] : 0;
   int cnt = 0, par = p;
   bool dense = false;
   int es = 0, ee = 0;                  // range excluded from the tests because it is already counted
@@ -284,7 +299,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        if (cnt < need) cnt += db_count_range(a.sxy, j0[r], j1[r], es, ee, me, a.eps);
+        if (cnt < need) cnt += db_count_range(a.sxy, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg);
     }
   }
   const bool core = cnt >= need;       // only 'count >= minPts' matters (:47)
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
       const int j0 = __ldg(a.cell_start + row * c.ncu + st.ulo);
       const int j1 = min(__ldg(a.cell_start + row * c.ncu + st.uhi + 1), p);  // each edge once: partners before p
       for (int j = j0; j < j1; ++j) {
-        if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) {
+        if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p])) {
           const int rj = uf_find(a.parent, j);
           if (rj != rp) rp = uf_unite_roots(a.parent, rp, rj);
         }
@@ -431,7 +446,8 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
       } else {
         const int j0 = __ldg(a.cell_start + base + st.ulo), j1 = __ldg(a.cell_start + base + st.uhi + 1);
         for (int j = j0; j < j1; ++j)
-          if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) key = max(key, a.cinfo[a.parent[j]].y);
+          if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p]))
+            key = max(key, a.cinfo[a.parent[j]].y);
       }
     }
     a.is_key[me_i] = 0;
@@ -445,7 +461,16 @@ __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
   if (i == 0 && a.cluster_amount) *a.cluster_amount = a.first_cluster_id + a.ctrl->n_roots;  // :112
   if (i >= a.n) return;
   const int key = a.compkey[i];
-  a.cluster_id[i] = (key < 0) ? 0 : a.first_cluster_id + 1 + __ldg(a.rank + key);
+  int base = a.first_cluster_id;
+  if (a.seg_off) {
+    // ids restart in every segment (each StartCode work item owns a fresh DBImproved, FrmMain.cs:2785)
+    const int sg = a.segof[i];
+    const int o0 = __ldg(a.seg_off + sg), o1 = __ldg(a.seg_off + sg + 1);
+    const int r0 = (o0 < a.n) ? __ldg(a.rank + o0) : a.ctrl->n_roots;
+    base = -r0;
+    if (a.seg_amount && i == o0) a.seg_amount[sg] = ((o1 < a.n) ? __ldg(a.rank + o1) : a.ctrl->n_roots) - r0;
+  }
+  a.cluster_id[i] = (key < 0) ? 0 : base + 1 + __ldg(a.rank + key);
   // isClassed is set when a point is taken from a nei list (:65); a point outside the grid is in nobody's list
   a.is_classed[i] = (key >= 0 && a.cellkey[i] >= 0) ? 1 : 0;
 }

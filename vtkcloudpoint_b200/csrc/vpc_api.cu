@@ -124,14 +124,15 @@ inline int blocks_for(long long n, int block) { return (int)std::max<long long>(
 // ---------------------------------------------------------------------------------------
 int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, double eps, int32_t min_pts,
                    int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
-                   int32_t* d_cluster_amount, cudaStream_t s) {
+                   int32_t* d_cluster_amount, cudaStream_t s, const int32_t* d_seg_off = nullptr, int32_t n_seg = 0,
+                   int32_t* d_seg_amount = nullptr) {
   const int ni = (int)n;
   // (u, v) cells of side ~eps: about 4 x (bounding area / eps^2); 8 per point covers clustered clouds,
   // anything sparser is coarsened on the device (exactness is unaffected).
   const long long cap_ll = std::min<long long>(8ll * n + 4096, 2147483000ll);
   const int cell_cap = (int)cap_ll;
   const int tiles0 = scan_tiles((long long)cell_cap + 1), tiles1 = scan_tiles(std::max<long long>(n, 1));
-  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * 5 + al256(8ull * n) + al256(4ull * (cell_cap + 1ull)) * 2 + al256(16ull * n) +
+  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * (d_seg_off ? 7 : 5) + al256(8ull * n) + al256(4ull * (cell_cap + 1ull)) * 2 + al256(16ull * n) +
                  al256((size_t)n) + al256(8ull * tiles0) + al256(8ull * tiles1) + 4096;
   const char* base_before = ctx->db.base;
   int rc = arena_reserve(ctx, ctx->db, bytes);
@@ -151,6 +152,8 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   a.cinfo = w.take<int2>(n);
   a.compkey = w.take<int>(n);
   a.rank = w.take<int>(n);
+  a.seg_off = d_seg_off; a.n_seg = n_seg; a.seg_amount = d_seg_amount;
+  if (d_seg_off) { a.segof = w.take<int>(n); a.sseg = w.take<int>(n); }
   a.tile_state0 = w.take<unsigned long long>(tiles0);
   a.tile_state1 = w.take<unsigned long long>(tiles1);
   a.tiles0 = tiles0; a.tiles1 = tiles1;
@@ -160,6 +163,7 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   const int gstride = std::min(gpts, ctx->sm_count * 8);
   // The control block and the cell counters clean up after themselves (k_db_bounds / k_db_scatter); they
   // are initialised only when the workspace is new or its layout (n) changed.
+  if (d_seg_off && d_seg_amount) VPC_CUDA(ctx, cudaMemsetAsync(d_seg_amount, 0, 4ull * n_seg, s));
   if (base_before != ctx->db.base || ctx->db_ws_n != n) {
     ctx->db_ws_n = -1;
     VPC_LAUNCH(ctx, k_db_ws_init, std::min(blocks_for((long long)cell_cap + 1, kDbBlock), ctx->sm_count * 16), kDbBlock, s, a);
@@ -366,6 +370,69 @@ int vpc_dbscan_l1_2d(vpc_ctx* ctx, const double* mx, const double* my, int64_t n
   VPC_CUDA(ctx, cudaMemcpyAsync(&amount, d_amount, 4, cudaMemcpyDeviceToHost, s));
   VPC_CUDA(ctx, cudaStreamSynchronize(s));
   if (cluster_amount) *cluster_amount = amount;
+  return VPC_OK;
+}
+
+int vpc_dbscan_l1_2d_cells_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, int64_t n, const int32_t* d_cell_offsets,
+                               int32_t n_cells, double eps, int32_t min_pts, int32_t* d_cluster_id, uint8_t* d_is_key,
+                               uint8_t* d_is_classed, int32_t* d_cluster_amount_per_cell, void* stream) {
+  int rc = dbscan_check(ctx, d_mx, d_my, n, eps, d_cluster_id, d_is_key, d_is_classed);
+  if (rc) return rc;
+  if (n_cells <= 0 || !d_cell_offsets) return fail(ctx, VPC_E_BADARG, "cell_offsets must hold n_cells + 1 >= 2 entries");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  if (n == 0) {
+    if (d_cluster_amount_per_cell) VPC_CUDA(ctx, cudaMemsetAsync(d_cluster_amount_per_cell, 0, 4ull * n_cells, static_cast<cudaStream_t>(stream)));
+    return VPC_OK;
+  }
+  // the segmented layout needs its own workspace initialisation: arrays move
+  ctx->db_ws_n = -1;
+  rc = dbscan_enqueue(ctx, d_mx, d_my, n, eps, min_pts, 0, d_cluster_id, d_is_key, d_is_classed, nullptr,
+                      static_cast<cudaStream_t>(stream), d_cell_offsets, n_cells, d_cluster_amount_per_cell);
+  ctx->db_ws_n = -1;
+  return rc;
+}
+
+int vpc_dbscan_l1_2d_cells(vpc_ctx* ctx, const double* mx, const double* my, int64_t n, const int64_t* cell_offsets,
+                           int32_t n_cells, double eps, int32_t min_pts, int32_t* cluster_id, uint8_t* is_key,
+                           uint8_t* is_classed, int32_t* cluster_amount_per_cell) {
+  int rc = dbscan_check(ctx, mx, my, n, eps, cluster_id, is_key, is_classed);
+  if (rc) return rc;
+  if (n_cells <= 0 || !cell_offsets) return fail(ctx, VPC_E_BADARG, "cell_offsets must hold n_cells + 1 >= 2 entries");
+  if (cell_offsets[0] != 0 || cell_offsets[n_cells] != n) return fail(ctx, VPC_E_BADARG, "cell_offsets must run from 0 to n");
+  std::vector<int32_t> off(n_cells + 1);
+  for (int32_t k = 0; k <= n_cells; ++k) {
+    if (k > 0 && cell_offsets[k] < cell_offsets[k - 1]) return fail(ctx, VPC_E_BADARG, "cell_offsets must be non-decreasing");
+    off[k] = (int32_t)cell_offsets[k];
+  }
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  if (n == 0) {
+    if (cluster_amount_per_cell) std::memset(cluster_amount_per_cell, 0, 4ull * n_cells);
+    return VPC_OK;
+  }
+  cudaStream_t s = ctx->own_stream;
+  rc = arena_reserve(ctx, ctx->io, al256(8ull * n) * 2 + al256(4ull * n) + al256((size_t)n) * 2 + al256(4ull * (n_cells + 1)) * 2 + 1024);
+  if (rc) return rc;
+  double* d_x = ctx->io.take<double>(n);
+  double* d_y = ctx->io.take<double>(n);
+  int* d_cid = ctx->io.take<int>(n);
+  unsigned char* d_key = ctx->io.take<unsigned char>(n);
+  unsigned char* d_cls = ctx->io.take<unsigned char>(n);
+  int* d_off = ctx->io.take<int>(n_cells + 1);
+  int* d_amt = ctx->io.take<int>(n_cells);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_x, mx, 8ull * n, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_y, my, 8ull * n, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), 4ull * (n_cells + 1), cudaMemcpyHostToDevice, s));
+  ctx->db_ws_n = -1;
+  rc = dbscan_enqueue(ctx, d_x, d_y, n, eps, min_pts, 0, d_cid, d_key, d_cls, nullptr, s, d_off, n_cells, d_amt);
+  ctx->db_ws_n = -1;
+  if (rc) return rc;
+  VPC_CUDA(ctx, cudaMemcpyAsync(cluster_id, d_cid, 4ull * n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(is_key, d_key, (size_t)n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(is_classed, d_cls, (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (cluster_amount_per_cell) VPC_CUDA(ctx, cudaMemcpyAsync(cluster_amount_per_cell, d_amt, 4ull * n_cells, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));   // also keeps `off` alive until the copy has been consumed
   return VPC_OK;
 }
 
