@@ -104,6 +104,29 @@ int vpc_dbscan_l1_2d_cells_dev(vpc_ctx* ctx, const double* d_mx, const double* d
                                int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
                                int32_t* d_cluster_amount_per_cell, void* stream);
 
+/* ---- DBSCAN across GPUs: one spatial slab per GPU, one process per GPU --------------------------
+ * (no counterpart in the reference, which has no halo and re-joins split clusters heuristically,
+ * FrmMain.cs:1507-1516; this is the exact replacement)  The exchange of slab + halo
+ * points and of the boundary component keys is done by the caller (vtkcloudpoint_b200/distributed.py
+ * over torch.distributed / NCCL); these three calls are the per-GPU compute between the exchanges.
+ *
+ * vpc_dbscan_slab_local_dev: DBSCAN of the local points (owned + 2*eps halo).  d_gidx[i] is the
+ *   GLOBAL index of local point i.  Outputs per local point: d_is_key (core flag as seen locally;
+ *   exact for points at least eps inside the received region) and d_local_key = the minimum global
+ *   index over the core points of its LOCAL component, -1 for non-core points.  The workspace is kept.
+ * vpc_dbscan_slab_finish_dev: must follow it on the same context.  (d_map_from ascending, d_map_to)
+ *   maps local component keys to merged global keys; every local point then gets d_key_out = key of
+ *   its cluster (core: its component; non-core: the LARGEST key among core points within eps -- the
+ *   reference's last-writer-wins rule, DBImproved.cs:87; -1 = noise).
+ * vpc_uf_edges_dev: connected components of an edge list over nodes 0..n_nodes-1 (lock-free
+ *   union-find); d_root[i] = smallest node id of i's component.  Used for the cross-slab merge. */
+int vpc_dbscan_slab_local_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, const int32_t* d_gidx, int64_t n,
+                              double eps, int32_t min_pts, uint8_t* d_is_key, int32_t* d_local_key, void* stream);
+int vpc_dbscan_slab_finish_dev(vpc_ctx* ctx, const int32_t* d_map_from, const int32_t* d_map_to, int64_t n_map,
+                               int32_t* d_key_out, void* stream);
+int vpc_uf_edges_dev(vpc_ctx* ctx, const int32_t* d_a, const int32_t* d_b, int64_t n_edges, int64_t n_nodes,
+                     int32_t* d_root, void* stream);
+
 /* ---- ICP ------------------------------------------------------------------------ */
 
 /* Point sets are PLANAR: xyz = x[0..k) y[0..k) z[0..k) (one H2D copy, coalesced). */

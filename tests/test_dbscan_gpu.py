@@ -144,3 +144,32 @@ def test_cells_batched_matches_per_cell_oracle(ctx, oracle):
             assert per_cell[k] == amount
     with pytest.raises(Exception):
         ctx.dbscan_cells(mx, my, np.array([0, 5, 3, n]), 0.05, 4)
+
+
+def test_slab_kernels_single_rank(ctx, oracle):
+    # the slab-mode exports (local keys -> merge table -> finish) through the distributed driver at world size 1
+    import torch
+    from vtkcloudpoint_b200.distributed import GpuBackend, dbscan_slabs
+    mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000)
+    cid, key, cls, amount = dbscan_slabs(GpuBackend(ctx), torch.from_numpy(mx).cuda(), torch.from_numpy(my).cuda(), 0, 0.07, 7, 11)
+    ocid, okey, ocls, oamount = oracle.dbscan(mx, my, 0.07, 7, 11)
+    assert amount == oamount
+    np.testing.assert_array_equal(cid.cpu().numpy(), ocid)
+    np.testing.assert_array_equal(key.cpu().numpy(), okey)
+    np.testing.assert_array_equal(cls.cpu().numpy(), ocls)
+
+
+def test_uf_edges(ctx):
+    import torch
+    from vtkcloudpoint_b200.distributed import GpuBackend
+    rng = np.random.default_rng(5)
+    n_nodes, n_edges = 5000, 4000
+    a = rng.integers(0, n_nodes, n_edges).astype(np.int32)
+    b = rng.integers(0, n_nodes, n_edges).astype(np.int32)
+    root = GpuBackend(ctx).uf_edges(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), n_nodes).cpu().numpy()
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    _, lab = connected_components(coo_matrix((np.ones(n_edges), (a, b)), shape=(n_nodes, n_nodes)), directed=False)
+    mins = np.full(lab.max() + 1, n_nodes)
+    np.minimum.at(mins, lab, np.arange(n_nodes))
+    np.testing.assert_array_equal(root, mins[lab])

@@ -67,6 +67,8 @@ struct DbArgs {
   int* segof;           // [n] segment of original point i
   int* sseg;            // [n] segment of sorted position
   int* seg_amount;      // [n_seg] out: clusters per segment (nullable)
+  // distributed mode: component keys are minima of GLOBAL point indices (gidx[i] of local point i)
+  const int* gidx;      // [n] device, nullptr = the local index
   int2* cinfo;       // [n]  .x at a cell's first slot: first core position of the cell; .y at a root: min original index
   int* compkey;      // [n]  by ORIGINAL index: min original core index of the point's cluster, -1 = noise
   int* rank;         // [n]  exclusive scan of (compkey[i] == i)
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
     a.cellkey[i] = -1;
     const bool key_pt = (0 >= a.min_pts);
     a.is_key[i] = key_pt ? 1 : 0;
-    a.compkey[i] = key_pt ? (int)i : -1;
+    a.compkey[i] = key_pt ? (a.gidx ? __ldg(a.gidx + i) : (int)i) : -1;
   }
 }
 
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_flatten(DbArgs a) {
     root = uf_find_ro(a.parent, p);
     a.parent[p] = root;                    // readers racing with this store still see an ancestor
     orig = __ldg(a.sidx + p);
+    if (a.gidx) orig = __ldg(a.gidx + orig);
   }
   // neighbours in sorted order mostly share a root: one atomic per distinct root per warp
   const unsigned grp = __match_any_sync(kFull, root);
@@ -473,6 +476,44 @@ __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
   a.cluster_id[i] = (key < 0) ? 0 : base + 1 + __ldg(a.rank + key);
   // isClassed is set when a point is taken from a nei list (:65); a point outside the grid is in nobody's list
   a.is_classed[i] = (key >= 0 && a.cellkey[i] >= 0) ? 1 : 0;
+}
+
+// ---- distributed mode (one slab per GPU, vtkcloudpoint_b200/distributed.py) ----------------------
+// after k_db_flatten: per local point, its core flag and the key of its LOCAL component
+__global__ void __launch_bounds__(kDbBlock) k_db_export_core(DbArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.ctrl->n_valid) return;
+  const int i = a.sidx[p];
+  const bool core = a.core[p] != 0;
+  a.is_key[i] = core ? 1 : 0;
+  a.compkey[i] = core ? a.cinfo[a.parent[p]].y : -1;
+}
+
+// after the cross-slab merge: every local root whose key is in the (sorted) table takes the merged key
+__global__ void __launch_bounds__(kDbBlock)
+k_db_remap_roots(DbArgs a, const int* __restrict__ map_from, const int* __restrict__ map_to, int n_map) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.ctrl->n_valid || !a.core[p] || a.parent[p] != p) return;
+  const int key = a.cinfo[p].y;
+  int lo = 0, hi = n_map;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(map_from + mid) < key) lo = mid + 1; else hi = mid; }
+  if (lo < n_map && __ldg(map_from + lo) == key) a.cinfo[p].y = __ldg(map_to + lo);
+}
+
+// ---- union-find over an explicit edge list (cross-slab component merge); root = smallest node id ----
+__global__ void __launch_bounds__(kDbBlock) k_uf_init(int* parent, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) parent[i] = i;
+}
+__global__ void __launch_bounds__(kDbBlock) k_uf_edges(int* parent, const int* __restrict__ ea, const int* __restrict__ eb, int n_edges) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_edges) return;
+  const int x = __ldg(ea + i), y = __ldg(eb + i);
+  if (x != y) uf_unite_roots(parent, uf_find(parent, x), uf_find(parent, y));
+}
+__global__ void __launch_bounds__(kDbBlock) k_uf_flatten(int* parent, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int r = uf_find_ro(parent, i); parent[i] = r; }
 }
 
 }  // namespace vpc

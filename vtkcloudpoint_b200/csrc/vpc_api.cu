@@ -57,6 +57,8 @@ struct vpc_ctx {
   unsigned* icp_ticket = nullptr;
   int icp_partial_blocks = 0;
   int sm_count = 148;
+  DbArgs db_slab{};       // arguments of the last vpc_dbscan_slab_local_dev, for ..._finish_dev
+  bool db_slab_valid = false;
   int64_t db_ws_n = -1;  // n the DBSCAN workspace is currently laid out and initialised for
   // optional per-kernel CUDA-event timing (bench.py's roofline leg)
   bool profile = false;
@@ -125,8 +127,9 @@ inline int blocks_for(long long n, int block) { return (int)std::max<long long>(
 int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, double eps, int32_t min_pts,
                    int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
                    int32_t* d_cluster_amount, cudaStream_t s, const int32_t* d_seg_off = nullptr, int32_t n_seg = 0,
-                   int32_t* d_seg_amount = nullptr) {
+                   int32_t* d_seg_amount = nullptr, const int32_t* d_gidx = nullptr, int32_t* d_local_keys = nullptr) {
   const int ni = (int)n;
+  ctx->db_slab_valid = false;
   // (u, v) cells of side ~eps: about 4 x (bounding area / eps^2); 8 per point covers clustered clouds,
   // anything sparser is coarsened on the device (exactness is unaffected).
   const long long cap_ll = std::min<long long>(8ll * n + 4096, 2147483000ll);
@@ -153,6 +156,8 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   a.compkey = w.take<int>(n);
   a.rank = w.take<int>(n);
   a.seg_off = d_seg_off; a.n_seg = n_seg; a.seg_amount = d_seg_amount;
+  a.gidx = d_gidx;
+  if (d_local_keys) a.compkey = d_local_keys;   // distributed mode: keys go straight to the caller's array
   if (d_seg_off) { a.segof = w.take<int>(n); a.sseg = w.take<int>(n); }
   a.tile_state0 = w.take<unsigned long long>(tiles0);
   a.tile_state1 = w.take<unsigned long long>(tiles1);
@@ -177,6 +182,13 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   VPC_LAUNCH(ctx, k_db_count, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_union, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_flatten, gpts, kDbBlock, s, a);
+  if (d_local_keys) {   // slab phase 1 ends here; vpc_dbscan_slab_finish_dev continues from the kept workspace
+    VPC_LAUNCH(ctx, k_db_export_core, gpts, kDbBlock, s, a);
+    ctx->db_slab = a;
+    ctx->db_slab_valid = true;
+    ctx->db_ws_n = n;
+    return VPC_OK;
+  }
   VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_scan_exclusive<true>, tiles1, kScanBlock, s, a.compkey, a.rank, (const int*)nullptr, ni, a.tile_state1,
              &a.ctrl->scan_counter[1], &a.ctrl->n_roots);
@@ -433,6 +445,48 @@ int vpc_dbscan_l1_2d_cells(vpc_ctx* ctx, const double* mx, const double* my, int
   VPC_CUDA(ctx, cudaMemcpyAsync(is_classed, d_cls, (size_t)n, cudaMemcpyDeviceToHost, s));
   if (cluster_amount_per_cell) VPC_CUDA(ctx, cudaMemcpyAsync(cluster_amount_per_cell, d_amt, 4ull * n_cells, cudaMemcpyDeviceToHost, s));
   VPC_CUDA(ctx, cudaStreamSynchronize(s));   // also keeps `off` alive until the copy has been consumed
+  return VPC_OK;
+}
+
+int vpc_dbscan_slab_local_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, const int32_t* d_gidx, int64_t n, double eps,
+                              int32_t min_pts, uint8_t* d_is_key, int32_t* d_local_key, void* stream) {
+  int rc = dbscan_check(ctx, d_mx, d_my, n, eps, d_local_key, d_is_key, d_is_key);
+  if (rc) return rc;
+  if (n <= 0) return fail(ctx, VPC_E_BADARG, "a slab needs at least one point");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return dbscan_enqueue(ctx, d_mx, d_my, n, eps, min_pts, 0, nullptr, d_is_key, nullptr, nullptr, static_cast<cudaStream_t>(stream),
+                        nullptr, 0, nullptr, d_gidx, d_local_key);
+}
+
+int vpc_dbscan_slab_finish_dev(vpc_ctx* ctx, const int32_t* d_map_from, const int32_t* d_map_to, int64_t n_map, int32_t* d_key_out,
+                               void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n_map < 0 || (n_map > 0 && (!d_map_from || !d_map_to)) || !d_key_out) return fail(ctx, VPC_E_BADARG, "bad map/key_out");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->db_slab_valid) return fail(ctx, VPC_E_STATE, "vpc_dbscan_slab_local_dev must be the previous DBSCAN call on this context");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DbArgs a = ctx->db_slab;
+  a.compkey = d_key_out;
+  const int gpts = blocks_for(a.n, kDbBlock);
+  if (n_map > 0) VPC_LAUNCH(ctx, k_db_remap_roots, gpts, kDbBlock, s, a, d_map_from, d_map_to, (int)n_map);
+  VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
+  ctx->db_slab_valid = false;
+  return VPC_OK;
+}
+
+int vpc_uf_edges_dev(vpc_ctx* ctx, const int32_t* d_a, const int32_t* d_b, int64_t n_edges, int64_t n_nodes, int32_t* d_root, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n_nodes < 0 || n_edges < 0 || (n_nodes > 0 && !d_root) || (n_edges > 0 && (!d_a || !d_b))) return fail(ctx, VPC_E_BADARG, "bad edge list");
+  if (n_nodes > 2147483646ll || n_edges > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "edge list exceeds 2^31-2");
+  if (n_nodes == 0) return VPC_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VPC_LAUNCH(ctx, k_uf_init, blocks_for(n_nodes, kDbBlock), kDbBlock, s, d_root, (int)n_nodes);
+  if (n_edges > 0) VPC_LAUNCH(ctx, k_uf_edges, blocks_for(n_edges, kDbBlock), kDbBlock, s, d_root, d_a, d_b, (int)n_edges);
+  VPC_LAUNCH(ctx, k_uf_flatten, blocks_for(n_nodes, kDbBlock), kDbBlock, s, d_root, (int)n_nodes);
   return VPC_OK;
 }
 
