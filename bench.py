@@ -182,17 +182,46 @@ def run_ours(args):
     ctx = Context(local_rank)
     peak_gbs, peak_src = load_peaks()
 
-    # ---- inputs: every rank owns one C2-sized cloud (weak scaling; slab exchange is in distributed.py)
-    mx, my = synth.dbscan_cloud(0xC2 + 1000 * rank, DB_GRID, n_total=DB_N)
+    # ---- inputs.  N = 1: the C2 cloud.  N > 1 (weak scaling): ONE cloud of N x 1M points from the same recipe
+    # (grid scaled to keep the density), cut into N slabs of u = x + y holding ~1M points each -- rank r owns
+    # slab r ("generated per slab") -- and clustered EXACTLY across the GPUs: eps-halo
+    # exchange + cross-slab union-find merge over NCCL (vtkcloudpoint_b200/distributed.py).
+    gidx0, splitters = 0, None
+    if world == 1:
+        mx, my = synth.dbscan_cloud(0xC2, DB_GRID, n_total=DB_N)
+    else:
+        n_tot = world * DB_N
+        fx, fy = synth.dbscan_cloud(0xC2, int(round(DB_GRID * world ** 0.5)), n_total=n_tot)
+        fu = fx + fy
+        qs = np.quantile(fu, [j / world for j in range(1, world)])
+        band = np.searchsorted(qs, fu, side="right")
+        counts = np.bincount(band, minlength=world)
+        gidx0 = int(counts[:rank].sum())
+        mx, my = fx[band == rank].copy(), fy[band == rank].copy()
+        splitters = torch.from_numpy(np.asarray(qs, dtype=np.float64)).to(dev)
+        del fx, fy, fu, band
+    n_loc = len(mx)
+    n_all = n_loc
+    if world > 1:
+        t = torch.tensor([n_loc], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        n_all = int(t.item())
     h_x = torch.from_numpy(mx).pin_memory()
     h_y = torch.from_numpy(my).pin_memory()
     d_x, d_y = h_x.to(dev), h_y.to(dev)
-    out_dev = (torch.empty(DB_N, dtype=torch.int32, device=dev), torch.empty(DB_N, dtype=torch.uint8, device=dev),
-               torch.empty(DB_N, dtype=torch.uint8, device=dev), torch.empty(1, dtype=torch.int32, device=dev))
+    out_dev = (torch.empty(n_loc, dtype=torch.int32, device=dev), torch.empty(n_loc, dtype=torch.uint8, device=dev),
+               torch.empty(n_loc, dtype=torch.uint8, device=dev), torch.empty(1, dtype=torch.int32, device=dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    backend = None
+    if world > 1:
+        from vtkcloudpoint_b200.distributed import GpuBackend, dbscan_slabs
+        backend = GpuBackend(ctx)
 
     def step_dev():
-        ctx.dbscan_dev(d_x, d_y, EPS, MIN_PTS, 0, out=out_dev)
+        if world == 1:
+            ctx.dbscan_dev(d_x, d_y, EPS, MIN_PTS, 0, out=out_dev)
+        else:
+            dbscan_slabs(backend, d_x, d_y, gidx0, EPS, MIN_PTS, 0, splitters=splitters)
 
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
@@ -215,32 +244,46 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = ctx.launch_count - launches0
     dev_ms = max_over_ranks(dev_ms)
-    value = world * DB_N * args.steps / (dev_ms * 1e-3) / 1e6
+    value = n_all * args.steps / (dev_ms * 1e-3) / 1e6
 
-    # ---- e2e: host-pointer C ABI, pinned host buffers, H2D + D2H inside the timed region
+    # ---- e2e: HOST buffers (pinned) in, HOST results out; H2D + D2H inside the timed region.
+    # N = 1: the host-pointer C ABI call a P/Invoke user makes.  N > 1: the distributed driver fed from pinned memory.
     from vtkcloudpoint_b200 import DbscanResult
-    res = DbscanResult(torch.empty(DB_N, dtype=torch.int32).pin_memory().numpy(), torch.empty(DB_N, dtype=torch.uint8).pin_memory().numpy(),
-                       torch.empty(DB_N, dtype=torch.uint8).pin_memory().numpy(), 0)
+    res = DbscanResult(torch.empty(n_loc, dtype=torch.int32).pin_memory().numpy(), torch.empty(n_loc, dtype=torch.uint8).pin_memory().numpy(),
+                       torch.empty(n_loc, dtype=torch.uint8).pin_memory().numpy(), 0)
     hx_np, hy_np = h_x.numpy(), h_y.numpy()
+    r_cid, r_key, r_cls = torch.from_numpy(res.cluster_id), torch.from_numpy(res.is_key), torch.from_numpy(res.is_classed)
+
+    def step_e2e():
+        if world == 1:
+            ctx.dbscan(hx_np, hy_np, EPS, MIN_PTS, 0, out=res)
+        else:
+            tx, ty = h_x.to(dev, non_blocking=True), h_y.to(dev, non_blocking=True)
+            cid, key, cls, _ = dbscan_slabs(backend, tx, ty, gidx0, EPS, MIN_PTS, 0, splitters=splitters)
+            r_cid.copy_(cid, non_blocking=True); r_key.copy_(key, non_blocking=True); r_cls.copy_(cls, non_blocking=True)
+            torch.cuda.synchronize()
+
     for _ in range(3):
-        ctx.dbscan(hx_np, hy_np, EPS, MIN_PTS, 0, out=res)
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.dbscan(hx_np, hy_np, EPS, MIN_PTS, 0, out=res)
+        step_e2e()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     clocks = sampler.stop()
-    e2e_value = world * DB_N * args.steps / e2e_s / 1e6
+    e2e_value = n_all * args.steps / e2e_s / 1e6
 
     # ---- roofline: per-kernel CUDA-event times of the same step (separate profiled passes)
     roofline, kernels = None, {}
     if rank == 0:
         ctx.profile(True)
-        for _ in range(max(3, min(args.steps, 10))):
-            flush.zero_()
-            step_dev()
+    for _ in range(max(3, min(args.steps, 10))):     # every rank takes part (the multi-GPU step has collectives)
+        flush.zero_()
+        step_dev()
+    torch.cuda.synchronize()
+    if rank == 0:
         rep = ctx.profile_report()
         ctx.profile(False)
         agg = {}
@@ -251,11 +294,11 @@ def run_ours(args):
         step_ms = sum(per_step.values())
         top = max(per_step, key=per_step.get)
         top_launch_ms = sum(agg[top]) / len(agg[top])
-        units_per_launch = DB_N
+        units_per_launch = n_loc
         achieved = DB_ALGO_BYTES_PER_PT * units_per_launch / (top_launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                     "traffic": None, "peak_source": peak_src, "kernel_ms": top_launch_ms, "kernel_share_of_step": per_step[top] / step_ms,
-                    "pipeline_frac": DB_ALGO_BYTES_PER_PT * DB_N / (dev_ms / args.steps * 1e-3) / 1e9 / peak_gbs}
+                    "pipeline_frac": DB_ALGO_BYTES_PER_PT * n_all / (dev_ms / args.steps * 1e-3) / 1e9 / (peak_gbs * world)}
         kernels = {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}
 
     # ---- secondary metric: ICP iters/s (C3), rank 0 only
@@ -309,10 +352,13 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7",
-                       "points_per_gpu": DB_N, "parallelism": "1 cloud per GPU" if world > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB write)",
+            "config": {"workload": ("C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7"
+                                    if world == 1 else
+                                    f"C2 recipe scaled to {n_all} points (1M per GPU), one cloud clustered exactly across {world} GPUs: u-slabs + 2*eps halo exchange + cross-slab union-find merge (NCCL)"),
+                       "points_total": n_all, "points_per_gpu": DB_N, "parallelism": f"{world} spatial slabs, one process per GPU" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB write)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * DB_N, "d2h_bytes_per_step": 6 * DB_N + 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_all, "d2h_bytes_per_step": 6 * n_all + 4 * (world == 1),
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -322,6 +368,7 @@ def run_ours(args):
             "kernel_ms_per_step": kernels,
         }
         print(json.dumps(line), flush=True)
+    barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

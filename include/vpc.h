@@ -165,6 +165,29 @@ int vpc_closest_point_set_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n,
 int vpc_icp_rigid_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, double e, int32_t max_iters,
                       double* d_state_out, int32_t* d_order_last, void* stream);
 
+/* ---- ICP across GPUs: the model is sharded (one shard per GPU, vpc_icp_set_model_dev on each), the
+ * data is replicated.  One round of ICP.go_hell_ICP (ICP.cs:23-180) becomes
+ *   vpc_icp_shard_nn_dev          local nearest model point: d2[i], idx[i] = local index + idx_offset
+ *   all_reduce(MIN) on d2         (caller, NCCL)
+ *   vpc_icp_shard_select_dev      idx[i] = INT32_MAX unless this shard holds the global minimum
+ *   all_reduce(MIN) on idx        exact argmin, ties -> lowest global index (ICP.cs:240)
+ *   vpc_icp_shard_accumulate_dev  16 sums {P, Y, P Y^T, |P-Y|^2} over the points this shard won
+ *   all_reduce(SUM) on the sums
+ *   vpc_icp_shard_solve_dev       replicated quaternion solve / compose / convergence test; state_out
+ *                                 (nullable) as in vpc_icp_rigid_dev.
+ * vpc_icp_shard_begin_dev resets the state (round 0, R/T untouched).  Once the state has converged or
+ * reached max_iters every step is a no-op, so a fixed number of rounds can be enqueued without reading
+ * the state back.  Inputs must be finite. */
+int vpc_icp_shard_begin_dev(vpc_ctx* ctx, int64_t n, void* stream);
+int vpc_icp_shard_nn_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, int32_t idx_offset, double* d_d2,
+                         int32_t* d_idx, void* stream);
+int vpc_icp_shard_select_dev(vpc_ctx* ctx, int64_t n, const double* d_d2_local, const double* d_d2_global,
+                             int32_t* d_idx, void* stream);
+int vpc_icp_shard_accumulate_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, const int32_t* d_idx_global,
+                                 int32_t idx_offset, double* d_sums16, void* stream);
+int vpc_icp_shard_solve_dev(vpc_ctx* ctx, const double* d_sums16, int64_t n, double e, int32_t max_iters,
+                            double* d_state_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,3 +43,76 @@ class CpuCheckerBackend:
         mins = np.full(lab.max() + 1, n_nodes, np.int64)
         np.minimum.at(mins, lab, np.arange(n_nodes))
         return torch.from_numpy(mins[lab].astype(np.int32))
+
+
+class CpuCheckerIcpBackend:
+    """Checker-backed stand-in for distributed.GpuIcpBackend (oracle NN search + NumPy solve)."""
+
+    def set_model(self, model_planar):
+        self.model = model_planar.numpy().copy()
+
+    def begin(self, data_planar):
+        self.n = data_planar.shape[1]
+        self.R, self.T, self.have_rt = np.zeros((3, 3)), np.zeros(3), False
+        self.round, self.done, self.converged, self.d = 0, False, False, 0.0
+        self.d2 = torch.zeros(self.n, dtype=torch.float64)
+        self.d2g = torch.zeros(self.n, dtype=torch.float64)
+        self.idx = torch.zeros(self.n, dtype=torch.int32)
+        self.sums = torch.zeros(16, dtype=torch.float64)
+
+    def _P(self, data_planar):
+        d = data_planar.numpy()
+        return oracle_py.trans_points(d, self.R, self.T) if self.have_rt else d.copy()
+
+    def nn(self, data_planar, idx_offset):
+        if not self.done:
+            order, sq = oracle_py.closest_point_set(self.model, self._P(data_planar), "grid")
+            self.d2.copy_(torch.from_numpy(sq))
+            self.idx.copy_(torch.from_numpy(order + idx_offset))
+        return self.d2, self.idx
+
+    def select(self, d2_local, d2_global, idx):
+        if not self.done:
+            idx[d2_local != d2_global] = np.iinfo(np.int32).max
+
+    def accumulate(self, data_planar, idx_global, idx_offset):
+        if not self.done:
+            j = idx_global.numpy().astype(np.int64) - idx_offset
+            mine = (j >= 0) & (j < self.model.shape[1])
+            P, Y = self._P(data_planar)[:, mine], self.model[:, j[mine]]
+            s = np.concatenate([P.sum(1), Y.sum(1), (P[:, None, :] * Y[None, :, :]).sum(2).ravel(), [((P - Y) ** 2).sum()]])
+            self.sums.copy_(torch.from_numpy(s))
+        return self.sums
+
+    def solve(self, sums, e, max_iters):
+        if not self.done:
+            S, N = sums.numpy(), float(self.n)
+            mp, my = S[0:3] / N, S[3:6] / N
+            m = S[6:15].reshape(3, 3) / N - np.outer(mp, my)
+            A = m - m.T
+            tr = np.trace(m)
+            Q = np.empty((4, 4))
+            Q[0, 0] = tr
+            Q[0, 1:] = Q[1:, 0] = [A[1, 2], A[2, 0], A[0, 1]]
+            Q[1:, 1:] = m + m.T - tr * np.eye(3)
+            w, v = np.linalg.eigh(Q)
+            q = v[:, -1] * (1 if v[0, -1] >= 0 else -1)
+            R1 = np.array([[q[0]**2 + q[1]**2 - q[2]**2 - q[3]**2, 2 * (q[1]*q[2] - q[0]*q[3]), 2 * (q[1]*q[3] + q[0]*q[2])],
+                           [2 * (q[1]*q[2] + q[0]*q[3]), q[0]**2 - q[1]**2 + q[2]**2 - q[3]**2, 2 * (q[2]*q[3] - q[0]*q[1])],
+                           [2 * (q[1]*q[3] - q[0]*q[2]), 2 * (q[2]*q[3] + q[0]*q[1]), q[0]**2 - q[1]**2 - q[2]**2 + q[3]**2]])
+            T1 = my - R1 @ mp
+            pre_d, self.d = self.d, float(S[15])
+            self.round += 1
+            if abs(self.d - pre_d) >= e:
+                if self.round == 1:
+                    self.R, self.T = R1, T1
+                else:
+                    self.R, self.T = R1 @ self.R, R1 @ self.T + T1
+                self.have_rt = True
+            else:
+                self.converged = True
+                self.done = True
+            if max_iters > 0 and self.round >= max_iters:
+                self.done = True
+        st = np.concatenate([self.R.ravel(), self.T, [self.d, self.round, float(self.converged), 0.0]])
+        return torch.from_numpy(st)

@@ -40,7 +40,7 @@ def _cloud(case):
     return pts[perm, 0].copy(), pts[perm, 1].copy()
 
 
-def _worker(rank, world, port, case, eps, min_pts, cf0):
+def _worker(rank, world, port, case, eps, min_pts, cf0, presplit=False):
     for p in (str(ROOT), str(ROOT / "oracle"), str(ROOT / "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -53,11 +53,23 @@ def _worker(rank, world, port, case, eps, min_pts, cf0):
         from vtkcloudpoint_b200.distributed import dbscan_slabs
         mx, my = _cloud(case)
         n = len(mx)
-        bounds = [n * r // world for r in range(world + 1)]
+        splitters = None
+        if presplit:
+            # pre-cut cloud: order the points by slab (rank r = the r-th u-quantile band), non-finite ones anywhere
+            u = mx + my
+            fin = np.isfinite(u)
+            qs = np.quantile(u[fin], [j / world for j in range(1, world)]) if world > 1 else np.empty(0)
+            band = np.where(fin, np.searchsorted(qs, u, side="right"), 0)
+            order = np.argsort(band, kind="stable")
+            mx, my, band = mx[order], my[order], band[order]
+            bounds = [int(np.searchsorted(band, r, side="left")) for r in range(world)] + [n]
+            splitters = torch.from_numpy(np.asarray(qs, dtype=np.float64))
+        else:
+            bounds = [n * r // world for r in range(world + 1)]
         a, b = bounds[rank], bounds[rank + 1]
         stats = {}
         cid, key, cls, amount = dbscan_slabs(CpuCheckerBackend(), torch.from_numpy(mx[a:b].copy()), torch.from_numpy(my[a:b].copy()),
-                                             a, eps, min_pts, cf0, stats=stats)
+                                             a, eps, min_pts, cf0, stats=stats, splitters=splitters)
         ocid, okey, ocls, oamount = oracle_py.dbscan(mx, my, eps, min_pts, cf0, variant="grid")
         assert amount == oamount, (amount, oamount)
         np.testing.assert_array_equal(key.numpy(), okey[a:b])
@@ -73,3 +85,39 @@ def _worker(rank, world, port, case, eps, min_pts, cf0):
                                                      (3, 2, 0.1, 4), (1, 1, 0.05, 5)])
 def test_dbscan_slabs_matches_whole_cloud(world, case, eps, min_pts):
     mp.spawn(_worker, args=(world, _free_port(), case, eps, min_pts, 7), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,case,eps,min_pts", [(2, 0, 0.06, 4), (3, 1, 0.05, 5), (3, 2, 0.1, 4)])
+def test_dbscan_slabs_presplit(world, case, eps, min_pts):
+    mp.spawn(_worker, args=(world, _free_port(), case, eps, min_pts, 0, True), nprocs=world, join=True)
+
+
+def _icp_worker(rank, world, port, e, max_iters):
+    for p in (str(ROOT), str(ROOT / "oracle"), str(ROOT / "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle_py
+        from dist_cpu_backend import CpuCheckerIcpBackend
+        from vtkcloudpoint_b200 import synth
+        from vtkcloudpoint_b200.distributed import icp_rigid_sharded
+        model, data, R, T = synth.icp_clouds(0xC3, 30_000, 3_000)
+        model[:, 7] = model[:, 20_007]                      # a duplicate across shards: the tie must go to the lower global index
+        m = model.shape[1]
+        a, b = m * rank // world, m * (rank + 1) // world
+        state, order = icp_rigid_sharded(CpuCheckerIcpBackend(), torch.from_numpy(model[:, a:b].copy()), a, torch.from_numpy(data), e, max_iters)
+        st = state.numpy()
+        Ro, To, it, sse, oo = oracle_py.icp_rigid(model, data, e, max_iters)
+        assert int(st[13]) == it, (st[13], it)
+        np.testing.assert_array_equal(order.numpy(), oo)
+        assert np.abs(st[:9].reshape(3, 3) - Ro).max() < 1e-6 and np.abs(st[9:12] - To).max() < 1e-6 and abs(st[12] - sse) <= 1e-6 * max(sse, 1e-30)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,e,max_iters", [(2, -1.0, 4), (3, 1e-4, 12), (1, -1.0, 3)])
+def test_icp_sharded_matches_whole_model(world, e, max_iters):
+    mp.spawn(_icp_worker, args=(world, _free_port(), e, max_iters), nprocs=world, join=True)

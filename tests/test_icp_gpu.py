@@ -125,3 +125,17 @@ def test_icp_device_entry(ctx, oracle):
     assert int(st[13]) == 10
     np.testing.assert_array_equal(order_last.cpu().numpy(), oo)
     assert _rel(st[:9].reshape(3, 3), Ro) < RTOL and _rel(st[9:12], To) < RTOL and abs(st[12] - sse) <= RTOL * sse
+
+
+def test_icp_shard_steps_single_rank(ctx, oracle):
+    # the vpc_icp_shard_* exports through the distributed driver at world size 1
+    import torch
+    from vtkcloudpoint_b200.distributed import GpuIcpBackend, icp_rigid_sharded
+    model, data, R, T = synth.icp_clouds(0xC3, 60_000, 6_000)
+    state, order = icp_rigid_sharded(GpuIcpBackend(ctx), torch.from_numpy(model).cuda(), 0, torch.from_numpy(data).cuda(), -1.0, 6)
+    torch.cuda.synchronize()
+    st = state.cpu().numpy()
+    Ro, To, it, sse, oo = oracle.icp_rigid(model, data, -1.0, 6)
+    assert int(st[13]) == it == 6
+    np.testing.assert_array_equal(order.cpu().numpy(), oo)
+    assert _rel(st[:9].reshape(3, 3), Ro) < RTOL and _rel(st[9:12], To) < RTOL and abs(st[12] - sse) <= RTOL * sse

@@ -481,6 +481,109 @@ k_icp_iter(IcpModel g, const double* __restrict__ data, int n, double e, int max
   }
 }
 
+// ---- sharded-model ICP (one model shard per GPU, data replicated; vtkcloudpoint_b200/distributed.py) ----
+// A round is: k_icp_nn_local -> all_reduce(MIN) d2 -> k_icp_select -> all_reduce(MIN) idx -> k_icp_accumulate
+// -> all_reduce(SUM) 16 sums -> k_icp_solve_sums.  Every kernel is a no-op once the state says done, so the
+// whole loop is enqueued without host round trips; the collectives then just re-reduce unchanged buffers.
+__device__ __forceinline__ void icp_apply_rt(const IcpState* st, double& px, double& py, double& pz) {
+  if (!st->have_rt) return;
+  const double x = px, y = py, z = pz;   // TransPoint, ICP.cs:195-219
+  px = (((0.0 + st->R[0] * x) + st->R[1] * y) + st->R[2] * z) + st->T[0];
+  py = (((0.0 + st->R[3] * x) + st->R[4] * y) + st->R[5] * z) + st->T[1];
+  pz = (((0.0 + st->R[6] * x) + st->R[7] * y) + st->R[8] * z) + st->T[2];
+}
+
+__global__ void __launch_bounds__(kIterBlock)
+k_icp_nn_local(IcpModel g, const double* __restrict__ data, int n, const IcpState* __restrict__ st, int idx_offset,
+               double* __restrict__ d2_out, int* __restrict__ idx_out) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const IcpGridCtrl c = *g.ctrl;
+  double px = __ldg(data + i), py = __ldg(data + n + i), pz = __ldg(data + 2ll * n + i);
+  icp_apply_rt(st, px, py, pz);
+  NnBest b;
+  icp_match(g, c, px, py, pz, b);
+  d2_out[i] = b.d;
+  idx_out[i] = b.i + idx_offset;
+}
+
+// keep the index only where this shard holds the global minimum; the MIN all_reduce then picks the lowest index
+__global__ void __launch_bounds__(kIterBlock)
+k_icp_select(int n, const IcpState* __restrict__ st, const double* __restrict__ d2_local, const double* __restrict__ d2_global,
+             int* __restrict__ idx) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!(d2_local[i] == d2_global[i])) idx[i] = 0x7fffffff;
+}
+
+// sums over the data points whose winning model point lives in THIS shard
+__global__ void __launch_bounds__(kIterBlock)
+k_icp_accumulate(IcpModel g, const double* __restrict__ data, int n, const IcpState* __restrict__ st, const int* __restrict__ idx_global,
+                 int idx_offset, double* __restrict__ partial, unsigned* ticket, double* __restrict__ sums_out) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s[kIcpSums];
+#pragma unroll
+  for (int k = 0; k < kIcpSums; ++k) s[k] = 0.0;
+  if (i < n) {
+    const int j = idx_global[i] - idx_offset;
+    if (j >= 0 && j < g.m) {
+      double px = __ldg(data + i), py = __ldg(data + n + i), pz = __ldg(data + 2ll * n + i);
+      icp_apply_rt(st, px, py, pz);
+      const double bx = __ldg(g.xyz + j), by = __ldg(g.xyz + g.m + j), bz = __ldg(g.xyz + 2ll * g.m + j);
+      s[0] = px; s[1] = py; s[2] = pz;
+      s[3] = bx; s[4] = by; s[5] = bz;
+      s[6] = px * bx; s[7] = px * by; s[8] = px * bz;
+      s[9] = py * bx; s[10] = py * by; s[11] = py * bz;
+      s[12] = pz * bx; s[13] = pz * by; s[14] = pz * bz;
+      const double ex = px - bx, ey = py - by, ez = pz - bz;
+      s[15] = ex * ex + ey * ey + ez * ez;
+    }
+  }
+  __shared__ double sm[kIcpSums][kIterBlock / kIcpSums + 1];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kIcpSums; ++k) {
+    const double v = warp_sum_d(s[k]);
+    if (lane == 0) sm[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kIcpSums) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kIterBlock / kWarp; ++w) v += sm[threadIdx.x][w];
+    partial[(long long)blockIdx.x * kIcpSums + threadIdx.x] = v;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  constexpr int kSlices = kIterBlock / kIcpSums;
+  const int q = threadIdx.x % kIcpSums, slice = threadIdx.x / kIcpSums;
+  double acc = 0.0;
+  for (int b = slice; b < (int)gridDim.x; b += kSlices) acc += __ldcg(partial + (long long)b * kIcpSums + q);
+  sm[q][slice] = acc;
+  __syncthreads();
+  if (threadIdx.x < kIcpSums) {
+    double v = 0.0;
+    for (int k = 0; k < kSlices; ++k) v += sm[threadIdx.x][k];
+    sums_out[threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+__global__ void k_icp_solve_sums(const double* __restrict__ sums, int n, double e, int max_iters, IcpState* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+  double S[kIcpSums];
+  for (int k = 0; k < kIcpSums; ++k) S[k] = sums[k];
+  icp_solve_round(S, n, e, max_iters, st);
+}
+
 __global__ void k_icp_state_init(IcpState* st, const double* R0, const double* T0, unsigned* ticket) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   *ticket = 0;

@@ -532,6 +532,64 @@ int vpc_icp_rigid_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, double 
   return VPC_OK;
 }
 
+// ---- sharded-model ICP steps (see include/vpc.h) ---------------------------------------------
+int vpc_icp_shard_begin_dev(vpc_ctx* ctx, int64_t n, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n <= 0 || n > 2147483646ll) return fail(ctx, VPC_E_BADARG, "bad n");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->model_set) return fail(ctx, VPC_E_STATE, "vpc_icp_set_model_dev has not been called");
+  DeviceGuard g(ctx->device);
+  int rc = icp_reserve_work(ctx, n);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_icp_state_init, 1, 32, static_cast<cudaStream_t>(stream), ctx->icp_state, (const double*)nullptr,
+             (const double*)nullptr, ctx->icp_ticket);
+  return VPC_OK;
+}
+
+int vpc_icp_shard_nn_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, int32_t idx_offset, double* d_d2, int32_t* d_idx,
+                         void* stream) {
+  if (!ctx || !d_data_xyz || !d_d2 || !d_idx || n <= 0) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->model_set || !ctx->icp_partial) return fail(ctx, VPC_E_STATE, "call vpc_icp_set_model_dev and vpc_icp_shard_begin_dev first");
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_icp_nn_local, blocks_for(n, kIterBlock), kIterBlock, static_cast<cudaStream_t>(stream), ctx->model, d_data_xyz,
+             (int)n, ctx->icp_state, idx_offset, d_d2, d_idx);
+  return VPC_OK;
+}
+
+int vpc_icp_shard_select_dev(vpc_ctx* ctx, int64_t n, const double* d_d2_local, const double* d_d2_global, int32_t* d_idx, void* stream) {
+  if (!ctx || !d_d2_local || !d_d2_global || !d_idx || n <= 0) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->icp_partial) return fail(ctx, VPC_E_STATE, "call vpc_icp_shard_begin_dev first");
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_icp_select, blocks_for(n, kIterBlock), kIterBlock, static_cast<cudaStream_t>(stream), (int)n, ctx->icp_state,
+             d_d2_local, d_d2_global, d_idx);
+  return VPC_OK;
+}
+
+int vpc_icp_shard_accumulate_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, const int32_t* d_idx_global, int32_t idx_offset,
+                                 double* d_sums16, void* stream) {
+  if (!ctx || !d_data_xyz || !d_idx_global || !d_sums16 || n <= 0) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->model_set || !ctx->icp_partial) return fail(ctx, VPC_E_STATE, "call vpc_icp_set_model_dev and vpc_icp_shard_begin_dev first");
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_icp_accumulate, blocks_for(n, kIterBlock), kIterBlock, static_cast<cudaStream_t>(stream), ctx->model, d_data_xyz,
+             (int)n, ctx->icp_state, d_idx_global, idx_offset, ctx->icp_partial, ctx->icp_ticket, d_sums16);
+  return VPC_OK;
+}
+
+int vpc_icp_shard_solve_dev(vpc_ctx* ctx, const double* d_sums16, int64_t n, double e, int32_t max_iters, double* d_state_out,
+                            void* stream) {
+  if (!ctx || !d_sums16 || n <= 0) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->icp_partial) return fail(ctx, VPC_E_STATE, "call vpc_icp_shard_begin_dev first");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VPC_LAUNCH(ctx, k_icp_solve_sums, 1, 32, s, d_sums16, (int)n, e, max_iters, ctx->icp_state);
+  if (d_state_out) VPC_LAUNCH(ctx, k_icp_state_export, 1, 32, s, ctx->icp_state, d_state_out);
+  return VPC_OK;
+}
+
 int vpc_closest_point_set(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double* data_xyz, int64_t n,
                           int32_t* order, double* sqdist) {
   if (!ctx) return VPC_E_BADARG;

@@ -117,11 +117,14 @@ def _all_gather_var(t, group):
 # DBSCAN over slabs
 # ------------------------------------------------------------------------------------------------
 def dbscan_slabs(backend, x, y, gidx0: int, eps: float, min_pts: int, first_cluster_id: int = 0, group=None, n_bins: int = 65536,
-                 stats: dict | None = None):
+                 stats: dict | None = None, splitters=None):
     """x, y: this rank's chunk of the global cloud (float64, on the backend's device); element i has global
     index gidx0 + i and the chunks of all ranks tile 0..n_total-1.  Returns (cluster_id int32, is_key uint8,
     is_classed uint8, cluster_amount int) for the chunk -- the same values vpc_dbscan_l1_2d gives on the whole
-    cloud (DBImproved.dbscan semantics, include/vpc.h)."""
+    cloud (DBImproved.dbscan semantics, include/vpc.h).
+    splitters (optional, float64 tensor of world-1 ascending u = x + y values, identical on all ranks): the cloud
+    is ALREADY cut into slabs -- rank r holds exactly the points with splitters[r-1] <= x + y < splitters[r].
+    Then only the halo strips travel (steps 1 and the return trip of step 6 disappear)."""
     rank, world = _world(group)
     dev = x.device
     n = x.numel()
@@ -159,7 +162,11 @@ def dbscan_slabs(backend, x, y, gidx0: int, eps: float, min_pts: int, first_clus
     err = amax * 2.0 ** -52
     H = 2.0 * (eps * (1.0 + 2.0 ** -30) + 8.0 * err) * (1.0 + 2.0 ** -30)
     span = max(umax - umin, 1e-300)
-    if world > 1:
+    presplit = splitters is not None
+    if presplit:
+        splitters = splitters.to(device=dev, dtype=torch.float64)
+        assert splitters.numel() == world - 1
+    elif world > 1:
         b = torch.clamp(((uv - umin) * (n_bins / span)).floor().to(torch.int64), 0, n_bins - 1)
         hist = torch.bincount(b, minlength=n_bins).to(torch.int64)
         dist.all_reduce(hist, group=group)
@@ -181,6 +188,8 @@ def dbscan_slabs(backend, x, y, gidx0: int, eps: float, min_pts: int, first_clus
     d_dest, d_src = [], []
     for d in range(maxspan + 1):
         m = (lo + d) <= hi
+        if presplit:
+            m = m & ((lo + d) != rank)          # own points stay where they are; only halo copies travel
         d_dest.append((lo + d)[m])
         d_src.append(idx[m])
     dest = torch.cat(d_dest) if d_dest else torch.empty(0, dtype=torch.int64, device=dev)
@@ -190,6 +199,9 @@ def dbscan_slabs(backend, x, y, gidx0: int, eps: float, min_pts: int, first_clus
     send_counts = torch.bincount(dest, minlength=world).to(torch.int64)
     owned_flag = (torch.searchsorted(splitters, u[src], right=True) == dest).to(torch.uint8)
     (rx, ry, rg, rown), _ = _all_to_all_var([x[src], y[src], gidx[src], owned_flag], send_counts, group)
+    if presplit:
+        rx, ry, rg = torch.cat([x[idx], rx]), torch.cat([y[idx], ry]), torch.cat([gidx[idx], rg])
+        rown = torch.cat([torch.ones(idx.numel(), dtype=torch.uint8, device=dev), torch.zeros(rown.numel(), dtype=torch.uint8, device=dev)])
     n_local = rx.numel()
     if stats is not None:
         stats.update(n_local=n_local, n_owned=int(rown.sum().item()), halo_width=H)
@@ -238,6 +250,10 @@ def dbscan_slabs(backend, x, y, gidx0: int, eps: float, min_pts: int, first_clus
     amount = first_cluster_id + int(all_heads.numel())
     ocid = torch.where(okey >= 0, (first_cluster_id + 1 + torch.searchsorted(all_heads, okey)).to(torch.int32),
                        torch.zeros_like(okey))
+    if presplit:                       # owned points are this rank's own valid points, in their original order
+        cid_out[idx] = ocid
+        key_out[idx] = ocore
+        return cid_out, key_out, (cid_out != 0).to(torch.uint8), amount
     home = torch.searchsorted(chunk_starts, og.to(torch.int64), right=True) - 1
     order = torch.sort(home, stable=True).indices
     back_counts = torch.bincount(home, minlength=world).to(torch.int64)
@@ -246,3 +262,73 @@ def dbscan_slabs(backend, x, y, gidx0: int, eps: float, min_pts: int, first_clus
     cid_out[pos] = bc
     key_out[pos] = bk
     return cid_out, key_out, (cid_out != 0).to(torch.uint8), amount
+
+
+# ------------------------------------------------------------------------------------------------
+# ICP with a sharded model
+# ------------------------------------------------------------------------------------------------
+class GpuIcpBackend:
+    """Per-GPU steps of the sharded ICP round (include/vpc.h, vpc_icp_shard_*)."""
+
+    def __init__(self, ctx):
+        self.ctx, self._lib, self._h = ctx, ctx._lib, ctx._h
+
+    def _s(self, t):
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    def set_model(self, model_planar):
+        self.ctx.icp_set_model_dev(model_planar)
+
+    def begin(self, data_planar):
+        n, dev = data_planar.shape[1], data_planar.device
+        self.n = n
+        self.d2 = torch.empty(n, dtype=torch.float64, device=dev)
+        self.d2g = torch.empty(n, dtype=torch.float64, device=dev)
+        self.idx = torch.empty(n, dtype=torch.int32, device=dev)
+        self.sums = torch.zeros(16, dtype=torch.float64, device=dev)
+        self.state = torch.zeros(16, dtype=torch.float64, device=dev)
+        self.ctx._check(self._lib.vpc_icp_shard_begin_dev(self._h, n, self._s(data_planar)))
+
+    def nn(self, data_planar, idx_offset):
+        self.ctx._check(self._lib.vpc_icp_shard_nn_dev(self._h, data_planar.data_ptr(), self.n, int(idx_offset), self.d2.data_ptr(),
+                                                       self.idx.data_ptr(), self._s(data_planar)))
+        return self.d2, self.idx
+
+    def select(self, d2_local, d2_global, idx):
+        self.ctx._check(self._lib.vpc_icp_shard_select_dev(self._h, self.n, d2_local.data_ptr(), d2_global.data_ptr(), idx.data_ptr(),
+                                                           self._s(idx)))
+
+    def accumulate(self, data_planar, idx_global, idx_offset):
+        self.ctx._check(self._lib.vpc_icp_shard_accumulate_dev(self._h, data_planar.data_ptr(), self.n, idx_global.data_ptr(),
+                                                               int(idx_offset), self.sums.data_ptr(), self._s(data_planar)))
+        return self.sums
+
+    def solve(self, sums, e, max_iters):
+        self.ctx._check(self._lib.vpc_icp_shard_solve_dev(self._h, sums.data_ptr(), self.n, float(e), int(max_iters),
+                                                          self.state.data_ptr(), self._s(sums)))
+        return self.state
+
+
+def icp_rigid_sharded(backend, model_shard, idx_offset: int, data, e: float, max_iters: int, group=None):
+    """model_shard: (3, m_r) float64, this rank's part of the model whose first point has global index idx_offset;
+    data: (3, n) float64, identical on every rank.  Runs max_iters rounds of ICP.go_hell_ICP (ICP.cs:18-181,
+    corrected solve) -- rounds after convergence are no-ops -- and returns (state f64[16] = R[9] T[3] sse iters
+    converged 0, order_last int32[n] of GLOBAL model indices), identical on every rank.  No host round trip."""
+    rank, world = _world(group)
+    if max_iters <= 0:
+        raise ValueError("the sharded loop needs max_iters > 0")
+    backend.set_model(model_shard)
+    backend.begin(data)
+    state, idx = None, None
+    for _ in range(max_iters):
+        d2, idx = backend.nn(data, idx_offset)
+        if world > 1:
+            backend.d2g.copy_(d2)
+            dist.all_reduce(backend.d2g, op=dist.ReduceOp.MIN, group=group)
+            backend.select(d2, backend.d2g, idx)
+            dist.all_reduce(idx, op=dist.ReduceOp.MIN, group=group)
+        sums = backend.accumulate(data, idx, idx_offset)
+        if world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        state = backend.solve(sums, e, max_iters)
+    return state, idx
