@@ -1,0 +1,48 @@
+// NativeMethods.cs -- P/Invoke declarations for libvpc (include/vpc.h), in the style of the only P/Invoke
+// precedent in the reference tree (vtkPointCloud/BaseClass/FileMap.cs:73-130, [DllImport("kernel32.dll")]).
+// Source only: the build image has no .NET toolchain, so this file is reviewed, not compiled (DESIGN.md).
+using System;
+using System.Runtime.InteropServices;
+
+namespace vtkPointCloud
+{
+    internal static class NativeMethods
+    {
+        private const string Lib = "vpc";   // vpc.dll on Windows, libvpc.so elsewhere (probing path: app.config:5-7)
+
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_create(out IntPtr ctx, int[] deviceIds, int nDevices);
+
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern void vpc_destroy(IntPtr ctx);
+
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern IntPtr vpc_last_error(IntPtr ctx);
+
+        // DBImproved.dbscan (BaseClass/DBImproved.cs:91-114)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_dbscan_l1_2d(IntPtr ctx, double[] mx, double[] my, long n, double eps, int minPts,
+            int firstClusterId, [Out] int[] clusterId, [Out] byte[] isKey, [Out] byte[] isClassed, out int clusterAmount);
+
+        // every StartCode work item (FrmMain.cs:2782-2794) in one call
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_dbscan_l1_2d_cells(IntPtr ctx, double[] mx, double[] my, long n, long[] cellOffsets, int nCells,
+            double eps, int minPts, [Out] int[] clusterId, [Out] byte[] isKey, [Out] byte[] isClassed, [Out] int[] clusterAmountPerCell);
+
+        // ICP.FindClosestPointSet (BaseClass/ICP.cs:224-250); xyz arrays are planar x[0..k) y[0..k) z[0..k)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_closest_point_set(IntPtr ctx, double[] modelXyz, long m, double[] dataXyz, long n,
+            [Out] int[] order, [Out] double[] sqdist);
+
+        // ICP.go_hell_ICP (BaseClass/ICP.cs:18-181)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_icp_rigid(IntPtr ctx, double[] modelXyz, long m, double[] dataXyz, long n, double e,
+            int maxIters, [In, Out] double[] R, [In, Out] double[] T, out int itersDone, out double sseLast, [Out] int[] orderLast);
+
+        internal static void Check(IntPtr ctx, int rc)
+        {
+            if (rc != 0)   // the reference signals errors with MException (Matrix.cs:710-715)
+                throw new MException("vpc error " + rc + ": " + Marshal.PtrToStringAnsi(vpc_last_error(ctx)));
+        }
+    }
+}
