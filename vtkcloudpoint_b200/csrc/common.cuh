@@ -89,8 +89,8 @@ constexpr int kScanTile = kScanBlock * kScanItems;  // 4096 items per tile
 constexpr unsigned long long kTileAggregate = 1ull << 32;
 constexpr unsigned long long kTilePrefix = 2ull << 32;
 
-// kSelfFlag: the scanned value of item i is (in[i] == i) instead of in[i] (rank of self-keyed items).
-template <bool kSelfFlag>
+// kPopc: the scanned value of item i is popc(in[i]) instead of in[i] (ranks inside a bitmap).
+template <bool kPopc>
 __global__ void __launch_bounds__(kScanBlock)
 k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr,
                  int n_static, unsigned long long* tile_state, int* tile_counter, int* total_out) {
@@ -120,11 +120,11 @@ k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* _
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) v[k] = (t0 + k < n) ? in[t0 + k] : (kSelfFlag ? -1 : 0);
+    for (int k = 0; k < kScanItems; ++k) v[k] = (t0 + k < n) ? in[t0 + k] : 0;
   }
-  if (kSelfFlag) {
+  if (kPopc) {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) v[k] = (v[k] == (int)(t0 + k)) ? 1 : 0;
+    for (int k = 0; k < kScanItems; ++k) v[k] = __popc((unsigned)v[k]);
   }
   int tsum = 0;
 #pragma unroll

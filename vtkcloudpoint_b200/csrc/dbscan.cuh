@@ -22,10 +22,13 @@
 //
 // Pipeline (one stream, no host round trip, no memsets):
 //   k_db_bounds -> k_db_hist -> scan(cells) -> k_db_scatter -> k_db_count -> k_db_union
-//   -> k_db_flatten -> k_db_resolve -> scan(self-keyed points) -> k_db_label
-// HBM layout: points are physically re-ordered by cell (counting sort) into sxy[] as double2
-// (one 128-bit load per candidate) with sidx[] = original index; cells of one grid row are
-// consecutive, so the candidates of a region query are <= 4 contiguous ranges of sxy[].
+//   -> k_db_flatten -> k_db_resolve -> scan(popc of the head bitmap) -> k_db_label
+// HBM layout: points are physically re-ordered by cell (counting sort) into rec[]: one 32-byte sector per
+// point {x, y, original index, parent, cell/component info}, written by two 128-bit stores; cells of one
+// grid row are consecutive, so the candidates of a region query are <= 4 contiguous ranges of rec[].
+// Work that only a minority of the points needs (region counts outside dense cells, the border
+// rule) is compacted inside each block first (warp ballots + shared-memory list), so that the
+// warps that do run are full and keep the sorted order's locality.
 #pragma once
 
 #include "common.cuh"
@@ -43,6 +46,15 @@ struct DbCtrl {
   int scan_counter[2];
 };
 
+// Everything a sorted position owns, in ONE 32-byte sector: the scatter writes a full sector per point and
+// a union-find hop, a leader lookup or a key lookup touch the sector the coordinates came with.
+struct __align__(32) DbRec {
+  double2 xy;    // original coordinates
+  int sidx;      // original index
+  int parent;    // union-find over sorted positions
+  int2 cinfo;    // .x at a cell's first slot: first core position of the cell; .y at a root: min original index of the component
+};
+
 struct DbArgs {
   const double* x;
   const double* y;
@@ -53,13 +65,11 @@ struct DbArgs {
   int cell_cap;  // capacity of cell_count / cell_start minus one
   // workspace
   DbCtrl* ctrl;
-  int* cellkey;      // [n]  cell of original point i, -1 = not in the grid
-  int* cell_count;   // [cell_cap+1]  zero on entry and on exit (k_db_scatter counts it back down)
+  int2* keyslot;     // [n]  {cell of original point i (-1 = not in the grid), its slot inside the cell}
+  int* cell_count;   // [cell_cap+1]  zero on entry and on exit (k_db_scatter clears what k_db_hist counted)
   int* cell_start;   // [cell_cap+1]
-  double2* sxy;      // [n]  coordinates in cell order
-  int* sidx;         // [n]  original index of sorted position
-  unsigned char* core;  // [n] by sorted position
-  int* parent;       // [n]  union-find over sorted positions
+  DbRec* rec;        // [n]  per sorted position: coordinates, original index, parent, cell/component info
+  unsigned char* core;  // [n] by sorted position: 0 = not core, 1 = core, 2 = still to be counted
   // segmented mode (vpc_dbscan_l1_2d_cells): independent clouds in one launch, points of a segment are
   // contiguous in the input (CSR offsets); neighbours must share the segment, ids are segment-local
   const int* seg_off;   // [n_seg+1] device, nullptr = one cloud
@@ -69,11 +79,11 @@ struct DbArgs {
   int* seg_amount;      // [n_seg] out: clusters per segment (nullable)
   // distributed mode: component keys are minima of GLOBAL point indices (gidx[i] of local point i)
   const int* gidx;      // [n] device, nullptr = the local index
-  int2* cinfo;       // [n]  .x at a cell's first slot: first core position of the cell; .y at a root: min original index
   int* compkey;      // [n]  by ORIGINAL index: min original core index of the point's cluster, -1 = noise
-  int* rank;         // [n]  exclusive scan of (compkey[i] == i)
+  unsigned* headbits;   // [n/32 + 1] bit i set <=> original point i is the minimum core index of its cluster
+  int* rank;         // [n/32 + 1] exclusive scan of popc(headbits)
   unsigned long long* tile_state0;  // scan states (cells)
-  unsigned long long* tile_state1;  // scan states (points)
+  unsigned long long* tile_state1;  // scan states (bitmap words)
   int tiles0, tiles1;
   // outputs (device)
   int* cluster_id;
@@ -83,6 +93,7 @@ struct DbArgs {
 };
 
 constexpr int kDbBlock = 256;
+constexpr int kNone = 0x7fffffff;
 
 // one-time initialisation of a fresh workspace (cell_count must be all zero, ctrl keys armed)
 __global__ void __launch_bounds__(kDbBlock) k_db_ws_init(DbArgs a) {
@@ -112,13 +123,25 @@ __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long i = tid; i < a.tiles0; i += nth) a.tile_state0[i] = 0;
   for (long long i = tid; i < a.tiles1; i += nth) a.tile_state1[i] = 0;
-  for (long long i = tid; i < a.n; i += nth) {
-    const double x = __ldg(a.x + i), y = __ldg(a.y + i);
+  for (long long i = tid; i <= (a.n >> 5); i += nth) a.headbits[i] = 0u;
+  auto take = [&](double x, double y) {
     if (db_valid(x, y, eps_ok)) {
       const double u = x + y, v = x - y;
       umn = fmin(umn, u); umx = fmax(umx, u);
       vmn = fmin(vmn, v); vmx = fmax(vmx, v);
     }
+  };
+  if ((((unsigned long long)a.x | (unsigned long long)a.y) & 15ull) == 0) {   // 128-bit loads, two points each
+    const double2* x2 = reinterpret_cast<const double2*>(a.x);
+    const double2* y2 = reinterpret_cast<const double2*>(a.y);
+    const long long n2 = a.n >> 1;
+    for (long long i = tid; i < n2; i += nth) {
+      const double2 xv = __ldg(x2 + i), yv = __ldg(y2 + i);
+      take(xv.x, yv.x); take(xv.y, yv.y);
+    }
+    if (tid == 0 && (a.n & 1)) take(__ldg(a.x + a.n - 1), __ldg(a.y + a.n - 1));
+  } else {
+    for (long long i = tid; i < a.n; i += nth) take(__ldg(a.x + i), __ldg(a.y + i));
   }
   umn = warp_min_d(umn); umx = warp_max_d(umx); vmn = warp_min_d(vmn); vmx = warp_max_d(vmx);
   __shared__ double s[4][kDbBlock / kWarp];
@@ -189,7 +212,7 @@ __device__ __forceinline__ int db_cell1(double t, double o, double inv_h, int nc
   return (int)fmin(fmax(q, 0.0), (double)(nc - 1));
 }
 
-// ---- k_db_hist: cell key per point + occupancy histogram; settles points outside the grid ----
+// ---- k_db_hist: cell key + slot per point (occupancy histogram); settles points outside the grid ----
 __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
@@ -204,30 +227,37 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
     const int cu = db_cell1(x + y, c.u0, c.inv_h, c.ncu);
     const int cv = db_cell1(x - y, c.v0, c.inv_h, c.ncv);
     const int key = cv * c.ncu + cu;
-    a.cellkey[i] = key;
-    atomicAdd(&a.cell_count[key], 1);
+    a.keyslot[i] = make_int2(key, atomicAdd(&a.cell_count[key], 1));
   } else {
     // NaN/inf coordinate (or eps < 0 / NaN): every getDisP(..) <= e is false, even against
     // itself (DBImproved.cs:41).  Zero neighbours: core only when 0 >= min_pts, and then a
     // one-point cluster whose isClassed stays false (the point is not in its own nei list).
-    a.cellkey[i] = -1;
+    a.keyslot[i] = make_int2(-1, 0);
     const bool key_pt = (0 >= a.min_pts);
     a.is_key[i] = key_pt ? 1 : 0;
-    a.compkey[i] = key_pt ? (a.gidx ? __ldg(a.gidx + i) : (int)i) : -1;
+    const int gi = a.gidx ? __ldg(a.gidx + i) : (int)i;
+    a.compkey[i] = key_pt ? gi : -1;
+    if (key_pt && !a.gidx) atomicOr(&a.headbits[i >> 5], 1u << (i & 31));
   }
 }
 
-// ---- k_db_scatter: physical reorder by cell; leaves cell_count at zero again ----------------------
+// ---- k_db_scatter: physical reorder by cell; classifies dense cells on the way ------------------
 __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  const int key = a.cellkey[i];
-  if (key < 0) return;
-  const int pos = a.cell_start[key] + atomicSub(&a.cell_count[key], 1) - 1;
-  a.sxy[pos] = make_double2(__ldg(a.x + i), __ldg(a.y + i));
-  a.sidx[pos] = (int)i;
+  const int2 ks = a.keyslot[i];
+  if (ks.x < 0) return;
+  const double x = __ldg(a.x + i), y = __ldg(a.y + i);
+  const int s = __ldg(a.cell_start + ks.x), e = __ldg(a.cell_start + ks.x + 1);
+  const int pos = s + ks.y;
+  if (ks.y == 0) a.cell_count[ks.x] = 0;          // leave the histogram clean for the next call
   if (a.seg_off) a.sseg[pos] = a.segof[i];
-  a.cinfo[pos] = make_int2(0x7fffffff, 0x7fffffff);   // {first core position of the cell, min original index of the component}
+  // dense clique cell (>= min_pts points): all core, one cluster, hung under the cell's first slot -- no test
+  const bool dense = a.ctrl->clique && (e - s >= a.min_pts);
+  a.core[pos] = dense ? 1 : 2;
+  double2* r2 = reinterpret_cast<double2*>(a.rec + pos);   // two 128-bit stores = one full sector
+  r2[0] = make_double2(x, y);
+  reinterpret_cast<int4*>(r2)[1] = make_int4((int)i, dense ? s : pos, (dense && pos == s) ? s : kNone, kNone);
 }
 
 // exact reference predicate: Math.Abs(dx) + Math.Abs(dy) <= e   (DBImproved.cs:16-21, :41)
@@ -237,7 +267,7 @@ __device__ __forceinline__ bool db_near(double2 p, double2 q, double eps) {
 }
 
 // the block of cells that can hold neighbours of p, and p's own cell.  ncols, nrows <= 4 by construction
-// (2E < 2.0001 h in clique mode, E <= h otherwise); the kernels clamp to 4 and loop if a range is longer.
+// (2E < 2.0001 h in clique mode, E <= h otherwise); the kernels loop if a range is longer.
 struct DbStencil {
   int cu, cv, ulo, uhi, vlo, vhi;
 };
@@ -253,14 +283,16 @@ __device__ __forceinline__ DbStencil db_stencil(const DbCtrl& c, double2 p) {
   return s;
 }
 
+__device__ __forceinline__ double2 db_xy(const DbRec* __restrict__ rec, int j) { return __ldg(reinterpret_cast<const double2*>(rec + j)); }
+
 // number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight
-__device__ __forceinline__ int db_count_range(const double2* __restrict__ sxy, int j0, int j1, int s, int e, double2 me, double eps,
+__device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int j0, int j1, int s, int e, double2 me, double eps,
                                               const int* __restrict__ sseg, int myseg) {
   int cnt = 0;
   for (int j = j0; j < j1; j += 4) {
     double2 q[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = ldg_d2(sxy + min(j + k, j1 - 1));
+    for (int k = 0; k < 4; ++k) q[k] = db_xy(rec, min(j + k, j1 - 1));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int jj = j + k;
@@ -270,71 +302,92 @@ __device__ __forceinline__ int db_count_range(const double2* __restrict__ sxy, i
   return cnt;
 }
 
+// Block-level stream compaction: threads with `want` append `item` to a shared list in thread order.
+// Returns the list length (same for every thread).  Needs kDbBlock ints of shared memory.
+__device__ __forceinline__ int db_block_compact(bool want, int item, int* s_list, int* s_warp_cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(kFull, want);
+  if (lane == 0) s_warp_cnt[warp] = __popc(m);
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kDbBlock / kWarp; ++w) {
+    const int cnt = s_warp_cnt[w];
+    if (w < warp) base += cnt;
+    total += cnt;
+  }
+  if (want) s_list[base + __popc(m & ((1u << lane) - 1u))] = item;
+  __syncthreads();
+  return total;
+}
+
 // ---- k_db_count: region query -> core flag (isKeyPoint, DBImproved.cs:33-54) ------------------
+// Only points outside dense cells (core[] == 2) still need a count; they are compacted per block.
 __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_list[kDbBlock];
+  __shared__ int s_cnt[kDbBlock / kWarp];
+  const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
   const DbCtrl c = *a.ctrl;
-  if (p >= c.n_valid) return;
-  const double2 me = a.sxy[p];
+  if (blockIdx.x * blockDim.x >= c.n_valid) return;
+  const bool todo = (p0 < c.n_valid) && (a.core[p0] == 2);
+  const int n_work = db_block_compact(todo, p0, s_list, s_cnt);
+  if ((int)threadIdx.x >= n_work) return;
+  const int p = s_list[threadIdx.x];
+  const double2 me = db_xy(a.rec, p);
   const DbStencil st = db_stencil(c, me);
   const int need = a.min_pts;
   const int own = st.cv * c.ncu + st.cu;
   const int s = __ldg(a.cell_start + own), e = __ldg(a.cell_start + own + 1);
   const int myseg = a.seg_off ? a.sseg[p] : 0;
-  int cnt = 0, par = p;
-  bool dense = false;
-  int es = 0, ee = 0;                  // range excluded from the tests because it is already counted
-  if (c.clique) {
-    cnt = e - s;                       // every point of the own cell is a neighbour (self included)
-    es = s; ee = e;
-    if (cnt >= need) { dense = true; par = s; }   // dense cell: all core, one cluster, hung under its first point
-  }
-  if (!dense) {
-    for (int rb = st.vlo; rb <= st.vhi && cnt < need; rb += 4) {
-      int j0[4], j1[4];
+  int cnt = 0, es = 0, ee = 0;         // [es, ee): range excluded from the tests because it is already counted
+  if (c.clique) { cnt = e - s; es = s; ee = e; }   // every point of the own cell is a neighbour (self included)
+  for (int rb = st.vlo; rb <= st.vhi && cnt < need; rb += 4) {
+    int j0[4], j1[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {    // all row ranges first: independent loads
-        const int row = rb + r;
-        const bool ok = row <= st.vhi;
-        j0[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.ulo) : 0;
-        j1[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.uhi + 1) : 0;
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (cnt < need) cnt += db_count_range(a.sxy, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg);
+    for (int r = 0; r < 4; ++r) {      // all row ranges first: independent loads
+      const int row = rb + r;
+      const bool ok = row <= st.vhi;
+      j0[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.ulo) : 0;
+      j1[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.uhi + 1) : 0;
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg);
   }
   const bool core = cnt >= need;       // only 'count >= minPts' matters (:47)
   a.core[p] = core ? 1 : 0;
-  a.parent[p] = par;
-  if (core && c.clique) {              // publish the first core position of the cell at the cell's first slot
-    if (dense) { if (p == s) a.cinfo[s].x = s; }
-    else atomicMin(&a.cinfo[s].x, p);
-  }
+  if (core && c.clique) atomicMin(&a.rec[s].cinfo.x, p);   // first core position of the cell, at the cell's first slot
 }
 
 // ---- union-find over sorted positions; hooks point towards smaller positions -------------------
-__device__ __forceinline__ int uf_find(int* parent, int x) {
-  int p = ld_relaxed_s32(parent + x);
+// PA maps a node to the address of its parent word (record field or plain array)
+struct RecParent { DbRec* r; __device__ __forceinline__ int* operator()(int x) const { return &r[x].parent; } };
+struct ArrParent { int* p; __device__ __forceinline__ int* operator()(int x) const { return p + x; } };
+
+template <class PA>
+__device__ __forceinline__ int uf_find(PA parent, int x) {
+  int p = ld_relaxed_s32(parent(x));
   while (p != x) {
-    const int gp = ld_relaxed_s32(parent + p);
+    const int gp = ld_relaxed_s32(parent(p));
     if (gp == p) return p;
-    st_relaxed_s32(parent + x, gp);  // path halving; x is not a root, so this races with no CAS
+    st_relaxed_s32(parent(x), gp);  // path halving; x is not a root, so this races with no CAS
     x = gp;
-    p = ld_relaxed_s32(parent + x);
+    p = ld_relaxed_s32(parent(x));
   }
   return x;
 }
-__device__ __forceinline__ int uf_find_ro(const int* parent, int x) {
-  int p = ld_relaxed_s32(parent + x);
-  while (p != x) { x = p; p = ld_relaxed_s32(parent + x); }
+template <class PA>
+__device__ __forceinline__ int uf_find_ro(PA parent, int x) {
+  int p = ld_relaxed_s32(parent(x));
+  while (p != x) { x = p; p = ld_relaxed_s32(parent(x)); }
   return x;
 }
 // ra, rb: (possibly stale) roots.  Returns the root of the merged set as seen by this thread.
-__device__ __forceinline__ int uf_unite_roots(int* parent, int ra, int rb) {
+template <class PA>
+__device__ __forceinline__ int uf_unite_roots(PA parent, int ra, int rb) {
   while (ra != rb) {
     if (ra < rb) { const int t = ra; ra = rb; rb = t; }
-    const int old = atomicCAS(parent + ra, ra, rb);   // hook the larger position under the smaller
+    const int old = atomicCAS(parent(ra), ra, rb);   // hook the larger position under the smaller
     if (old == ra) return rb;
     ra = uf_find(parent, ra);
     rb = uf_find(parent, rb);
@@ -348,15 +401,16 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
   const DbCtrl c = *a.ctrl;
   if (p >= c.n_valid) return;
   if (!a.core[p]) return;
-  const double2 me = a.sxy[p];
+  const double2 me = db_xy(a.rec, p);
   const DbStencil st = db_stencil(c, me);
-  int rp = uf_find(a.parent, p);
+  const RecParent par{a.rec};
+  int rp = uf_find(par, p);
   if (c.clique) {
     const int own = st.cv * c.ncu + st.cu;
     const int s = __ldg(a.cell_start + own);
     // the core points of a cell are mutual neighbours: everybody joins the cell's first core point
-    const int lead = a.cinfo[s].x;
-    if (lead != p) rp = uf_unite_roots(a.parent, rp, uf_find(a.parent, lead));
+    const int lead = a.rec[s].cinfo.x;
+    if (lead != p && rp != lead) rp = uf_unite_roots(par, rp, uf_find(par, lead));
     // Each unordered pair of cells is handled from the cell with the larger key.  All core points of a
     // cell share one cluster, so one root comparison dismisses a whole cell and one hit settles it.
     for (int row = st.vlo; row <= st.cv; ++row) {
@@ -367,16 +421,16 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) sB[k] = __ldg(a.cell_start + base + min(kb + k, khi + 1));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) lB[k] = (kb + k <= khi && sB[k] < sB[k + 1]) ? a.cinfo[sB[k]].x : 0x7fffffff;
+        for (int k = 0; k < 4; ++k) lB[k] = (kb + k <= khi && sB[k] < sB[k + 1]) ? a.rec[sB[k]].cinfo.x : kNone;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rB[k] = (lB[k] != 0x7fffffff) ? ld_relaxed_s32(a.parent + lB[k]) : -1;
+        for (int k = 0; k < 4; ++k) rB[k] = (lB[k] != kNone) ? ld_relaxed_s32(par(lB[k])) : -1;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (rB[k] < 0 || rB[k] == rp) continue;           // no core point there / parent is already our root
-          const int root = uf_find(a.parent, lB[k]);
+          const int root = uf_find(par, lB[k]);
           if (root == rp) continue;
           for (int j = lB[k]; j < sB[k + 1]; ++j)
-            if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) { rp = uf_unite_roots(a.parent, rp, root); break; }
+            if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps)) { rp = uf_unite_roots(par, rp, root); break; }
         }
       }
     }
@@ -385,9 +439,9 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
       const int j0 = __ldg(a.cell_start + row * c.ncu + st.ulo);
       const int j1 = min(__ldg(a.cell_start + row * c.ncu + st.uhi + 1), p);  // each edge once: partners before p
       for (int j = j0; j < j1; ++j) {
-        if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p])) {
-          const int rj = uf_find(a.parent, j);
-          if (rj != rp) rp = uf_unite_roots(a.parent, rp, rj);
+        if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p])) {
+          const int rj = uf_find(par, j);
+          if (rj != rp) rp = uf_unite_roots(par, rp, rj);
         }
       }
     }
@@ -399,63 +453,82 @@ __global__ void __launch_bounds__(kDbBlock) k_db_flatten(DbArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_valid = a.ctrl->n_valid;
   const bool active = (p < n_valid) && a.core[p];
-  int root = -1, orig = 0x7fffffff;
+  int root = -1, orig = kNone;
   if (active) {
-    root = uf_find_ro(a.parent, p);
-    a.parent[p] = root;                    // readers racing with this store still see an ancestor
-    orig = __ldg(a.sidx + p);
+    root = uf_find_ro(RecParent{a.rec}, p);
+    a.rec[p].parent = root;                // readers racing with this store still see an ancestor
+    orig = a.rec[p].sidx;
     if (a.gidx) orig = __ldg(a.gidx + orig);
   }
   // neighbours in sorted order mostly share a root: one atomic per distinct root per warp
   const unsigned grp = __match_any_sync(kFull, root);
   const int mn = __reduce_min_sync(grp, orig);
-  if (active && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicMin(&a.cinfo[root].y, mn);
+  if (active && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicMin(&a.rec[root].cinfo.y, mn);
 }
 
 // ---- k_db_resolve: component key per point, in ORIGINAL order ----------------------------------
+// Core points read their root's key; the non-core minority (border rule) is compacted per block.
 __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_list[kDbBlock];
+  __shared__ int s_cnt[kDbBlock / kWarp];
+  const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
   const DbCtrl c = *a.ctrl;
-  if (p >= c.n_valid) return;
-  const int me_i = a.sidx[p];
-  int key;
-  if (a.core[p]) {
-    key = a.cinfo[a.parent[p]].y;
-    a.is_key[me_i] = 1;
-  } else {
-    // border rule: the reference relabels unconditionally (:87), so the cluster expanded
-    // last -- the one with the largest id = largest minimum core index -- wins.
-    const double2 me = a.sxy[p];
-    const DbStencil st = db_stencil(c, me);
-    key = -1;
-    for (int row = st.vlo; row <= st.vhi; ++row) {
-      const int base = row * c.ncu;
-      if (c.clique) {
-        for (int kb = st.ulo; kb <= st.uhi; kb += 4) {
-          int sB[5], lB[4], kB[4];
-#pragma unroll
-          for (int k = 0; k < 5; ++k) sB[k] = __ldg(a.cell_start + base + min(kb + k, st.uhi + 1));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) lB[k] = (kb + k <= st.uhi && sB[k] < sB[k + 1]) ? a.cinfo[sB[k]].x : 0x7fffffff;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) kB[k] = (lB[k] != 0x7fffffff) ? a.cinfo[a.parent[lB[k]]].y : -1;   // one cluster per cell
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (kB[k] <= key) continue;
-            for (int j = lB[k]; j < sB[k + 1]; ++j)
-              if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps)) { key = kB[k]; break; }
-          }
-        }
-      } else {
-        const int j0 = __ldg(a.cell_start + base + st.ulo), j1 = __ldg(a.cell_start + base + st.uhi + 1);
-        for (int j = j0; j < j1; ++j)
-          if (a.core[j] && db_near(me, ldg_d2(a.sxy + j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p]))
-            key = max(key, a.cinfo[a.parent[j]].y);
-      }
+  if (blockIdx.x * blockDim.x >= c.n_valid) return;
+  bool border = false;
+  if (p0 < c.n_valid) {
+    if (a.core[p0]) {
+      const int me_i = a.rec[p0].sidx;
+      const int key = a.rec[a.rec[p0].parent].cinfo.y;
+      a.is_key[me_i] = 1;
+      a.compkey[me_i] = key;
+      // the minimum core index of a cluster heads it: cluster numbering ranks these (DBImproved.cs:93-110)
+      if (!a.gidx && key == me_i) atomicOr(&a.headbits[me_i >> 5], 1u << (me_i & 31));
+    } else {
+      border = true;
     }
-    a.is_key[me_i] = 0;
   }
+  const int n_work = db_block_compact(border, p0, s_list, s_cnt);
+  if ((int)threadIdx.x >= n_work) return;
+  const int p = s_list[threadIdx.x];
+  // border rule: the reference relabels unconditionally (:87), so the cluster expanded
+  // last -- the one with the largest id = largest minimum core index -- wins.
+  const int me_i = a.rec[p].sidx;
+  const double2 me = db_xy(a.rec, p);
+  const DbStencil st = db_stencil(c, me);
+  int key = -1;
+  for (int row = st.vlo; row <= st.vhi; ++row) {
+    const int base = row * c.ncu;
+    if (c.clique) {
+      for (int kb = st.ulo; kb <= st.uhi; kb += 4) {
+        int sB[5], lB[4], kB[4];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sB[k] = __ldg(a.cell_start + base + min(kb + k, st.uhi + 1));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lB[k] = (kb + k <= st.uhi && sB[k] < sB[k + 1]) ? a.rec[sB[k]].cinfo.x : kNone;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) kB[k] = (lB[k] != kNone) ? a.rec[a.rec[lB[k]].parent].cinfo.y : -1;   // one cluster per cell
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (kB[k] <= key) continue;
+          for (int j = lB[k]; j < sB[k + 1]; ++j)
+            if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps)) { key = kB[k]; break; }
+        }
+      }
+    } else {
+      const int j0 = __ldg(a.cell_start + base + st.ulo), j1 = __ldg(a.cell_start + base + st.uhi + 1);
+      for (int j = j0; j < j1; ++j)
+        if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p]))
+          key = max(key, a.rec[a.rec[j].parent].cinfo.y);
+    }
+  }
+  a.is_key[me_i] = 0;
   a.compkey[me_i] = key;
+}
+
+// number of cluster heads with an original index below idx (idx may be n)
+__device__ __forceinline__ int db_rank_of(const DbArgs& a, int idx) {
+  if (idx >= a.n) return a.ctrl->n_roots;
+  return __ldg(a.rank + (idx >> 5)) + __popc(a.headbits[idx >> 5] & ((1u << (idx & 31)) - 1u));
 }
 
 // ---- k_db_label: cluster ids in the reference's numbering ---------------------------------------
@@ -469,13 +542,13 @@ __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
     // ids restart in every segment (each StartCode work item owns a fresh DBImproved, FrmMain.cs:2785)
     const int sg = a.segof[i];
     const int o0 = __ldg(a.seg_off + sg), o1 = __ldg(a.seg_off + sg + 1);
-    const int r0 = (o0 < a.n) ? __ldg(a.rank + o0) : a.ctrl->n_roots;
+    const int r0 = db_rank_of(a, o0);
     base = -r0;
-    if (a.seg_amount && i == o0) a.seg_amount[sg] = ((o1 < a.n) ? __ldg(a.rank + o1) : a.ctrl->n_roots) - r0;
+    if (a.seg_amount && i == o0) a.seg_amount[sg] = db_rank_of(a, o1) - r0;
   }
-  a.cluster_id[i] = (key < 0) ? 0 : base + 1 + __ldg(a.rank + key);
+  a.cluster_id[i] = (key < 0) ? 0 : base + 1 + db_rank_of(a, key);
   // isClassed is set when a point is taken from a nei list (:65); a point outside the grid is in nobody's list
-  a.is_classed[i] = (key >= 0 && a.cellkey[i] >= 0) ? 1 : 0;
+  a.is_classed[i] = (key >= 0 && a.keyslot[i].x >= 0) ? 1 : 0;
 }
 
 // ---- distributed mode (one slab per GPU, vtkcloudpoint_b200/distributed.py) ----------------------
@@ -483,21 +556,21 @@ __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
 __global__ void __launch_bounds__(kDbBlock) k_db_export_core(DbArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.ctrl->n_valid) return;
-  const int i = a.sidx[p];
+  const int i = a.rec[p].sidx;
   const bool core = a.core[p] != 0;
   a.is_key[i] = core ? 1 : 0;
-  a.compkey[i] = core ? a.cinfo[a.parent[p]].y : -1;
+  a.compkey[i] = core ? a.rec[a.rec[p].parent].cinfo.y : -1;
 }
 
 // after the cross-slab merge: every local root whose key is in the (sorted) table takes the merged key
 __global__ void __launch_bounds__(kDbBlock)
 k_db_remap_roots(DbArgs a, const int* __restrict__ map_from, const int* __restrict__ map_to, int n_map) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.ctrl->n_valid || !a.core[p] || a.parent[p] != p) return;
-  const int key = a.cinfo[p].y;
+  if (p >= a.ctrl->n_valid || !a.core[p] || a.rec[p].parent != p) return;
+  const int key = a.rec[p].cinfo.y;
   int lo = 0, hi = n_map;
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(map_from + mid) < key) lo = mid + 1; else hi = mid; }
-  if (lo < n_map && __ldg(map_from + lo) == key) a.cinfo[p].y = __ldg(map_to + lo);
+  if (lo < n_map && __ldg(map_from + lo) == key) a.rec[p].cinfo.y = __ldg(map_to + lo);
 }
 
 // ---- union-find over an explicit edge list (cross-slab component merge); root = smallest node id ----
@@ -509,11 +582,11 @@ __global__ void __launch_bounds__(kDbBlock) k_uf_edges(int* parent, const int* _
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_edges) return;
   const int x = __ldg(ea + i), y = __ldg(eb + i);
-  if (x != y) uf_unite_roots(parent, uf_find(parent, x), uf_find(parent, y));
+  if (x != y) { const ArrParent pa{parent}; uf_unite_roots(pa, uf_find(pa, x), uf_find(pa, y)); }
 }
 __global__ void __launch_bounds__(kDbBlock) k_uf_flatten(int* parent, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { const int r = uf_find_ro(parent, i); parent[i] = r; }
+  if (i < n) { const int r = uf_find_ro(ArrParent{parent}, i); parent[i] = r; }
 }
 
 }  // namespace vpc

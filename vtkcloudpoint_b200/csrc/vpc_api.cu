@@ -134,8 +134,10 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   // anything sparser is coarsened on the device (exactness is unaffected).
   const long long cap_ll = std::min<long long>(8ll * n + 4096, 2147483000ll);
   const int cell_cap = (int)cap_ll;
-  const int tiles0 = scan_tiles((long long)cell_cap + 1), tiles1 = scan_tiles(std::max<long long>(n, 1));
-  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * (d_seg_off ? 7 : 5) + al256(8ull * n) + al256(4ull * (cell_cap + 1ull)) * 2 + al256(16ull * n) +
+  const long long nwords = (n >> 5) + 1;   // cluster-head bitmap
+  const int tiles0 = scan_tiles((long long)cell_cap + 1), tiles1 = scan_tiles(nwords);
+  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * (d_seg_off ? 3 : 1) + al256(8ull * n) + al256(32ull * n) + al256(4ull * nwords) * 2 +
+                 al256(4ull * (cell_cap + 1ull)) * 2 +
                  al256((size_t)n) + al256(8ull * tiles0) + al256(8ull * tiles1) + 4096;
   const char* base_before = ctx->db.base;
   int rc = arena_reserve(ctx, ctx->db, bytes);
@@ -147,14 +149,12 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   a.ctrl = w.take<DbCtrl>(1);
   a.cell_count = w.take<int>(cell_cap + 1ull);
   a.cell_start = w.take<int>(cell_cap + 1ull);
-  a.cellkey = w.take<int>(n);
-  a.sxy = w.take<double2>(n);
-  a.sidx = w.take<int>(n);
+  a.keyslot = w.take<int2>(n);
+  a.rec = w.take<DbRec>(n);
   a.core = w.take<unsigned char>(n);
-  a.parent = w.take<int>(n);
-  a.cinfo = w.take<int2>(n);
   a.compkey = w.take<int>(n);
-  a.rank = w.take<int>(n);
+  a.headbits = w.take<unsigned>(nwords);
+  a.rank = w.take<int>(nwords);
   a.seg_off = d_seg_off; a.n_seg = n_seg; a.seg_amount = d_seg_amount;
   a.gidx = d_gidx;
   if (d_local_keys) a.compkey = d_local_keys;   // distributed mode: keys go straight to the caller's array
@@ -190,7 +190,7 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
     return VPC_OK;
   }
   VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
-  VPC_LAUNCH(ctx, k_scan_exclusive<true>, tiles1, kScanBlock, s, a.compkey, a.rank, (const int*)nullptr, ni, a.tile_state1,
+  VPC_LAUNCH(ctx, k_scan_exclusive<true>, tiles1, kScanBlock, s, reinterpret_cast<const int*>(a.headbits), a.rank, (const int*)nullptr, (int)nwords, a.tile_state1,
              &a.ctrl->scan_counter[1], &a.ctrl->n_roots);
   VPC_LAUNCH(ctx, k_db_label, gpts, kDbBlock, s, a);
   ctx->db_ws_n = n;
