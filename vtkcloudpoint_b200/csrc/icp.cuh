@@ -227,7 +227,13 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
     lo[d] = (p[d] < mid) ? max(cc[d] - 1, 0) : cc[d];
     hi[d] = (p[d] < mid) ? cc[d] : min(cc[d] + 1, c.nc[d] - 1);
   }
-  const double slack = ldexp(c.slack_base + fabs(px) + fabs(py) + fabs(pz), -40);
+  const double slack = (c.slack_base + fabs(px) + fabs(py) + fabs(pz)) * 9.094947017729282e-13;   // 2^-40
+  {  // stage 0: the query's own cell.  Once ICP has (nearly) converged the match is much closer than the cell
+     // walls for most points, and one cell (about one 32-byte record) is all that has to be read.
+    const int own = (cc[2] * c.nc[1] + cc[1]) * c.nc[0] + cc[0];
+    icp_scan_range(g.spts, __ldg(g.cell_start + own), __ldg(g.cell_start + own + 1), px, py, pz, b);
+    if (b.i != 0x7fffffff && icp_box_done(c, p, cc, cc, b, slack)) return;
+  }
   {  // stage 1: nearest octant block, at most 4 row segments; all range loads first
     int j0[4], j1[4];
 #pragma unroll
@@ -238,14 +244,46 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
       j0[r] = dup ? 0 : __ldg(g.cell_start + row + lo[0]);
       j1[r] = dup ? 0 : __ldg(g.cell_start + row + hi[0] + 1);
     }
+    // the k-th record of all four segments is fetched together (four records in flight), twice; what is
+    // left of a long segment goes through the plain loop
+    const double2* s2 = reinterpret_cast<const double2*>(g.spts);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) icp_scan_range(g.spts, j0[r], j1[r], px, py, pz, b);
+    for (int k = 0; k < 2; ++k) {
+      double2 ra[4], rw[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = (j0[r] + k < j1[r]) ? j0[r] + k : 0;     // slot 0 always exists; it is not considered when out of range
+        ra[r] = __ldg(s2 + 2 * j); rw[r] = __ldg(s2 + 2 * j + 1);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (j0[r] + k < j1[r]) icp_consider(b, ra[r], rw[r], px, py, pz);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) icp_scan_range(g.spts, j0[r] + 2, j1[r], px, py, pz, b);
     if (icp_box_done(c, p, lo, hi, b, slack)) return;
   }
   const int rmax = max(c.nc[0], max(c.nc[1], c.nc[2]));
   for (int r = 1; r <= rmax; ++r) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) { lo[d] = max(cc[d] - r, 0); hi[d] = min(cc[d] + r, c.nc[d] - 1); }
+    if (r == 1) {   // the 3x3x3 block: nine row segments, all eighteen range loads issued before any scan
+      for (int z = lo[2]; z <= hi[2]; ++z) {   // per z-plane: three row segments, six range loads issued together
+        int a0[3], a1[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int y = cc[1] + t - 1;
+          const bool ok = y >= 0 && y < c.nc[1];
+          const int row = (z * c.nc[1] + y) * c.nc[0];
+          a0[t] = ok ? __ldg(g.cell_start + row + lo[0]) : 0;
+          a1[t] = ok ? __ldg(g.cell_start + row + hi[0] + 1) : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) icp_scan_range(g.spts, a0[t], a1[t], px, py, pz, b);
+      }
+      if (icp_box_done(c, p, lo, hi, b, slack)) return;
+      continue;
+    }
     for (int z = lo[2]; z <= hi[2]; ++z) {
       for (int y = lo[1]; y <= hi[1]; ++y) {
         const int row = (z * c.nc[1] + y) * c.nc[0];
@@ -337,6 +375,77 @@ __device__ __forceinline__ void jacobi4(double (&A)[4][4], double (&V)[4][4]) {
   }
 }
 
+__device__ __forceinline__ double det3(double a, double b, double c, double d, double e, double f, double g, double h, double i) {
+  return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+}
+
+// Fast path for the quaternion: unit-free eigenvector of the LARGEST eigenvalue of the symmetric 4x4 Q.
+// Newton's iteration on the characteristic polynomial from the Frobenius bound (monotone from above, so it
+// lands on the largest root), eigenvector = best-conditioned row of adj(Q - lambda I).  About forty times
+// cheaper than a full Jacobi decomposition on one thread (no sqrt/div chain per rotation).  Returns false --
+// and the caller runs the Jacobi solver -- unless the result is certified: well separated root (cofactor
+// norm) and residual |(Q - lambda I) v| <= 1e-13 |Q| |v|.
+__device__ __forceinline__ bool eig4_max_fast(const double (&Q)[4][4], double (&v)[4]) {
+  double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  double Q2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += Q[i][k] * Q[k][j];
+      Q2[i][j] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    t1 += Q[i][i]; t2 += Q2[i][i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t3 += Q2[i][j] * Q[j][i];
+  }
+  if (!(t2 > 0.0) || !finite_d(t2)) return false;
+  const double det = Q[0][0] * det3(Q[1][1], Q[1][2], Q[1][3], Q[2][1], Q[2][2], Q[2][3], Q[3][1], Q[3][2], Q[3][3]) -
+                     Q[0][1] * det3(Q[1][0], Q[1][2], Q[1][3], Q[2][0], Q[2][2], Q[2][3], Q[3][0], Q[3][2], Q[3][3]) +
+                     Q[0][2] * det3(Q[1][0], Q[1][1], Q[1][3], Q[2][0], Q[2][1], Q[2][3], Q[3][0], Q[3][1], Q[3][3]) -
+                     Q[0][3] * det3(Q[1][0], Q[1][1], Q[1][2], Q[2][0], Q[2][1], Q[2][2], Q[3][0], Q[3][1], Q[3][2]);
+  // lambda^4 + c3 lambda^3 + c2 lambda^2 + c1 lambda + c0 (Faddeev-LeVerrier)
+  const double c3 = -t1, c2 = 0.5 * (t1 * t1 - t2), c1 = -(t1 * t1 * t1 - 3.0 * t1 * t2 + 2.0 * t3) / 6.0, c0 = det;
+  const double fro = sqrt(t2);
+  double lam = fro;   // >= spectral radius
+  for (int it = 0; it < 48; ++it) {
+    const double p = (((lam + c3) * lam + c2) * lam + c1) * lam + c0;
+    const double dp = ((4.0 * lam + 3.0 * c3) * lam + 2.0 * c2) * lam + c1;
+    if (!(dp > 0.0)) return false;
+    const double step = p / dp;
+    lam -= step;
+    if (fabs(step) <= 1e-16 * fro) break;
+  }
+  double B[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) B[i][j] = Q[i][j] - (i == j ? lam : 0.0);
+  double best2 = -1.0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {   // cofactors along row r: a null vector of the singular B
+    const int r0 = (r == 0) ? 1 : 0, r1 = (r <= 1) ? 2 : 1, r2 = (r <= 2) ? 3 : 2;
+    const double w0 = det3(B[r0][1], B[r0][2], B[r0][3], B[r1][1], B[r1][2], B[r1][3], B[r2][1], B[r2][2], B[r2][3]);
+    const double w1 = -det3(B[r0][0], B[r0][2], B[r0][3], B[r1][0], B[r1][2], B[r1][3], B[r2][0], B[r2][2], B[r2][3]);
+    const double w2 = det3(B[r0][0], B[r0][1], B[r0][3], B[r1][0], B[r1][1], B[r1][3], B[r2][0], B[r2][1], B[r2][3]);
+    const double w3 = -det3(B[r0][0], B[r0][1], B[r0][2], B[r1][0], B[r1][1], B[r1][2], B[r2][0], B[r2][1], B[r2][2]);
+    const double n2 = w0 * w0 + w1 * w1 + w2 * w2 + w3 * w3;
+    if (n2 > best2) { best2 = n2; v[0] = w0; v[1] = w1; v[2] = w2; v[3] = w3; }
+  }
+  if (!(best2 > 1e-8 * t2 * t2 * t2)) return false;        // |adj| >= 1e-4 |Q|^3: the largest root is well separated
+  double res2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double ri = B[i][0] * v[0] + B[i][1] * v[1] + B[i][2] * v[2] + B[i][3] * v[3];
+    res2 += ri * ri;
+  }
+  return res2 <= 1e-26 * t2 * best2;
+}
+
 // The rigid step of one round from the 16 sums S (ICP.cs:31-180, intended algorithm): means, cross-covariance,
 // Horn's 4x4 matrix, quaternion of the largest eigenvalue, R1/T1, SSE, convergence test, composition.
 __device__ __forceinline__ void icp_solve_round(const double* S, int n, double e, int max_iters, IcpState* st) {
@@ -360,12 +469,16 @@ __device__ __forceinline__ void icp_solve_round(const double* S, int n, double e
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int b = 0; b < 3; ++b) Q[a + 1][b + 1] = (m[a][b] + m[b][a]) - (a == b ? tr : 0.0);
-  jacobi4(Q, V);
-  double qv[4] = {V[0][0], V[1][0], V[2][0], V[3][0]};
-  double best = Q[0][0];
+  double qv[4];
+  if (!eig4_max_fast(Q, qv)) {
+    // (near-)degenerate spectrum: full Jacobi decomposition, the job of Matrix.ComputeEvJacobi
+    jacobi4(Q, V);
+    qv[0] = V[0][0]; qv[1] = V[1][0]; qv[2] = V[2][0]; qv[3] = V[3][0];
+    double best = Q[0][0];
 #pragma unroll
-  for (int k = 1; k < 4; ++k)
-    if (Q[k][k] > best) { best = Q[k][k]; qv[0] = V[0][k]; qv[1] = V[1][k]; qv[2] = V[2][k]; qv[3] = V[3][k]; }  // largest eigenvalue
+    for (int k = 1; k < 4; ++k)
+      if (Q[k][k] > best) { best = Q[k][k]; qv[0] = V[0][k]; qv[1] = V[1][k]; qv[2] = V[2][k]; qv[3] = V[3][k]; }  // largest eigenvalue
+  }
   const double nq = sqrt(qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2] + qv[3] * qv[3]);
   if (nq > 0.0) { qv[0] = qv[0] / nq; qv[1] = qv[1] / nq; qv[2] = qv[2] / nq; qv[3] = qv[3] / nq; }
   if (qv[0] < 0.0) { qv[0] = -qv[0]; qv[1] = -qv[1]; qv[2] = -qv[2]; qv[3] = -qv[3]; }
