@@ -127,6 +127,33 @@ int vpc_dbscan_slab_finish_dev(vpc_ctx* ctx, const int32_t* d_map_from, const in
 int vpc_uf_edges_dev(vpc_ctx* ctx, const int32_t* d_a, const int32_t* d_b, int64_t n_edges, int64_t n_nodes,
                      int32_t* d_root, void* stream);
 
+/* Slab exchange helpers for a cloud that is ALREADY cut into u-slabs (rank r holds s_lo <= x + y < s_hi).
+ * They keep the multi-GPU step free of host round trips: every message is a fixed-capacity buffer whose
+ * element count sits in slot 0, so NCCL transfer sizes are known to the host; a buffer that would overflow
+ * sets *d_overflow = 1 (the caller then falls back to the general path).
+ *   vpc_slab_halo_pack_dev  owned points within H of the lower/upper boundary -> buffers for the left/right
+ *                           neighbour: double[1 + 3*cap] = {count, x[cap], y[cap], global index[cap]}
+ *   vpc_slab_assemble_dev   local cloud = own points ++ left halo ++ right halo, NaN-padded to n + 2*cap
+ *                           (NaN points are outside the grid and cluster as noise, DBImproved.cs:41)
+ *   vpc_slab_pairs_dev      (global index, local key) of locally-core points that also live on a neighbour:
+ *                           int32[1 + 2*cap] = {count, gidx[cap], key[cap]}, pre-filled with INT32_MAX / count 0
+ *   vpc_slab_heads_dev      owned core points heading their merged cluster: int32[1 + cap] = {count, gidx[cap]}
+ *   vpc_slab_ids_dev        cluster id = first + 1 + rank of the key in the sorted (INT32_MAX-padded) head list */
+int vpc_slab_halo_pack_dev(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int32_t gidx0, double s_lo,
+                           double s_hi, double H, int32_t has_left, int32_t has_right, int32_t cap, double* d_buf_left,
+                           double* d_buf_right, int32_t* d_counters2, int32_t* d_overflow, void* stream);
+int vpc_slab_assemble_dev(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int32_t gidx0,
+                          const double* d_recv_left, const double* d_recv_right, int32_t cap, double* d_lx, double* d_ly,
+                          int32_t* d_lg, void* stream);
+int vpc_slab_pairs_dev(vpc_ctx* ctx, const double* d_lx, const double* d_ly, const int32_t* d_lg, const uint8_t* d_is_key,
+                       const int32_t* d_key, int64_t n_local, int64_t n_own, double s_lo, double s_hi, double H,
+                       int32_t has_left, int32_t has_right, int32_t cap, int32_t* d_buf, int32_t* d_overflow, void* stream);
+int vpc_slab_heads_dev(vpc_ctx* ctx, const int32_t* d_lg, const uint8_t* d_is_key, const int32_t* d_gkey, int64_t n_own,
+                       int32_t cap, int32_t* d_buf, int32_t* d_overflow, void* stream);
+int vpc_slab_ids_dev(vpc_ctx* ctx, const int32_t* d_gkey, const uint8_t* d_is_key_local, int64_t n_own,
+                     const int32_t* d_heads_sorted, int64_t n_heads_cap, int32_t first_cluster_id, int32_t* d_cluster_id,
+                     uint8_t* d_is_key, uint8_t* d_is_classed, void* stream);
+
 /* ---- ICP ------------------------------------------------------------------------ */
 
 /* Point sets are PLANAR: xyz = x[0..k) y[0..k) z[0..k) (one H2D copy, coalesced). */

@@ -173,3 +173,20 @@ def test_uf_edges(ctx):
     mins = np.full(lab.max() + 1, n_nodes)
     np.minimum.at(mins, lab, np.arange(n_nodes))
     np.testing.assert_array_equal(root, mins[lab])
+
+
+def test_slab_lean_single_rank(ctx, oracle):
+    # the sync-free pre-cut path (count-prefixed buffers, NaN padding) at world size 1
+    import torch
+    from vtkcloudpoint_b200.distributed import LeanSlabPlan, dbscan_slabs_lean
+    mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000)
+    dev = torch.device("cuda", 0)
+    plan = LeanSlabPlan(ctx, len(mx), [], 0.07, float(np.abs(mx).max() + np.abs(my).max()), dev)
+    for first in (0, 5):
+        cid, key, cls, amount, overflow = dbscan_slabs_lean(plan, torch.from_numpy(mx).to(dev), torch.from_numpy(my).to(dev), 0, 7, first)
+        torch.cuda.synchronize()
+        ocid, okey, ocls, oamount = oracle.dbscan(mx, my, 0.07, 7, first)
+        assert int(overflow.item()) == 0 and int(amount.item()) == oamount
+        np.testing.assert_array_equal(cid.cpu().numpy(), ocid)
+        np.testing.assert_array_equal(key.cpu().numpy(), okey)
+        np.testing.assert_array_equal(cls.cpu().numpy(), ocls)

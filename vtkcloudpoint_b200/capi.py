@@ -36,6 +36,11 @@ SIGNATURES = {
     "vpc_dbscan_slab_local_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _i32, _p, _p, _p]),
     "vpc_dbscan_slab_finish_dev": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
     "vpc_uf_edges_dev": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p]),
+    "vpc_slab_halo_pack_dev": (C.c_int, [_p, _p, _p, _i64, _i32, _f64, _f64, _f64, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "vpc_slab_assemble_dev": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p]),
+    "vpc_slab_pairs_dev": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _f64, _f64, _f64, _i32, _i32, _i32, _p, _p, _p]),
+    "vpc_slab_heads_dev": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _p]),
+    "vpc_slab_ids_dev": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _i32, _p, _p, _p, _p]),
     "vpc_closest_point_set": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p]),
     "vpc_icp_rigid": (C.c_int, [_p, _p, _i64, _p, _i64, _f64, _i32, _p, _p, _p, _p, _p]),
     "vpc_icp_set_model_dev": (C.c_int, [_p, _p, _i64, _p]),

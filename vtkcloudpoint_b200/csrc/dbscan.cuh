@@ -590,3 +590,105 @@ __global__ void __launch_bounds__(kDbBlock) k_uf_flatten(int* parent, int n) {
 }
 
 }  // namespace vpc
+
+// ---- slab exchange helpers: fixed-capacity, count-prefixed buffers, no host round trip ----------------
+// (vtkcloudpoint_b200/distributed.py, dbscan_slabs_lean).  A buffer holds its element count in slot 0 so that
+// it can travel through NCCL with a size known to the host; an overfull buffer raises *overflow.
+namespace vpc {
+
+// warp-aggregated append: returns this lane's slot (or -1 when !want)
+__device__ __forceinline__ int db_append_slot(bool want, int* counter) {
+  const unsigned m = __ballot_sync(kFull, want);
+  if (!m) return -1;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(kFull, base, leader);
+  return want ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// Owned points within H of the slab's lower / upper u-boundary go to the left / right neighbour as halo copies.
+// buf = [count | x[cap] | y[cap] | gidx-as-double[cap]]; counters[0..1] must be zero on entry.
+__global__ void __launch_bounds__(kDbBlock)
+k_slab_halo_pack(const double* __restrict__ x, const double* __restrict__ y, int n, int gidx0, double s_lo, double s_hi, double H,
+                 int has_left, int has_right, int cap, double* bufL, double* bufR, int* counters, int* overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool toL = false, toR = false;
+  double xi = 0, yi = 0;
+  if (i < n) {
+    xi = __ldg(x + i); yi = __ldg(y + i);
+    const double u = xi + yi;
+    if (finite_d(xi) && finite_d(yi) && finite_d(u) && finite_d(xi - yi)) {
+      toL = has_left && (u - H < s_lo);
+      toR = has_right && (u + H >= s_hi);
+    }
+  }
+  const int sl = db_append_slot(toL, counters + 0);
+  const int sr = db_append_slot(toR, counters + 1);
+  if (sl >= 0) { if (sl < cap) { bufL[1 + sl] = xi; bufL[1 + cap + sl] = yi; bufL[1 + 2 * cap + sl] = (double)(gidx0 + i); } else *overflow = 1; }
+  if (sr >= 0) { if (sr < cap) { bufR[1 + sr] = xi; bufR[1 + cap + sr] = yi; bufR[1 + 2 * cap + sr] = (double)(gidx0 + i); } else *overflow = 1; }
+}
+__global__ void k_slab_publish_counts(const int* counters, int cap, double* bufL, double* bufR) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { bufL[0] = (double)min(counters[0], cap); bufR[0] = (double)min(counters[1], cap); }
+}
+
+// local = own points ++ halo from the left ++ halo from the right, padded with NaN (= points outside the grid)
+__global__ void __launch_bounds__(kDbBlock)
+k_slab_assemble(const double* __restrict__ x, const double* __restrict__ y, int n, int gidx0, const double* __restrict__ recvL,
+                const double* __restrict__ recvR, int cap, double* __restrict__ lx, double* __restrict__ ly, int* __restrict__ lg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n + 2 * cap) return;
+  if (i < n) { lx[i] = __ldg(x + i); ly[i] = __ldg(y + i); lg[i] = gidx0 + i; return; }
+  const int cl = (int)recvL[0], cr = (int)recvR[0];
+  const int j = i - n;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  if (j < cl) { lx[i] = recvL[1 + j]; ly[i] = recvL[1 + cap + j]; lg[i] = (int)recvL[1 + 2 * cap + j]; }
+  else if (j - cl < cr) { const int k = j - cl; lx[i] = recvR[1 + k]; ly[i] = recvR[1 + cap + k]; lg[i] = (int)recvR[1 + 2 * cap + k]; }
+  else { lx[i] = nan; ly[i] = nan; lg[i] = -1; }
+}
+
+// (global index, local component key) of the locally-core points that also live on a neighbouring rank
+// buf = [count | gidx[cap] | key[cap]], unused slots hold INT_MAX
+__global__ void __launch_bounds__(kDbBlock)
+k_slab_pairs(const double* __restrict__ lx, const double* __restrict__ ly, const int* __restrict__ lg, const unsigned char* __restrict__ is_key,
+             const int* __restrict__ key, int n_local, int n_own, double s_lo, double s_hi, double H, int has_left, int has_right, int cap,
+             int* buf, int* overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool want = false;
+  if (i < n_local && is_key[i]) {
+    if (i >= n_own) want = true;                                   // a halo copy: its owner reports it too
+    else { const double u = lx[i] + ly[i]; want = (has_left && (u - H < s_lo)) || (has_right && (u + H >= s_hi)); }
+  }
+  const int s = db_append_slot(want, buf);
+  if (s >= 0) { if (s < cap) { buf[1 + s] = lg[i]; buf[1 + cap + s] = key[i]; } else *overflow = 1; }
+}
+
+// owned core points that are the minimum core index of their (merged) cluster
+__global__ void __launch_bounds__(kDbBlock)
+k_slab_heads(const int* __restrict__ lg, const unsigned char* __restrict__ is_key, const int* __restrict__ gkey, int n_own, int cap, int* buf,
+             int* overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool want = (i < n_own) && is_key[i] && gkey[i] == lg[i];
+  const int s = db_append_slot(want, buf);
+  if (s >= 0) { if (s < cap) buf[1 + s] = lg[i]; else *overflow = 1; }
+}
+
+// cluster id = first + 1 + rank of the key among all (sorted) cluster heads
+__global__ void __launch_bounds__(kDbBlock)
+k_slab_ids(const int* __restrict__ gkey, const unsigned char* __restrict__ is_key_l, int n_own, const int* __restrict__ heads_sorted, int n_heads_cap,
+           int first_cluster_id, int* __restrict__ cid, unsigned char* __restrict__ is_key, unsigned char* __restrict__ is_classed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_own) return;
+  const int k = gkey[i];
+  int id = 0;
+  if (k >= 0) {
+    int lo = 0, hi = n_heads_cap;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(heads_sorted + mid) < k) lo = mid + 1; else hi = mid; }
+    id = first_cluster_id + 1 + lo;
+  }
+  cid[i] = id;
+  is_key[i] = is_key_l[i];
+  is_classed[i] = id != 0;
+}
+
+}  // namespace vpc

@@ -476,6 +476,62 @@ int vpc_dbscan_slab_finish_dev(vpc_ctx* ctx, const int32_t* d_map_from, const in
   return VPC_OK;
 }
 
+// ---- slab exchange helpers (count-prefixed fixed-capacity buffers; see include/vpc.h) ----------------
+int vpc_slab_halo_pack_dev(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int32_t gidx0, double s_lo, double s_hi, double H,
+                           int32_t has_left, int32_t has_right, int32_t cap, double* d_buf_left, double* d_buf_right, int32_t* d_counters2,
+                           int32_t* d_overflow, void* stream) {
+  if (!ctx || n <= 0 || cap <= 0 || !d_x || !d_y || !d_buf_left || !d_buf_right || !d_counters2 || !d_overflow) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VPC_CUDA(ctx, cudaMemsetAsync(d_counters2, 0, 8, s));
+  VPC_LAUNCH(ctx, k_slab_halo_pack, blocks_for(n, kDbBlock), kDbBlock, s, d_x, d_y, (int)n, gidx0, s_lo, s_hi, H, has_left, has_right, cap,
+             d_buf_left, d_buf_right, d_counters2, d_overflow);
+  VPC_LAUNCH(ctx, k_slab_publish_counts, 1, 32, s, d_counters2, cap, d_buf_left, d_buf_right);
+  return VPC_OK;
+}
+
+int vpc_slab_assemble_dev(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, int32_t gidx0, const double* d_recv_left,
+                          const double* d_recv_right, int32_t cap, double* d_lx, double* d_ly, int32_t* d_lg, void* stream) {
+  if (!ctx || n <= 0 || cap <= 0 || !d_x || !d_y || !d_recv_left || !d_recv_right || !d_lx || !d_ly || !d_lg) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_slab_assemble, blocks_for(n + 2ll * cap, kDbBlock), kDbBlock, static_cast<cudaStream_t>(stream), d_x, d_y, (int)n, gidx0,
+             d_recv_left, d_recv_right, cap, d_lx, d_ly, d_lg);
+  return VPC_OK;
+}
+
+int vpc_slab_pairs_dev(vpc_ctx* ctx, const double* d_lx, const double* d_ly, const int32_t* d_lg, const uint8_t* d_is_key, const int32_t* d_key,
+                       int64_t n_local, int64_t n_own, double s_lo, double s_hi, double H, int32_t has_left, int32_t has_right, int32_t cap,
+                       int32_t* d_buf, int32_t* d_overflow, void* stream) {
+  if (!ctx || n_local <= 0 || cap <= 0 || !d_lx || !d_ly || !d_lg || !d_is_key || !d_key || !d_buf || !d_overflow) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_slab_pairs, blocks_for(n_local, kDbBlock), kDbBlock, static_cast<cudaStream_t>(stream), d_lx, d_ly, d_lg, d_is_key, d_key,
+             (int)n_local, (int)n_own, s_lo, s_hi, H, has_left, has_right, cap, d_buf, d_overflow);
+  return VPC_OK;
+}
+
+int vpc_slab_heads_dev(vpc_ctx* ctx, const int32_t* d_lg, const uint8_t* d_is_key, const int32_t* d_gkey, int64_t n_own, int32_t cap,
+                       int32_t* d_buf, int32_t* d_overflow, void* stream) {
+  if (!ctx || n_own <= 0 || cap <= 0 || !d_lg || !d_is_key || !d_gkey || !d_buf || !d_overflow) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_slab_heads, blocks_for(n_own, kDbBlock), kDbBlock, static_cast<cudaStream_t>(stream), d_lg, d_is_key, d_gkey, (int)n_own, cap,
+             d_buf, d_overflow);
+  return VPC_OK;
+}
+
+int vpc_slab_ids_dev(vpc_ctx* ctx, const int32_t* d_gkey, const uint8_t* d_is_key_local, int64_t n_own, const int32_t* d_heads_sorted,
+                     int64_t n_heads_cap, int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed, void* stream) {
+  if (!ctx || n_own <= 0 || n_heads_cap < 0 || !d_gkey || !d_is_key_local || !d_cluster_id || !d_is_key || !d_is_classed) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_slab_ids, blocks_for(n_own, kDbBlock), kDbBlock, static_cast<cudaStream_t>(stream), d_gkey, d_is_key_local, (int)n_own,
+             d_heads_sorted, (int)n_heads_cap, first_cluster_id, d_cluster_id, d_is_key, d_is_classed);
+  return VPC_OK;
+}
+
 int vpc_uf_edges_dev(vpc_ctx* ctx, const int32_t* d_a, const int32_t* d_b, int64_t n_edges, int64_t n_nodes, int32_t* d_root, void* stream) {
   if (!ctx) return VPC_E_BADARG;
   if (n_nodes < 0 || n_edges < 0 || (n_nodes > 0 && !d_root) || (n_edges > 0 && (!d_a || !d_b))) return fail(ctx, VPC_E_BADARG, "bad edge list");

@@ -332,3 +332,123 @@ def icp_rigid_sharded(backend, model_shard, idx_offset: int, data, e: float, max
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         state = backend.solve(sums, e, max_iters)
     return state, idx
+
+
+# ------------------------------------------------------------------------------------------------
+# DBSCAN over PRE-CUT slabs without host round trips
+# ------------------------------------------------------------------------------------------------
+class LeanSlabPlan:
+    """Buffers and constants for dbscan_slabs_lean: one cloud already cut into u-slabs (rank r holds
+    splitters[r-1] <= x + y < splitters[r]), at most `n` points on this rank.
+
+    Every message is a fixed-capacity, count-prefixed buffer (vpc_slab_* helpers), so the whole step -- halo
+    exchange with the two neighbours (NCCL send/recv), local clustering, all_gather of the boundary component
+    keys, union-find merge, all_gather of the cluster heads, numbering -- is ENQUEUED without a single host
+    synchronisation.  `coord_bound` >= max(|x + y|, |x - y|) over the whole cloud sizes the rounding slack of the
+    halo width (pass it; computing it would cost a reduction and a sync per call)."""
+
+    INT_MAX = 2 ** 31 - 1
+
+    def __init__(self, ctx, n: int, splitters, eps: float, coord_bound: float, device, group=None, halo_frac: float = 0.08,
+                 pair_frac: float = 0.08, head_frac: float = 0.08):
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = _world(group)
+        self.n, self.eps, self.dev = int(n), float(eps), device
+        s = [float(v) for v in splitters]
+        assert len(s) == self.world - 1
+        err = coord_bound * 2.0 ** -52
+        self.H = 2.0 * (eps * (1.0 + 2.0 ** -30) + 8.0 * err) * (1.0 + 2.0 ** -30)
+        if any(b - a < self.H for a, b in zip(s[:-1], s[1:])):
+            raise ValueError("a slab is thinner than the halo: use dbscan_slabs (general path)")
+        self.has_left, self.has_right = self.rank > 0, self.rank < self.world - 1
+        self.s_lo = s[self.rank - 1] if self.has_left else -math.inf
+        self.s_hi = s[self.rank] if self.has_right else math.inf
+        self.cap = max(1024, int(n * halo_frac))
+        self.cap_pairs = max(1024, int(n * pair_frac))
+        self.cap_heads = max(1024, int(n * head_frac))
+        f64, i32, u8 = torch.float64, torch.int32, torch.uint8
+        z = lambda k, dt: torch.zeros(k, dtype=dt, device=device)  # noqa: E731
+        self.bufL, self.bufR = z(1 + 3 * self.cap, f64), z(1 + 3 * self.cap, f64)
+        self.recvL, self.recvR = z(1 + 3 * self.cap, f64), z(1 + 3 * self.cap, f64)     # count 0 unless a neighbour writes
+        self.counters, self.overflow = z(2, i32), z(1, i32)
+        self.n_max = self.n + 2 * self.cap
+        self.lx, self.ly, self.lg = z(self.n_max, f64), z(self.n_max, f64), z(self.n_max, i32)
+        self.is_key_l, self.key_l, self.gkey = z(self.n_max, u8), z(self.n_max, i32), z(self.n_max, i32)
+        self.pairs_tpl = torch.full((1 + 2 * self.cap_pairs,), self.INT_MAX, dtype=i32, device=device)
+        self.pairs_tpl[0] = 0
+        self.pairs = self.pairs_tpl.clone()
+        self.pairs_all = z(self.world * (1 + 2 * self.cap_pairs), i32)
+        self.heads_tpl = torch.full((1 + self.cap_heads,), self.INT_MAX, dtype=i32, device=device)
+        self.heads_tpl[0] = 0
+        self.heads = self.heads_tpl.clone()
+        self.heads_all = z(self.world * (1 + self.cap_heads), i32)
+        self.n_nodes = self.world * self.cap_pairs
+        self.root = z(self.n_nodes, i32)
+        self.cid, self.is_key, self.is_classed = z(self.n, i32), z(self.n, u8), z(self.n, u8)
+
+
+def dbscan_slabs_lean(plan: LeanSlabPlan, x, y, gidx0: int, min_pts: int, first_cluster_id: int = 0):
+    """One exact DBSCAN of the whole (pre-cut) cloud across the GPUs, enqueued without host synchronisation.
+    x, y: this rank's slab (float64 CUDA tensors of plan.n points; element i has global index gidx0 + i).
+    Returns (cluster_id, is_key, is_classed, cluster_amount[1] int32 tensor, overflow[1] int32 tensor) -- device
+    tensors owned by the plan.  A non-zero overflow means a fixed-capacity buffer was too small: rerun through
+    dbscan_slabs (or a plan with larger *_frac)."""
+    if min_pts <= 0:
+        raise NotImplementedError("min_pts <= 0: use the single-GPU entry point")
+    p, lib, h = plan, plan.ctx._lib, plan.ctx._h
+    assert x.numel() == p.n and y.numel() == p.n and x.is_contiguous() and y.is_contiguous()
+    st = torch.cuda.current_stream(p.dev).cuda_stream
+    chk = plan.ctx._check
+    p.overflow.zero_()
+    chk(lib.vpc_slab_halo_pack_dev(h, x.data_ptr(), y.data_ptr(), p.n, int(gidx0), p.s_lo, p.s_hi, p.H, int(p.has_left), int(p.has_right),
+                                   p.cap, p.bufL.data_ptr(), p.bufR.data_ptr(), p.counters.data_ptr(), p.overflow.data_ptr(), st))
+    if p.world > 1:
+        ops = []
+        if p.has_left:
+            ops += [dist.P2POp(dist.isend, p.bufL, p.rank - 1, p.group), dist.P2POp(dist.irecv, p.recvL, p.rank - 1, p.group)]
+        if p.has_right:
+            ops += [dist.P2POp(dist.isend, p.bufR, p.rank + 1, p.group), dist.P2POp(dist.irecv, p.recvR, p.rank + 1, p.group)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    chk(lib.vpc_slab_assemble_dev(h, x.data_ptr(), y.data_ptr(), p.n, int(gidx0), p.recvL.data_ptr(), p.recvR.data_ptr(), p.cap,
+                                  p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), st))
+    chk(lib.vpc_dbscan_slab_local_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.n_max, p.eps, int(min_pts),
+                                      p.is_key_l.data_ptr(), p.key_l.data_ptr(), st))
+    if p.world > 1:
+        p.pairs.copy_(p.pairs_tpl)
+        chk(lib.vpc_slab_pairs_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.is_key_l.data_ptr(), p.key_l.data_ptr(), p.n_max, p.n,
+                                   p.s_lo, p.s_hi, p.H, int(p.has_left), int(p.has_right), p.cap_pairs, p.pairs.data_ptr(),
+                                   p.overflow.data_ptr(), st))
+        dist.all_gather_into_tensor(p.pairs_all, p.pairs, group=p.group)
+        pa = p.pairs_all.view(p.world, 1 + 2 * p.cap_pairs)
+        G = pa[:, 1:1 + p.cap_pairs].reshape(-1)
+        K = pa[:, 1 + p.cap_pairs:].reshape(-1)
+        srt = torch.sort(G)                                     # equal global indices become adjacent
+        Gs, Ks = srt.values, K[srt.indices]
+        nodes = torch.sort(K).values                            # node id of a key = its first slot in the sorted keys
+        ia = torch.searchsorted(nodes, Ks[:-1].contiguous()).to(torch.int32)
+        ib = torch.searchsorted(nodes, Ks[1:].contiguous()).to(torch.int32)
+        ib = torch.where((Gs[1:] == Gs[:-1]) & (Gs[1:] != LeanSlabPlan.INT_MAX), ib, ia).contiguous()   # no edge -> self loop
+        chk(lib.vpc_uf_edges_dev(h, ia.data_ptr(), ib.data_ptr(), ia.numel(), p.n_nodes, p.root.data_ptr(), st))
+        map_from, map_to = nodes, nodes[p.root.long()].contiguous()
+        n_map = p.n_nodes
+    else:
+        map_from = map_to = p.root
+        n_map = 0
+    chk(lib.vpc_dbscan_slab_finish_dev(h, map_from.data_ptr(), map_to.data_ptr(), n_map, p.gkey.data_ptr(), st))
+    p.heads.copy_(p.heads_tpl)
+    chk(lib.vpc_slab_heads_dev(h, p.lg.data_ptr(), p.is_key_l.data_ptr(), p.gkey.data_ptr(), p.n, p.cap_heads, p.heads.data_ptr(),
+                               p.overflow.data_ptr(), st))
+    if p.world > 1:
+        dist.all_gather_into_tensor(p.heads_all, p.heads, group=p.group)
+    else:
+        p.heads_all.copy_(p.heads)
+    ha = p.heads_all.view(p.world, 1 + p.cap_heads)
+    heads_sorted = torch.sort(ha[:, 1:].reshape(-1)).values.contiguous()
+    amount = (first_cluster_id + torch.clamp(ha[:, 0], max=p.cap_heads).sum()).to(torch.int32).reshape(1)
+    chk(lib.vpc_slab_ids_dev(h, p.gkey.data_ptr(), p.is_key_l.data_ptr(), p.n, heads_sorted.data_ptr(), heads_sorted.numel(),
+                             int(first_cluster_id), p.cid.data_ptr(), p.is_key.data_ptr(), p.is_classed.data_ptr(), st))
+    if p.world > 1:
+        dist.all_reduce(p.overflow, op=dist.ReduceOp.MAX, group=p.group)
+    return p.cid, p.is_key, p.is_classed, amount, p.overflow
+
