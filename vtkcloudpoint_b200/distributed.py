@@ -349,8 +349,8 @@ class LeanSlabPlan:
 
     INT_MAX = 2 ** 31 - 1
 
-    def __init__(self, ctx, n: int, splitters, eps: float, coord_bound: float, device, group=None, halo_frac: float = 0.08,
-                 pair_frac: float = 0.08, head_frac: float = 0.08):
+    def __init__(self, ctx, n: int, splitters, eps: float, coord_bound: float, device, group=None, halo_frac: float = 0.05,
+                 pair_frac: float = 0.03, head_frac: float = 0.04):
         self.ctx, self.group = ctx, group
         self.rank, self.world = _world(group)
         self.n, self.eps, self.dev = int(n), float(eps), device
