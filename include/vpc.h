@@ -192,6 +192,24 @@ int vpc_closest_point_set_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n,
 int vpc_icp_rigid_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t n, double e, int32_t max_iters,
                       double* d_state_out, int32_t* d_order_last, void* stream);
 
+/* ---- around the path: the matching and statistics steps on either side of DBSCAN / ICP ----
+ *
+ * vpc_match_within: replaces the search loop of MainForm.RecorrectMatchingPtsByDistance (FrmMain.cs:3588-3618): for every
+ *   (transformed) cluster centre the nearest truth point by getDisP = sqrt(dx*dx + dy*dy + dz*dz) (FrmMain.cs:829-835),
+ *   first minimum wins (:3597-3601); matched_id[j] = that truth index if the distance < match_distance (:3603), else -1
+ *   (Point3D.isMatched / matchNum).  dist (nullable) = the minimal distance.  Planar xyz like the ICP calls.
+ * vpc_match_within_dev: same on device pointers after vpc_icp_set_model_dev(truth points).
+ * vpc_cluster_means_dev: Tools.GetClusList's per-cluster averages (Tools.cs:187-194) as a segmented reduction:
+ *   d_vals is planar [n_fields][n] (e.g. X, Y, Z, motor_x, motor_y); d_means is planar [n_fields][n_clusters + 1], entry c
+ *   = mean over the points with cluster_id == c (NaN for an empty cluster, entry 0 unused); d_counts[n_clusters + 1].
+ *   Floating-point sums are accumulated in parallel: equal to the C#'s sequential Average within 1e-12 relative. */
+int vpc_match_within(vpc_ctx* ctx, const double* truth_xyz, int64_t m, const double* centers_xyz, int64_t n,
+                     double match_distance, int32_t* matched_id, double* dist);
+int vpc_match_within_dev(vpc_ctx* ctx, const double* d_centers_xyz, int64_t n, double match_distance,
+                         int32_t* d_matched_id, double* d_dist, void* stream);
+int vpc_cluster_means_dev(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, const double* d_vals,
+                          int32_t n_fields, double* d_means, int32_t* d_counts, void* stream);
+
 /* ---- ICP across GPUs: the model is sharded (one shard per GPU, vpc_icp_set_model_dev on each), the
  * data is replicated.  One round of ICP.go_hell_ICP (ICP.cs:23-180) becomes
  *   vpc_icp_shard_nn_dev          local nearest model point: d2[i], idx[i] = local index + idx_offset

@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         "vpco_icp_rigid": [_p, _i64, _p, _i64, _f64, _i32, _p, _p, _p, _p, _p, C.c_int, C.c_int],
         "vpco_jacobi_eig": [_p, C.c_int, _p, _p, C.c_int, _f64],
         "vpco_trans_points": [_p, _i64, _p, _p, _p],
+        "vpco_match_within_literal": [_p, _i64, _p, _i64, _f64, _p, _p],
     }
     for name, args in sig.items():
         fn = getattr(dll, name)
@@ -135,3 +136,14 @@ def trans_points(src_xyz, R, T):
     T = np.ascontiguousarray(T, np.float64).reshape(3)
     lib().vpco_trans_points(_ptr(src), src.shape[1], _ptr(R), _ptr(T), _ptr(dst))
     return dst
+
+
+def match_within(truth_xyz, centers_xyz, match_distance):
+    truth, cen = _planar(truth_xyz), _planar(centers_xyz)
+    n = cen.shape[1]
+    mid = np.empty(n, np.int32)
+    dist = np.empty(n, np.float64)
+    rc = lib().vpco_match_within_literal(_ptr(truth), truth.shape[1], _ptr(cen), n, match_distance, _ptr(mid), _ptr(dist))
+    if rc != 0:
+        raise RuntimeError(f"oracle match_within rc={rc}")
+    return mid, dist

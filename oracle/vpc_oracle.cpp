@@ -443,6 +443,29 @@ int vpco_closest_point_set_grid(const double* model_xyz, int64_t m, const double
   return VPCO_OK;
 }
 
+int vpco_match_within_literal(const double* truth_xyz, int64_t m, const double* centers_xyz, int64_t n, double match_distance,
+                              int32_t* matched_id, double* dist) {
+  // MainForm.RecorrectMatchingPtsByDistance, FrmMain.cs:3588-3618 with getDisP, FrmMain.cs:829-835
+  if (m <= 0 || n < 0 || !truth_xyz || (n > 0 && (!centers_xyz || !matched_id))) return VPCO_E_BADARG;
+  const double *TX = truth_xyz, *TY = truth_xyz + m, *TZ = truth_xyz + 2 * m;
+  const double *CX = centers_xyz, *CY = centers_xyz + n, *CZ = centers_xyz + 2 * n;
+  auto get_dis_p = [&](int64_t i, int64_t j) {
+    double dx = TX[i] - CX[j], dy = TY[i] - CY[j], dz = TZ[i] - CZ[j];   // :831-833 (truth - centre)
+    return std::sqrt(dx * dx + dy * dy + dz * dz);                       // :834
+  };
+  for (int64_t j = 0; j < n; ++j) {
+    int32_t id = 0;                                                       // :3594
+    double best = get_dis_p(0, j);                                        // :3596
+    for (int64_t i = 0; i < m; ++i) {                                     // :3597
+      double ddd = get_dis_p(i, j);
+      if (ddd < best) { best = ddd; id = (int32_t)i; }                    // :3600-3604
+    }
+    matched_id[j] = (best < match_distance) ? id : -1;                    // :3605-3611
+    if (dist) dist[j] = best;
+  }
+  return VPCO_OK;
+}
+
 int vpco_jacobi_eig(double* a, int n, double* eigval, double* v, int max_it, double eps) {
   // Matrix.ComputeEvJacobi, Matrix.cs:571-668, classical (largest off-diagonal pivot) Jacobi.
   // The C# rotation loops ignore their loop index (defect iv in SURVEY 8a-a11); the index

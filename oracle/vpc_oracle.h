@@ -75,6 +75,11 @@ int vpco_icp_rigid(const double* model_xyz, int64_t m, const double* data_xyz, i
                    double e, int32_t max_iters, double R[9], double T[3], int32_t* iters_done,
                    double* sse_last, int32_t* order_last, int use_grid, int n_threads);
 
+/* MainForm.RecorrectMatchingPtsByDistance's search, FrmMain.cs:3588-3618: nearest truth point by
+ * sqrt(dx*dx+dy*dy+dz*dz), first minimum wins; matched_id = -1 when not < match_distance. */
+int vpco_match_within_literal(const double* truth_xyz, int64_t m, const double* centers_xyz, int64_t n,
+                              double match_distance, int32_t* matched_id, double* dist);
+
 /* Matrix.ComputeEvJacobi with the commented-out indices (Matrix.cs:621-624, 644, 655-656,
  * 664-665) restored.  a: n x n row-major symmetric, destroyed; v: eigenvectors in
  * columns.  Returns 1 on convergence, 0 otherwise (like the C# bool). */

@@ -139,3 +139,43 @@ def test_icp_shard_steps_single_rank(ctx, oracle):
     assert int(st[13]) == it == 6
     np.testing.assert_array_equal(order.cpu().numpy(), oo)
     assert _rel(st[:9].reshape(3, 3), Ro) < RTOL and _rel(st[9:12], To) < RTOL and abs(st[12] - sse) <= RTOL * sse
+
+
+def test_match_within(ctx, oracle):
+    # MainForm.RecorrectMatchingPtsByDistance (FrmMain.cs:3588-3618): sqrt-ranked nearest truth point + threshold
+    rng = np.random.default_rng(9)
+    for m, n, thr in ((196, 196, 0.05), (1, 10, 1.0), (3000, 2000, 0.3)):
+        truth = rng.uniform(0, 10, (3, m))
+        cen = truth[:, rng.integers(0, m, n)] + rng.normal(0, 0.04, (3, n))
+        mid, dist = ctx.match_within(truth, cen, thr)
+        omid, odist = oracle.match_within(truth, cen, thr)
+        np.testing.assert_array_equal(mid, omid)
+        np.testing.assert_array_equal(dist, odist)
+    # lattice with duplicated truth points: exact ties, also ties created by the rounding of sqrt
+    g = np.arange(5.0)
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij")).reshape(3, -1)
+    truth = np.concatenate([lat, lat[:, ::-1]], axis=1)
+    cen = rng.integers(0, 9, (3, 800)) * 0.5
+    mid, dist = ctx.match_within(truth, cen, 0.8)
+    omid, odist = oracle.match_within(truth, cen, 0.8)
+    np.testing.assert_array_equal(mid, omid)
+    np.testing.assert_array_equal(dist, odist)
+
+
+def test_cluster_means_dev(ctx):
+    # Tools.GetClusList's per-cluster averages (Tools.cs:187-194) as a segmented reduction
+    import torch
+    rng = np.random.default_rng(10)
+    n, k = 20_000, 300
+    cid = rng.integers(0, k + 1, n).astype(np.int32)
+    cid[cid == 7] = 0                                     # an empty cluster
+    vals = rng.normal(size=(5, n)) * 100 + 1000
+    means, counts = ctx.cluster_means_dev(torch.from_numpy(cid).cuda(), k, torch.from_numpy(vals).cuda())
+    means, counts = means.cpu().numpy(), counts.cpu().numpy()
+    for c in range(1, k + 1):
+        sel = cid == c
+        assert counts[c] == sel.sum()
+        if sel.any():
+            np.testing.assert_allclose(means[:, c], [np.cumsum(v[sel])[-1] / sel.sum() for v in vals], rtol=1e-12)
+        else:
+            assert np.isnan(means[:, c]).all()

@@ -181,6 +181,29 @@ class Context:
                                             _ptr(order) if order is not None else None))
         return IcpResult(R.reshape(3, 3), T, int(iters.value), float(sse.value), order)
 
+    def match_within(self, truth_xyz, centers_xyz, match_distance: float):
+        """MainForm.RecorrectMatchingPtsByDistance's search (FrmMain.cs:3588-3618): (matched_id int32 [-1 = unmatched], dist)."""
+        truth, cen = _planar(truth_xyz), _planar(centers_xyz)
+        n = cen.shape[1]
+        mid = np.empty(n, np.int32)
+        dist = np.empty(n, np.float64)
+        self._check(self._lib.vpc_match_within(self._h, _ptr(truth), truth.shape[1], _ptr(cen), n, float(match_distance), _ptr(mid), _ptr(dist)))
+        return mid, dist
+
+    def cluster_means_dev(self, cluster_id, n_clusters: int, vals_planar):
+        """Tools.GetClusList's averages (Tools.cs:187-194) on the device.  cluster_id: int32 CUDA tensor [n]; vals_planar:
+        float64 CUDA tensor [n_fields, n].  Returns (means [n_fields, n_clusters + 1], counts int32 [n_clusters + 1])."""
+        import torch
+        assert cluster_id.is_cuda and cluster_id.dtype == torch.int32 and vals_planar.is_cuda and vals_planar.dtype == torch.float64
+        assert vals_planar.is_contiguous() and cluster_id.is_contiguous() and vals_planar.shape[1] == cluster_id.numel()
+        nf = vals_planar.shape[0]
+        means = torch.empty((nf, n_clusters + 1), dtype=torch.float64, device=cluster_id.device)
+        counts = torch.empty(n_clusters + 1, dtype=torch.int32, device=cluster_id.device)
+        stream = torch.cuda.current_stream(cluster_id.device).cuda_stream
+        self._check(self._lib.vpc_cluster_means_dev(self._h, cluster_id.data_ptr(), cluster_id.numel(), int(n_clusters), vals_planar.data_ptr(),
+                                                    nf, means.data_ptr(), counts.data_ptr(), stream))
+        return means, counts
+
     # ------------------------------------------------------------------ ICP, device tensors
     def icp_set_model_dev(self, model_planar):
         """model_planar: float64 CUDA tensor of shape (3, m), contiguous.  It must stay alive while queries run."""

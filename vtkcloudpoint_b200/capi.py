@@ -46,6 +46,9 @@ SIGNATURES = {
     "vpc_icp_set_model_dev": (C.c_int, [_p, _p, _i64, _p]),
     "vpc_closest_point_set_dev": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "vpc_icp_rigid_dev": (C.c_int, [_p, _p, _i64, _f64, _i32, _p, _p, _p]),
+    "vpc_match_within": (C.c_int, [_p, _p, _i64, _p, _i64, _f64, _p, _p]),
+    "vpc_match_within_dev": (C.c_int, [_p, _p, _i64, _f64, _p, _p, _p]),
+    "vpc_cluster_means_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _p, _p]),
     "vpc_icp_shard_begin_dev": (C.c_int, [_p, _i64, _p]),
     "vpc_icp_shard_nn_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
     "vpc_icp_shard_select_dev": (C.c_int, [_p, _i64, _p, _p, _p, _p]),

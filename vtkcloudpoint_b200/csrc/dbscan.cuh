@@ -692,3 +692,36 @@ k_slab_ids(const int* __restrict__ gkey, const unsigned char* __restrict__ is_ke
 }
 
 }  // namespace vpc
+
+// ---- cluster statistics: Tools.GetClusList's per-cluster means (Tools.cs:187-194) as a segmented reduction ----
+namespace vpc {
+// sums[f * (n_clusters + 1) + c] += vals[f * n + i] for c = cluster_id[i] in 1..n_clusters; counts[c] += 1.
+// One warp-aggregated atomic per run of equal ids keeps the pressure on hot clusters low.
+__global__ void __launch_bounds__(kDbBlock)
+k_cluster_sums(const int* __restrict__ cluster_id, int n, int n_clusters, const double* __restrict__ vals, int n_fields,
+               double* __restrict__ sums, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = 0;
+  if (i < n) { c = cluster_id[i]; if (c < 1 || c > n_clusters) c = 0; }
+  const unsigned grp = __match_any_sync(kFull, c);
+  if (c == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+  if (lane == leader) atomicAdd(&counts[c], __popc(grp));
+  for (int f = 0; f < n_fields; ++f) {
+    double v = __ldg(vals + (long long)f * n + i);
+    // sum the group's values on the leader (lanes of a group walk their mask)
+    double acc = 0.0;
+    unsigned m = grp;
+    while (m) { const int src = __ffs(m) - 1; acc += __shfl_sync(grp, v, src); m &= m - 1; }
+    if (lane == leader) atomicAdd(&sums[(long long)f * (n_clusters + 1) + c], acc);
+  }
+}
+__global__ void __launch_bounds__(kDbBlock)
+k_cluster_means(int n_clusters, int n_fields, const double* __restrict__ sums, const int* __restrict__ counts, double* __restrict__ means) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_clusters) return;
+  const int k = counts[c];
+  for (int f = 0; f < n_fields; ++f)
+    means[(long long)f * (n_clusters + 1) + c] = (k > 0) ? sums[(long long)f * (n_clusters + 1) + c] / (double)k : __longlong_as_double(0x7ff8000000000000ll);
+}
+}  // namespace vpc

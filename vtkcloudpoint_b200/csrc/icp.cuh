@@ -178,13 +178,18 @@ struct NnBest {
   double x, y, z;
 };
 
+template <bool kSqrt = false>
 __device__ __forceinline__ void icp_consider(NnBest& b, double2 a, double2 w, double px, double py, double pz) {
-  const double d2 = icp_sqd(px, py, pz, a.x, a.y, w.x);
+  // kSqrt: candidates are ranked by the ROUNDED distance like FrmMain.cs:829-835 / :3594-3601 (sqrt can merge
+  // distinct d2 into one value, which then ties to the lowest index); otherwise by d2 like ICP.cs:238-244
+  double d2 = icp_sqd(px, py, pz, a.x, a.y, w.x);
+  if (kSqrt) d2 = sqrt(d2);
   const int i = (int)__double_as_longlong(w.y);
   if (d2 < b.d || (d2 == b.d && i < b.i)) { b.d = d2; b.i = i; b.x = a.x; b.y = a.y; b.z = w.x; }
 }
 
 // candidates [j0, j1) of the cell-ordered model; two records (four 128-bit loads) in flight
+template <bool kSqrt = false>
 __device__ __forceinline__ void icp_scan_range(const double4* __restrict__ spts, int j0, int j1, double px, double py,
                                                double pz, NnBest& b) {
   const double2* s2 = reinterpret_cast<const double2*>(spts);
@@ -192,12 +197,13 @@ __device__ __forceinline__ void icp_scan_range(const double4* __restrict__ spts,
     const int j2 = min(j + 1, j1 - 1);
     const double2 a0 = __ldg(s2 + 2 * j), w0 = __ldg(s2 + 2 * j + 1);
     const double2 a1 = __ldg(s2 + 2 * j2), w1 = __ldg(s2 + 2 * j2 + 1);
-    icp_consider(b, a0, w0, px, py, pz);
-    icp_consider(b, a1, w1, px, py, pz);   // j2 == j repeats a record: harmless for an argmin
+    icp_consider<kSqrt>(b, a0, w0, px, py, pz);
+    icp_consider<kSqrt>(b, a1, w1, px, py, pz);   // j2 == j repeats a record: harmless for an argmin
   }
 }
 
 // true when nothing outside the searched cell box [lo, hi] can be closer than, or as close as, the best so far
+template <bool kSqrt = false>
 __device__ __forceinline__ bool icp_box_done(const IcpGridCtrl& c, const double* p, const int* lo, const int* hi,
                                              const NnBest& b, double slack) {
   bool all = true;
@@ -209,12 +215,13 @@ __device__ __forceinline__ bool icp_box_done(const IcpGridCtrl& c, const double*
   }
   if (all) return true;
   const double lbs = lb - slack;
-  return b.i != 0x7fffffff && lbs > 0.0 && b.d < lbs * lbs * (1.0 - 9.094947017729282e-13);
+  return b.i != 0x7fffffff && lbs > 0.0 && b.d < (kSqrt ? lbs : lbs * lbs) * (1.0 - 9.094947017729282e-13);
 }
 
 // Exact argmin_j d2(p, model[j]) with ties to the lowest j (ICP.cs:229-248) for a finite p over the
 // finite model points.  Search order: the 2x2x2 block of cells nearest to p, then the 3x3x3 block, then
 // shells of cells outward -- each time until nothing outside the searched box can beat or tie the best.
+template <bool kSqrt = false>
 __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl& c, double px, double py, double pz,
                                             NnBest& b) {
   b.d = INFINITY; b.i = 0x7fffffff; b.x = b.y = b.z = 0.0;
@@ -231,8 +238,8 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
   {  // stage 0: the query's own cell.  Once ICP has (nearly) converged the match is much closer than the cell
      // walls for most points, and one cell (about one 32-byte record) is all that has to be read.
     const int own = (cc[2] * c.nc[1] + cc[1]) * c.nc[0] + cc[0];
-    icp_scan_range(g.spts, __ldg(g.cell_start + own), __ldg(g.cell_start + own + 1), px, py, pz, b);
-    if (b.i != 0x7fffffff && icp_box_done(c, p, cc, cc, b, slack)) return;
+    icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + own), __ldg(g.cell_start + own + 1), px, py, pz, b);
+    if (b.i != 0x7fffffff && icp_box_done<kSqrt>(c, p, cc, cc, b, slack)) return;
   }
   {  // stage 1: nearest octant block, at most 4 row segments; all range loads first
     int j0[4], j1[4];
@@ -257,11 +264,11 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        if (j0[r] + k < j1[r]) icp_consider(b, ra[r], rw[r], px, py, pz);
+        if (j0[r] + k < j1[r]) icp_consider<kSqrt>(b, ra[r], rw[r], px, py, pz);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) icp_scan_range(g.spts, j0[r] + 2, j1[r], px, py, pz, b);
-    if (icp_box_done(c, p, lo, hi, b, slack)) return;
+    for (int r = 0; r < 4; ++r) icp_scan_range<kSqrt>(g.spts, j0[r] + 2, j1[r], px, py, pz, b);
+    if (icp_box_done<kSqrt>(c, p, lo, hi, b, slack)) return;
   }
   const int rmax = max(c.nc[0], max(c.nc[1], c.nc[2]));
   for (int r = 1; r <= rmax; ++r) {
@@ -279,9 +286,9 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
           a1[t] = ok ? __ldg(g.cell_start + row + hi[0] + 1) : 0;
         }
 #pragma unroll
-        for (int t = 0; t < 3; ++t) icp_scan_range(g.spts, a0[t], a1[t], px, py, pz, b);
+        for (int t = 0; t < 3; ++t) icp_scan_range<kSqrt>(g.spts, a0[t], a1[t], px, py, pz, b);
       }
-      if (icp_box_done(c, p, lo, hi, b, slack)) return;
+      if (icp_box_done<kSqrt>(c, p, lo, hi, b, slack)) return;
       continue;
     }
     for (int z = lo[2]; z <= hi[2]; ++z) {
@@ -289,29 +296,31 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
         const int row = (z * c.nc[1] + y) * c.nc[0];
         const bool shell_row = (r == 1) || (abs(z - cc[2]) == r) || (abs(y - cc[1]) == r);
         if (shell_row) {
-          icp_scan_range(g.spts, __ldg(g.cell_start + row + lo[0]), __ldg(g.cell_start + row + hi[0] + 1), px, py, pz, b);
+          icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + row + lo[0]), __ldg(g.cell_start + row + hi[0] + 1), px, py, pz, b);
         } else {
-          if (cc[0] - r >= 0) icp_scan_range(g.spts, __ldg(g.cell_start + row + cc[0] - r), __ldg(g.cell_start + row + cc[0] - r + 1), px, py, pz, b);
-          if (cc[0] + r <= c.nc[0] - 1) icp_scan_range(g.spts, __ldg(g.cell_start + row + cc[0] + r), __ldg(g.cell_start + row + cc[0] + r + 1), px, py, pz, b);
+          if (cc[0] - r >= 0) icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + row + cc[0] - r), __ldg(g.cell_start + row + cc[0] - r + 1), px, py, pz, b);
+          if (cc[0] + r <= c.nc[0] - 1) icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + row + cc[0] + r), __ldg(g.cell_start + row + cc[0] + r + 1), px, py, pz, b);
         }
       }
     }
-    if (icp_box_done(c, p, lo, hi, b, slack)) return;
+    if (icp_box_done<kSqrt>(c, p, lo, hi, b, slack)) return;
   }
 }
 
 // Full reference semantics for one data point, including the non-finite corner cases of the
 // literal scan (min starts at d(i,0); 'd < min' is false for NaN).
+template <bool kSqrt = false>
 __device__ __forceinline__ void icp_match(const IcpModel& g, const IcpGridCtrl& c, double px, double py, double pz,
                                           NnBest& b) {
   bool searched = false;
   if (!c.model0_nan && c.n_valid > 0 && finite3(px, py, pz)) {
-    icp_nearest(g, c, px, py, pz, b);
+    icp_nearest<kSqrt>(g, c, px, py, pz, b);
     searched = (b.i != 0x7fffffff);
   }
   if (!searched) {
     b.x = g.xyz[0]; b.y = g.xyz[g.m]; b.z = g.xyz[2ll * g.m];
     b.i = 0; b.d = icp_sqd(px, py, pz, b.x, b.y, b.z);
+    if (kSqrt) b.d = sqrt(b.d);
   }
 }
 
@@ -325,6 +334,21 @@ k_icp_closest(IcpModel g, const double* __restrict__ data, int n, int* __restric
   icp_match(g, c, __ldg(data + i), __ldg(data + n + i), __ldg(data + 2ll * n + i), b);
   order[i] = b.i;
   if (sqdist) sqdist[i] = b.d;
+}
+
+// ---- thresholded nearest match: MainForm.RecorrectMatchingPtsByDistance (FrmMain.cs:3588-3618) ----------
+// For every (transformed) centroid the nearest truth point by getDisP = sqrt(dx*dx + dy*dy + dz*dz) (FrmMain.cs:829-835),
+// first minimum wins (:3597-3601); matched iff that distance < match_distance (:3603).  matched_id = -1 otherwise.
+__global__ void __launch_bounds__(kIcpBlock)
+k_match_within(IcpModel g, const double* __restrict__ data, int n, double match_distance, int* __restrict__ matched_id,
+               double* __restrict__ dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const IcpGridCtrl c = *g.ctrl;
+  NnBest b;
+  icp_match<true>(g, c, __ldg(data + i), __ldg(data + n + i), __ldg(data + 2ll * n + i), b);
+  matched_id[i] = (b.d < match_distance) ? b.i : -1;
+  if (dist) dist[i] = b.d;
 }
 
 // One cyclic-Jacobi rotation on the symmetric 4x4 A (annihilates A[P][Q]) with static indices so that

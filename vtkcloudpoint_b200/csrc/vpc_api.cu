@@ -646,6 +646,65 @@ int vpc_icp_shard_solve_dev(vpc_ctx* ctx, const double* d_sums16, int64_t n, dou
   return VPC_OK;
 }
 
+int vpc_match_within_dev(vpc_ctx* ctx, const double* d_centers_xyz, int64_t n, double match_distance, int32_t* d_matched_id,
+                         double* d_dist, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || (n > 0 && (!d_centers_xyz || !d_matched_id))) return fail(ctx, VPC_E_BADARG, "bad centers/matched_id");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->model_set) return fail(ctx, VPC_E_STATE, "vpc_icp_set_model_dev (the truth points) has not been called");
+  if (n == 0) return VPC_OK;
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_match_within, blocks_for(n, kIcpBlock), kIcpBlock, static_cast<cudaStream_t>(stream), ctx->model, d_centers_xyz, (int)n,
+             match_distance, d_matched_id, d_dist);
+  return VPC_OK;
+}
+
+int vpc_match_within(vpc_ctx* ctx, const double* truth_xyz, int64_t m, const double* centers_xyz, int64_t n, double match_distance,
+                     int32_t* matched_id, double* dist) {
+  if (!ctx) return VPC_E_BADARG;
+  if (m <= 0 || !truth_xyz) return fail(ctx, VPC_E_BADARG, "there must be at least one truth point (FrmMain.cs:3596 reads GetPoint(0))");
+  if (n < 0 || (n > 0 && (!centers_xyz || !matched_id))) return fail(ctx, VPC_E_BADARG, "bad centers/matched_id");
+  if (m > 2147483646ll || n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "size exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n == 0) return VPC_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->own_stream;
+  int rc = arena_reserve(ctx, ctx->io, al256(24ull * m) + al256(24ull * n) + al256(4ull * n) + al256(8ull * n) + 1024);
+  if (rc) return rc;
+  double* d_model = ctx->io.take<double>(3 * m);
+  double* d_data = ctx->io.take<double>(3 * n);
+  int* d_id = ctx->io.take<int>(n);
+  double* d_dist = ctx->io.take<double>(n);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_model, truth_xyz, 24ull * m, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_data, centers_xyz, 24ull * n, cudaMemcpyHostToDevice, s));
+  rc = icp_set_model(ctx, d_model, m, s);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_match_within, blocks_for(n, kIcpBlock), kIcpBlock, s, ctx->model, d_data, (int)n, match_distance, d_id,
+             dist ? d_dist : (double*)nullptr);
+  VPC_CUDA(ctx, cudaMemcpyAsync(matched_id, d_id, 4ull * n, cudaMemcpyDeviceToHost, s));
+  if (dist) VPC_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, 8ull * n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->model_set = false;
+  return VPC_OK;
+}
+
+int vpc_cluster_means_dev(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, const double* d_vals, int32_t n_fields,
+                          double* d_means, int32_t* d_counts, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || n_clusters < 0 || n_fields <= 0 || !d_means || !d_counts || (n > 0 && (!d_cluster_id || !d_vals))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t cells = (size_t)n_fields * (n_clusters + 1ull);
+  VPC_CUDA(ctx, cudaMemsetAsync(d_means, 0, 8ull * cells, s));            // d_means doubles as the sum accumulator
+  VPC_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 4ull * (n_clusters + 1ull), s));
+  if (n > 0) VPC_LAUNCH(ctx, k_cluster_sums, blocks_for(n, kDbBlock), kDbBlock, s, d_cluster_id, (int)n, n_clusters, d_vals, n_fields, d_means, d_counts);
+  VPC_LAUNCH(ctx, k_cluster_means, blocks_for(n_clusters + 1ll, kDbBlock), kDbBlock, s, n_clusters, n_fields, d_means, d_counts, d_means);
+  return VPC_OK;
+}
+
 int vpc_closest_point_set(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double* data_xyz, int64_t n,
                           int32_t* order, double* sqdist) {
   if (!ctx) return VPC_E_BADARG;
