@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
     // one-point cluster whose isClassed stays false (the point is not in its own nei list).
     a.keyslot[i] = make_int2(-1, 0);
     const bool key_pt = (0 >= a.min_pts);
-    a.is_key[i] = key_pt ? 1 : 0;
     const int gi = a.gidx ? __ldg(a.gidx + i) : (int)i;
-    a.compkey[i] = key_pt ? gi : -1;
+    if (a.cluster_id) a.compkey[i] = key_pt ? -2 - gi : -1;           // full pipeline: core flag folded into the key (see k_db_label)
+    else { a.is_key[i] = key_pt ? 1 : 0; a.compkey[i] = key_pt ? gi : -1; }
     if (key_pt && !a.gidx) atomicOr(&a.headbits[i >> 5], 1u << (i & 31));
   }
 }
@@ -479,8 +479,9 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
     if (a.core[p0]) {
       const int me_i = a.rec[p0].sidx;
       const int key = a.rec[a.rec[p0].parent].cinfo.y;
-      a.is_key[me_i] = 1;
-      a.compkey[me_i] = key;
+      // one scattered store per point: in the full pipeline the core flag rides in the key (core: -2 - key)
+      if (a.cluster_id) a.compkey[me_i] = -2 - key;
+      else { a.is_key[me_i] = 1; a.compkey[me_i] = key; }
       // the minimum core index of a cluster heads it: cluster numbering ranks these (DBImproved.cs:93-110)
       if (!a.gidx && key == me_i) atomicOr(&a.headbits[me_i >> 5], 1u << (me_i & 31));
     } else {
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
           key = max(key, a.rec[a.rec[j].parent].cinfo.y);
     }
   }
-  a.is_key[me_i] = 0;
+  if (!a.cluster_id) a.is_key[me_i] = 0;
   a.compkey[me_i] = key;
 }
 
@@ -536,7 +537,9 @@ __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && a.cluster_amount) *a.cluster_amount = a.first_cluster_id + a.ctrl->n_roots;  // :112
   if (i >= a.n) return;
-  const int key = a.compkey[i];
+  const int enc = a.compkey[i];                 // >= 0: border point's key, -1: noise, <= -2: core point, key = -2 - enc
+  const int key = (enc <= -2) ? -2 - enc : enc;
+  a.is_key[i] = (enc <= -2) ? 1 : 0;
   int base = a.first_cluster_id;
   if (a.seg_off) {
     // ids restart in every segment (each StartCode work item owns a fresh DBImproved, FrmMain.cs:2785)
