@@ -33,6 +33,7 @@ EPS, MIN_PTS = 0.07, 7
 DB_GRID, DB_N = 140, 1_000_000            # config C2
 ICP_M, ICP_N, ICP_ITERS = 1_000_000, 100_000, 50   # config C3
 DB_ALGO_BYTES_PER_PT = 21                  # 16 B read + 4 B cluster_id + 1 B is_key
+WORKLOAD_C2 = "C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7"
 METRIC = "dbscan_mpts_per_s"
 UNIT = "Mpts/s"
 
@@ -122,23 +123,26 @@ def run_reference(args):
     from vtkcloudpoint_b200 import synth
     oracle.lib()
     cores = os.cpu_count() or 1
-    mx, my = synth.dbscan_cloud(0xC2, DB_GRID, n_total=DB_N)
+    # same workload as our arm at this N: the C2 cloud, or the N x 1M cloud of the multi-GPU run (fewer passes then)
+    n_pts = DB_N * max(args.gpus, 1)
+    mx, my = synth.dbscan_cloud(0xC2, int(round(DB_GRID * max(args.gpus, 1) ** 0.5)), n_total=n_pts)
     for _ in range(min(args.warmup, 1)):
         cpu_dbscan_pass(oracle, mx, my, cores)
-    times = [cpu_dbscan_pass(oracle, mx, my, cores) for _ in range(args.steps)]
+    times = [cpu_dbscan_pass(oracle, mx, my, cores) for _ in range(args.steps if args.gpus <= 1 else min(args.steps, 3))]
     total = sum(times)
-    value = DB_N * len(times) / total / 1e6
+    value = n_pts * len(times) / total / 1e6
     # ICP: bounded sample = 2 of the 50 iterations on the full C3 clouds
     model, data, _, _ = synth.icp_clouds(0xC3, ICP_M, ICP_N)
     t0 = time.perf_counter()
     oracle.icp_rigid(model, data, -1.0, 2, use_grid=True, n_threads=cores)
     icp_s = time.perf_counter() - t0
-    sample = f"full C2 cloud ({DB_N} pts), {len(times)} passes of the grid-accelerated C++ port of DBImproved.dbscan, {cores} threads for the region queries"
+    sample = f"full cloud ({n_pts} pts), {len(times)} passes of the grid-accelerated C++ port of DBImproved.dbscan, {cores} threads for the region queries"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: DBSCAN 1M-point clustered cloud + noise, eps 0.07, minPts 7 (host CPU, reference algorithm)"},
+        "config": {"workload": WORKLOAD_C2 if args.gpus <= 1 else f"C2 recipe scaled to {n_pts} points (the cloud our arm clusters across {args.gpus} GPUs)",
+                   "arm": "reference algorithm (C++ port of DBImproved.dbscan) on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "secondary": {"metric": "icp_iters_per_s", "value": 2 / icp_s, "unit": "iters/s",
@@ -390,8 +394,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": ("C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7"
-                                    if world == 1 else
+            "config": {"workload": (WORKLOAD_C2 if world == 1 else
                                     f"C2 recipe scaled to {n_all} points (1M per GPU), one cloud clustered exactly across {world} GPUs: u-slabs + 2*eps halo exchange + cross-slab union-find merge (NCCL)"),
                        "points_total": n_all, "points_per_gpu": DB_N, "parallelism": f"{world} spatial slabs, one process per GPU" if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write)",
