@@ -210,6 +210,86 @@ int vpc_match_within_dev(vpc_ctx* ctx, const double* d_centers_xyz, int64_t n, d
 int vpc_cluster_means_dev(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, const double* d_vals,
                           int32_t n_fields, double* d_means, int32_t* d_counts, void* stream);
 
+/* ---- sorting (the reference's List.Sort / OrderBy steps around the path) -----------------------------------------
+ * vpc_sort_pairs_dev: stable LSD radix sort of n (uint64 key, int32 value) pairs on key bits [begin_bit, end_bit), in
+ *   place (device pointers).  vals_identity != 0: d_vals is output only and starts as 0..n-1, i.e. the call returns the
+ *   stable sorting permutation.
+ * vpc_argsort_f64_dev: d_order = stable ascending permutation of n doubles in Double.CompareTo order (NaN first,
+ *   -0.0 == +0.0).  Replaces `rawData.Sort(...)` on the key max(mx - xmin, my - ymin) in MainForm.getClusterFromMotor
+ *   (FrmMain.cs:1229-1233); List.Sort is unstable, ties are pinned to the original order here. */
+int vpc_sort_pairs_dev(vpc_ctx* ctx, uint64_t* d_keys, int32_t* d_vals, int64_t n, int32_t begin_bit, int32_t end_bit,
+                       int32_t vals_identity, void* stream);
+int vpc_argsort_f64_dev(vpc_ctx* ctx, const double* d_vals, int64_t n, int32_t* d_order, void* stream);
+
+/* ---- cluster statistics -------------------------------------------------------------------------
+ * vpc_cluster_groups_dev: Tools.GetClusList's grouping loop (Tools.cs:181-187): d_members[n] = point indices grouped
+ *   by cluster id ascending (0 = noise first), rawData order inside a group; d_offsets[n_clusters + 2], members of
+ *   cluster c are d_members[d_offsets[c] .. d_offsets[c+1]).  Ids outside 0..n_clusters (the C# would throw) count as noise.
+ * vpc_cluster_means_ordered_dev: the centroids of Tools.cs:188-194 (LINQ Average: sequential sum in list order, one
+ *   division) -- bit-identical to the C#.  d_vals planar [n_fields][n]; d_means planar [n_fields][n_clusters + 1]
+ *   (NaN for an empty cluster; entry 0 unused); d_counts[n_clusters + 1].
+ * vpc_cluster_circles_dev: Tools.getCircles (Tools.cs:394-409) = Geometry.FindMinimalBoundingCircle per cluster
+ *   (BaseClass/Geometry.cs:122-420: gift-wrapping hull in list order, then the smallest enclosing circle through two
+ *   or three hull points, first minimum wins), in the C#'s operation order: centre and radius are bit-identical.
+ *   d_hx/d_hy = the coordinates the hull is built on (X, Y for is3D = true; motor_x, motor_y for is3D = false).
+ *   Outputs are indexed by cluster id [n_clusters + 1]; d_status: 1 = circle, 0 = skipped (<= 3 members, :400),
+ *   -1 = the C# would throw (every member has NaN x and y), -2 = non-finite member coordinate (not reproduced).
+ *   Note: HullCull's culling box is always 0,0,0,0 in the C# (Rectangle2D.Left/Right/Top/Bottom are never assigned,
+ *   DataModel.cs:204-207), so no point is ever culled; that behaviour is kept.
+ * vpc_radius_filter_dev: MainForm.FilterClustersByRadius (FrmMain.cs:1905-1920): d_flag[c] = 1 iff cluster c has a
+ *   circle and radius > threshold (strict), c = 0..n_clusters.
+ * vpc_cluster_stats: host-pointer form of the statistics block of CompleteWork3 (FrmMain.cs:1521-1540): grouping,
+ *   the five means (X, Y, Z, motor_x, motor_y; means5 planar [5][n_clusters + 1]), and optionally the 3-D and 2-D
+ *   circles (circle* planar [3][n_clusters + 1] = cx, cy, radius).  xyz planar [3][n]. */
+int vpc_cluster_groups_dev(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, int32_t* d_members,
+                           int32_t* d_offsets, void* stream);
+int vpc_cluster_means_ordered_dev(vpc_ctx* ctx, const int32_t* d_members, const int32_t* d_offsets, int32_t n_clusters,
+                                  const double* d_vals, int64_t n, int32_t n_fields, double* d_means, int32_t* d_counts,
+                                  void* stream);
+int vpc_cluster_circles_dev(vpc_ctx* ctx, const int32_t* d_members, const int32_t* d_offsets, int32_t n_clusters, int64_t n,
+                            const double* d_hx, const double* d_hy, double* d_cx, double* d_cy, double* d_radius,
+                            int32_t* d_status, void* stream);
+int vpc_radius_filter_dev(vpc_ctx* ctx, const double* d_radius, const int32_t* d_status, int32_t n_clusters,
+                          double threshold, uint8_t* d_flag, void* stream);
+int vpc_cluster_stats(vpc_ctx* ctx, const int32_t* cluster_id, int64_t n, int32_t n_clusters, const double* xyz,
+                      const double* mx, const double* my, double* means5, int32_t* counts, double* circle3d,
+                      int32_t* status3d, double* circle2d, int32_t* status2d);
+
+/* ---- nearest truth point in 2-D (SURVEY.md 8f-3 ii) ---------------------------------------------------------------
+ * Replaces the LINQ query of MainForm.refreshClusList (FrmMain.cs:3446-3467): for every scan point the truth with the
+ * smallest DISTANCE = sqrt((tx-mx)*(tx-mx) + (ty-my)*(ty-my)) among those with DISTANCE < radius; equal DISTANCEs
+ * resolve to the HIGHEST truth index (OrderByDescending is stable, Reverse flips ties); id = that truth's clusterId
+ * (truth_id, NULL = index + 1), 0 when no truth is inside the radius.  The _dev form expects the truths as the model
+ * (vpc_icp_set_model_dev with z = 0); d_index / d_dist are nullable extras (truth index or -1, DISTANCE or NaN). */
+int vpc_nearest_truth_2d(vpc_ctx* ctx, const double* truth_x, const double* truth_y, const int32_t* truth_id, int64_t m,
+                         const double* px, const double* py, int64_t n, double radius, int32_t* id);
+int vpc_nearest_truth_2d_dev(vpc_ctx* ctx, const int32_t* d_truth_id, const double* d_px, const double* d_py, int64_t n,
+                             double radius, int32_t* d_id, int32_t* d_index, double* d_dist, void* stream);
+
+/* ---- ingest --------------------------------------------------------------------------------------
+ * vpc_polar_to_xyz_dev: the import loop's gate and conversion (FrmMain.cs:1012, 1025-1062): d_keep[i] = 0 when
+ *   Distance == 0 or Distance > 1000; yangjiao = -2 (mx - x_angle) / 180 pi, fangweijiao = 2 (my - y_angle) / 180 pi,
+ *   tmpx = D cos(yang) sin(fang), tmpy = D sin(yang) cos(fang), Z = D cos(yang); X / Y pick +-tmpx / +-tmpy by the
+ *   ImportPts codes xdir, ydir (1: tmpy, 2: tmpx, 3: -tmpy, 4: -tmpx; defaults xdir = 2, ydir = 1).  d_xyz planar [3][n].
+ *   Floating point with sin/cos: agrees with the C# (x87 fsin/fcos) to ~1e-15 relative, not bit for bit.
+ * vpc_dedupe_xyz_dev: the typpe == 1 duplicate test (FrmMain.cs:1063-1068) without its Theta(n^2) FindAll: d_keep[i] = 1
+ *   for the first row with a given (X, Y, Z) (== semantics: -0.0 equals 0.0, NaN equals nothing) among the rows with
+ *   d_live[i] != 0 (NULL = all), 0 for later copies and dead rows; d_first_of (nullable) = index of the first
+ *   occurrence (-1 for dead rows); d_n_dup (nullable) = duplicatNum.  n <= 2^30.
+ * vpc_ingest_text: a whole scan file in memory ("header\n" then "motor_x\tmotor_y\tDistance\n" rows, FrmMain.cs:975-1011)
+ *   parsed, gated, converted and de-duplicated on the GPU.  Outputs have row_cap entries; *n_rows = rows found (the call
+ *   fails with VPC_E_BADARG if that exceeds row_cap); row_status[i]: 0 = parsed exactly, 1 = syntax error (the C# throws
+ *   FormatException), 2 = number outside the exactly-converted range (> 19 significant digits or |exponent| > 22).
+ *   keep[i] = row i survives gate (+ duplicate removal when remove_duplicates != 0, default orientation only). */
+int vpc_polar_to_xyz_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, const double* d_dist, int64_t n,
+                         double x_angle, double y_angle, int32_t xdir, int32_t ydir, double* d_xyz, uint8_t* d_keep,
+                         void* stream);
+int vpc_dedupe_xyz_dev(vpc_ctx* ctx, const double* d_xyz, const uint8_t* d_live, int64_t n, uint8_t* d_keep,
+                       int32_t* d_first_of, int32_t* d_n_dup, void* stream);
+int vpc_ingest_text(vpc_ctx* ctx, const char* text, int64_t len, double x_angle, double y_angle, int32_t xdir, int32_t ydir,
+                    int32_t remove_duplicates, int64_t row_cap, double* mx, double* my, double* dist, double* xyz,
+                    uint8_t* keep, uint8_t* row_status, int64_t* n_rows, int64_t* n_kept, int64_t* n_duplicates);
+
 /* ---- ICP across GPUs: the model is sharded (one shard per GPU, vpc_icp_set_model_dev on each), the
  * data is replicated.  One round of ICP.go_hell_ICP (ICP.cs:23-180) becomes
  *   vpc_icp_shard_nn_dev          local nearest model point: d2[i], idx[i] = local index + idx_offset

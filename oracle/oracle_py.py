@@ -17,7 +17,7 @@ LIB = HERE / "libvpc_oracle.so"
 
 
 def build(force: bool = False) -> Path:
-    srcs = [HERE / "vpc_oracle.cpp", HERE / "vpc_oracle.h"]
+    srcs = [HERE / "vpc_oracle.cpp", HERE / "vpc_oracle_stats.cpp", HERE / "vpc_oracle.h"]
     if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
         res = subprocess.run(["make", "-C", str(HERE), "-B", "libvpc_oracle.so"], capture_output=True, text=True)
         if res.returncode != 0:
@@ -41,6 +41,11 @@ def lib() -> C.CDLL:
         "vpco_jacobi_eig": [_p, C.c_int, _p, _p, C.c_int, _f64],
         "vpco_trans_points": [_p, _i64, _p, _p, _p],
         "vpco_match_within_literal": [_p, _i64, _p, _i64, _f64, _p, _p],
+        "vpco_cluster_stats_literal": [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+        "vpco_nearest_truth_2d_literal": [_p, _p, _p, _i64, _p, _p, _i64, _f64, _p],
+        "vpco_polar_to_xyz": [_p, _p, _p, _i64, _f64, _f64, _i32, _i32, _p, _p],
+        "vpco_dedupe_xyz_literal": [_p, _p, _i64, _p, _p, _p],
+        "vpco_parse_rows": [C.c_char_p, _i64, _i64, _p, _p, _p, _p, _p],
     }
     for name, args in sig.items():
         fn = getattr(dll, name)
@@ -147,3 +152,64 @@ def match_within(truth_xyz, centers_xyz, match_distance):
     if rc != 0:
         raise RuntimeError(f"oracle match_within rc={rc}")
     return mid, dist
+
+
+def cluster_stats(cluster_id, n_clusters, xyz, mx, my, circles3d=True, circles2d=True):
+    cid = np.ascontiguousarray(cluster_id, np.int32)
+    pts = _planar(xyz) if len(cid) else np.zeros((3, 0))
+    mx = np.ascontiguousarray(mx, np.float64)
+    my = np.ascontiguousarray(my, np.float64)
+    k1 = int(n_clusters) + 1
+    means = np.empty((5, k1)); counts = np.empty(k1, np.int32)
+    c3 = np.empty((3, k1)) if circles3d else None
+    s3 = np.empty(k1, np.int32) if circles3d else None
+    c2 = np.empty((3, k1)) if circles2d else None
+    s2 = np.empty(k1, np.int32) if circles2d else None
+    rc = lib().vpco_cluster_stats_literal(_ptr(cid), len(cid), int(n_clusters), _ptr(pts), _ptr(mx), _ptr(my), _ptr(means), _ptr(counts),
+                                          _ptr(c3), _ptr(s3), _ptr(c2), _ptr(s2))
+    if rc != 0:
+        raise RuntimeError(f"oracle cluster_stats rc={rc}")
+    return {"means": means, "counts": counts, "circle3d": c3, "status3d": s3, "circle2d": c2, "status2d": s2}
+
+
+def nearest_truth_2d(truth_x, truth_y, truth_id, px, py, radius):
+    tx = np.ascontiguousarray(truth_x, np.float64); ty = np.ascontiguousarray(truth_y, np.float64)
+    tid = None if truth_id is None else np.ascontiguousarray(truth_id, np.int32)
+    px = np.ascontiguousarray(px, np.float64); py = np.ascontiguousarray(py, np.float64)
+    out = np.empty(len(px), np.int32)
+    rc = lib().vpco_nearest_truth_2d_literal(_ptr(tx), _ptr(ty), _ptr(tid), len(tx), _ptr(px), _ptr(py), len(px), float(radius), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle nearest_truth_2d rc={rc}")
+    return out
+
+
+def polar_to_xyz(mx, my, dist, x_angle, y_angle, xdir=2, ydir=1):
+    mx = np.ascontiguousarray(mx, np.float64); my = np.ascontiguousarray(my, np.float64); dist = np.ascontiguousarray(dist, np.float64)
+    n = len(mx)
+    xyz = np.empty((3, n)); keep = np.empty(n, np.uint8)
+    rc = lib().vpco_polar_to_xyz(_ptr(mx), _ptr(my), _ptr(dist), n, float(x_angle), float(y_angle), int(xdir), int(ydir), _ptr(xyz), _ptr(keep))
+    if rc != 0:
+        raise RuntimeError(f"oracle polar_to_xyz rc={rc}")
+    return xyz, keep
+
+
+def dedupe_xyz(xyz_planar, live=None):
+    xyz = np.ascontiguousarray(xyz_planar, np.float64)
+    n = xyz.shape[1]
+    live = None if live is None else np.ascontiguousarray(live, np.uint8)
+    keep = np.empty(n, np.uint8); first = np.empty(n, np.int32); ndup = C.c_int64(0)
+    rc = lib().vpco_dedupe_xyz_literal(_ptr(xyz), _ptr(live), n, _ptr(keep), _ptr(first), C.cast(C.byref(ndup), C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"oracle dedupe rc={rc}")
+    return keep, first, int(ndup.value)
+
+
+def parse_rows(text: bytes):
+    cap = text.count(b"\n") + 1
+    mx, my, ds = (np.empty(cap) for _ in range(3))
+    st = np.empty(cap, np.uint8); rows = C.c_int64(0)
+    rc = lib().vpco_parse_rows(text, len(text), cap, _ptr(mx), _ptr(my), _ptr(ds), _ptr(st), C.cast(C.byref(rows), C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"oracle parse_rows rc={rc}")
+    r = int(rows.value)
+    return mx[:r], my[:r], ds[:r], st[:r]

@@ -89,6 +89,25 @@ int vpco_jacobi_eig(double* a, int n, double* eigval, double* v, int max_it, dou
 int vpco_trans_points(const double* src_xyz, int64_t n, const double R[9], const double T[3],
                       double* dst_xyz);
 
+/* ---- part 2 (vpc_oracle_stats.cpp): the steps on either side of DBSCAN / ICP, SURVEY.md 8f ---- */
+
+/* Tools.GetClusList (Tools.cs:162-195) + Tools.getCircles (Tools.cs:394-409, Geometry.cs:17-420), literal, list based.
+ * Layouts as vpc_cluster_stats in include/vpc.h.  circle3d/circle2d nullable (with their status arrays). */
+int vpco_cluster_stats_literal(const int32_t* cluster_id, int64_t n, int32_t n_clusters, const double* xyz, const double* mx,
+                               const double* my, double* means5, int32_t* counts, double* circle3d, int32_t* status3d,
+                               double* circle2d, int32_t* status2d);
+/* MainForm.refreshClusList's LINQ query, FrmMain.cs:3446-3467, literal (stable sort descending, reverse, first). */
+int vpco_nearest_truth_2d_literal(const double* truth_x, const double* truth_y, const int32_t* truth_id, int64_t m,
+                                  const double* px, const double* py, int64_t n, double radius, int32_t* id);
+/* Import loop, FrmMain.cs:1012, 1025-1062 (libm sin/cos). */
+int vpco_polar_to_xyz(const double* mx, const double* my, const double* dist, int64_t n, double x_angle, double y_angle,
+                      int32_t xdir, int32_t ydir, double* xyz, uint8_t* keep);
+/* FindAll de-duplication, FrmMain.cs:1063-1068, literal Theta(n^2). */
+int vpco_dedupe_xyz_literal(const double* xyz, const uint8_t* live, int64_t n, uint8_t* keep, int32_t* first_of, int64_t* n_dup);
+/* Row parsing, FrmMain.cs:975-1011 (strtod). */
+int vpco_parse_rows(const char* text, int64_t len, int64_t row_cap, double* mx, double* my, double* dist, uint8_t* status,
+                    int64_t* n_rows);
+
 #ifdef __cplusplus
 }
 #endif

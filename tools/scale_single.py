@@ -29,6 +29,11 @@ for n in [int(a) for a in sys.argv[1:]] or [1_000_000, 4_000_000, 16_000_000]:
         ts.append(e0.elapsed_time(e1))
     t = sorted(ts)[len(ts) // 2]
     print(f"n={n}: {t:.3f} ms  {n / t / 1e3:.1f} Mpts/s  clusters={int(out[3].item())}  ({21 * n / t / 1e6 / 6549.4 * 100:.2f}% of HBM roofline at 21 B/pt)", flush=True)
+    ctx.profile(True)
+    ctx.dbscan_dev(dx, dy, 0.07, 7, 0, out=out)
+    rep = ctx.profile_report()
+    ctx.profile(False)
+    print("   " + "  ".join(f"{k.replace('k_db_', '').replace('k_scan_exclusive', 'scan')}={v * 1e3:.0f}us" for k, v in rep), flush=True)
     del dx, dy, out
     torch.cuda.empty_cache()
 ctx.close()

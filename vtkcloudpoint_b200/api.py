@@ -238,3 +238,131 @@ class Context:
         self._check(self._lib.vpc_icp_rigid_dev(self._h, data_planar.data_ptr(), n, float(e), int(max_iters), state.data_ptr(),
                                                 order.data_ptr(), stream))
         return out
+
+    # ------------------------------------------------------------------ cluster statistics / matching / ingest
+    def cluster_stats(self, cluster_id, n_clusters: int, xyz, mx, my, circles3d: bool = True, circles2d: bool = True):
+        """The statistics block of CompleteWork3 (FrmMain.cs:1521-1540) through the host-pointer ABI.  Returns a dict:
+        means [5, k+1] (X Y Z motor_x motor_y), counts [k+1], circle3d / circle2d [3, k+1] (cx, cy, radius) and their status [k+1]."""
+        cid = np.ascontiguousarray(cluster_id, np.int32)
+        pts = _planar(xyz) if len(cid) else np.zeros((3, 0))
+        mx = np.ascontiguousarray(mx, np.float64)
+        my = np.ascontiguousarray(my, np.float64)
+        n, k1 = len(cid), int(n_clusters) + 1
+        means = np.empty((5, k1), np.float64)
+        counts = np.empty(k1, np.int32)
+        c3 = np.empty((3, k1), np.float64) if circles3d else None
+        s3 = np.empty(k1, np.int32) if circles3d else None
+        c2 = np.empty((3, k1), np.float64) if circles2d else None
+        s2 = np.empty(k1, np.int32) if circles2d else None
+        opt = lambda a: _ptr(a) if a is not None else None   # noqa: E731
+        self._check(self._lib.vpc_cluster_stats(self._h, _ptr(cid), n, int(n_clusters), _ptr(pts), _ptr(mx), _ptr(my), _ptr(means), _ptr(counts),
+                                                opt(c3), opt(s3), opt(c2), opt(s2)))
+        return {"means": means, "counts": counts, "circle3d": c3, "status3d": s3, "circle2d": c2, "status2d": s2}
+
+    def nearest_truth_2d(self, truth_x, truth_y, truth_id, px, py, radius: float):
+        """MainForm.refreshClusList's query (FrmMain.cs:3446-3467): id of the nearest truth within radius (ties -> highest index), else 0."""
+        tx = np.ascontiguousarray(truth_x, np.float64)
+        ty = np.ascontiguousarray(truth_y, np.float64)
+        tid = None if truth_id is None else np.ascontiguousarray(truth_id, np.int32)
+        px = np.ascontiguousarray(px, np.float64)
+        py = np.ascontiguousarray(py, np.float64)
+        out = np.empty(len(px), np.int32)
+        self._check(self._lib.vpc_nearest_truth_2d(self._h, _ptr(tx), _ptr(ty), _ptr(tid) if tid is not None else None, len(tx), _ptr(px), _ptr(py),
+                                                   len(px), float(radius), _ptr(out)))
+        return out
+
+    def ingest_text(self, text: bytes, x_angle: float, y_angle: float, xdir: int = 2, ydir: int = 1, remove_duplicates: bool = True):
+        """A scan file in memory -> dict(mx, my, dist, xyz [3, rows], keep, row_status, n_kept, n_duplicates) (FrmMain.cs:975-1068)."""
+        cap = text.count(b"\n") + 1
+        mx, my, ds = (np.empty(cap, np.float64) for _ in range(3))
+        xyz = np.empty(3 * cap, np.float64)
+        keep, st = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+        n_rows, n_kept, n_dup = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        ref = lambda v: C.cast(C.byref(v), C.c_void_p)   # noqa: E731
+        self._check(self._lib.vpc_ingest_text(self._h, text, len(text), float(x_angle), float(y_angle), int(xdir), int(ydir), 1 if remove_duplicates else 0,
+                                              cap, _ptr(mx), _ptr(my), _ptr(ds), _ptr(xyz), _ptr(keep), _ptr(st), ref(n_rows), ref(n_kept), ref(n_dup)))
+        r = int(n_rows.value)
+        return {"mx": mx[:r], "my": my[:r], "dist": ds[:r], "xyz": xyz[:3 * r].reshape(3, r), "keep": keep[:r], "row_status": st[:r],
+                "n_kept": int(n_kept.value), "n_duplicates": int(n_dup.value)}
+
+    # device-tensor forms ---------------------------------------------------------------------------------------------
+    def _stream(self, t):
+        import torch
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    def sort_pairs_dev(self, keys, vals=None, begin_bit: int = 0, end_bit: int = 64):
+        """Stable radix sort in place.  keys: int64/uint64-viewed CUDA tensor; vals None -> returns the sorting permutation."""
+        import torch
+        n = keys.numel()
+        identity = vals is None
+        if identity:
+            vals = torch.empty(n, dtype=torch.int32, device=keys.device)
+        self._check(self._lib.vpc_sort_pairs_dev(self._h, keys.data_ptr(), vals.data_ptr(), n, begin_bit, end_bit, 1 if identity else 0, self._stream(keys)))
+        return keys, vals
+
+    def argsort_f64_dev(self, vals):
+        import torch
+        order = torch.empty(vals.numel(), dtype=torch.int32, device=vals.device)
+        self._check(self._lib.vpc_argsort_f64_dev(self._h, vals.data_ptr(), vals.numel(), order.data_ptr(), self._stream(vals)))
+        return order
+
+    def cluster_groups_dev(self, cluster_id, n_clusters: int):
+        import torch
+        n = cluster_id.numel()
+        members = torch.empty(max(n, 1), dtype=torch.int32, device=cluster_id.device)
+        offsets = torch.empty(n_clusters + 2, dtype=torch.int32, device=cluster_id.device)
+        self._check(self._lib.vpc_cluster_groups_dev(self._h, cluster_id.data_ptr(), n, int(n_clusters), members.data_ptr(), offsets.data_ptr(), self._stream(cluster_id)))
+        return members[:n], offsets
+
+    def cluster_means_ordered_dev(self, members, offsets, n_clusters: int, vals_planar):
+        import torch
+        nf, n = vals_planar.shape
+        means = torch.empty((nf, n_clusters + 1), dtype=torch.float64, device=vals_planar.device)
+        counts = torch.empty(n_clusters + 1, dtype=torch.int32, device=vals_planar.device)
+        self._check(self._lib.vpc_cluster_means_ordered_dev(self._h, members.data_ptr(), offsets.data_ptr(), int(n_clusters), vals_planar.data_ptr(), n, nf,
+                                                            means.data_ptr(), counts.data_ptr(), self._stream(vals_planar)))
+        return means, counts
+
+    def cluster_circles_dev(self, members, offsets, n_clusters: int, hx, hy):
+        import torch
+        k1 = n_clusters + 1
+        circ = torch.empty((3, k1), dtype=torch.float64, device=hx.device)
+        status = torch.empty(k1, dtype=torch.int32, device=hx.device)
+        self._check(self._lib.vpc_cluster_circles_dev(self._h, members.data_ptr(), offsets.data_ptr(), int(n_clusters), hx.numel(), hx.data_ptr(), hy.data_ptr(),
+                                                      circ[0].data_ptr(), circ[1].data_ptr(), circ[2].data_ptr(), status.data_ptr(), self._stream(hx)))
+        return circ, status
+
+    def radius_filter_dev(self, radius, status, n_clusters: int, threshold: float):
+        import torch
+        flag = torch.empty(n_clusters + 1, dtype=torch.uint8, device=radius.device)
+        self._check(self._lib.vpc_radius_filter_dev(self._h, radius.data_ptr(), status.data_ptr(), int(n_clusters), float(threshold), flag.data_ptr(), self._stream(radius)))
+        return flag
+
+    def nearest_truth_2d_dev(self, truth_id, px, py, radius: float, want_extras: bool = False):
+        import torch
+        n = px.numel()
+        out = torch.empty(n, dtype=torch.int32, device=px.device)
+        idx = torch.empty(n, dtype=torch.int32, device=px.device) if want_extras else None
+        dist = torch.empty(n, dtype=torch.float64, device=px.device) if want_extras else None
+        self._check(self._lib.vpc_nearest_truth_2d_dev(self._h, truth_id.data_ptr() if truth_id is not None else None, px.data_ptr(), py.data_ptr(), n, float(radius),
+                                                       out.data_ptr(), idx.data_ptr() if want_extras else None, dist.data_ptr() if want_extras else None, self._stream(px)))
+        return (out, idx, dist) if want_extras else out
+
+    def polar_to_xyz_dev(self, mx, my, dist, x_angle: float, y_angle: float, xdir: int = 2, ydir: int = 1):
+        import torch
+        n = mx.numel()
+        xyz = torch.empty((3, n), dtype=torch.float64, device=mx.device)
+        keep = torch.empty(n, dtype=torch.uint8, device=mx.device)
+        self._check(self._lib.vpc_polar_to_xyz_dev(self._h, mx.data_ptr(), my.data_ptr(), dist.data_ptr(), n, float(x_angle), float(y_angle), int(xdir), int(ydir),
+                                                   xyz.data_ptr(), keep.data_ptr(), self._stream(mx)))
+        return xyz, keep
+
+    def dedupe_xyz_dev(self, xyz_planar, live=None):
+        import torch
+        n = xyz_planar.shape[1]
+        keep = torch.empty(n, dtype=torch.uint8, device=xyz_planar.device)
+        first = torch.empty(n, dtype=torch.int32, device=xyz_planar.device)
+        ndup = torch.zeros(1, dtype=torch.int32, device=xyz_planar.device)
+        self._check(self._lib.vpc_dedupe_xyz_dev(self._h, xyz_planar.data_ptr(), live.data_ptr() if live is not None else None, n, keep.data_ptr(), first.data_ptr(),
+                                                 ndup.data_ptr(), self._stream(xyz_planar)))
+        return keep, first, ndup

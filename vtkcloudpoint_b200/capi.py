@@ -49,6 +49,18 @@ SIGNATURES = {
     "vpc_match_within": (C.c_int, [_p, _p, _i64, _p, _i64, _f64, _p, _p]),
     "vpc_match_within_dev": (C.c_int, [_p, _p, _i64, _f64, _p, _p, _p]),
     "vpc_cluster_means_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _p, _p]),
+    "vpc_sort_pairs_dev": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "vpc_argsort_f64_dev": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "vpc_cluster_groups_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
+    "vpc_cluster_means_ordered_dev": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i32, _p, _p, _p]),
+    "vpc_cluster_circles_dev": (C.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "vpc_radius_filter_dev": (C.c_int, [_p, _p, _p, _i32, _f64, _p, _p]),
+    "vpc_cluster_stats": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vpc_nearest_truth_2d": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i64, _f64, _p]),
+    "vpc_nearest_truth_2d_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _p, _p, _p, _p]),
+    "vpc_polar_to_xyz_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _f64, _i32, _i32, _p, _p, _p]),
+    "vpc_dedupe_xyz_dev": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p]),
+    "vpc_ingest_text": (C.c_int, [_p, _p, _i64, _f64, _f64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vpc_icp_shard_begin_dev": (C.c_int, [_p, _i64, _p]),
     "vpc_icp_shard_nn_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
     "vpc_icp_shard_select_dev": (C.c_int, [_p, _i64, _p, _p, _p, _p]),

@@ -178,18 +178,20 @@ struct NnBest {
   double x, y, z;
 };
 
-template <bool kSqrt = false>
+template <bool kSqrt = false, bool kHigh = false>
 __device__ __forceinline__ void icp_consider(NnBest& b, double2 a, double2 w, double px, double py, double pz) {
   // kSqrt: candidates are ranked by the ROUNDED distance like FrmMain.cs:829-835 / :3594-3601 (sqrt can merge
   // distinct d2 into one value, which then ties to the lowest index); otherwise by d2 like ICP.cs:238-244
   double d2 = icp_sqd(px, py, pz, a.x, a.y, w.x);
   if (kSqrt) d2 = sqrt(d2);
   const int i = (int)__double_as_longlong(w.y);
-  if (d2 < b.d || (d2 == b.d && i < b.i)) { b.d = d2; b.i = i; b.x = a.x; b.y = a.y; b.z = w.x; }
+  // kHigh: equal distances resolve to the HIGHEST index (the LINQ chain of FrmMain.cs:3452-3456); 0x7fffffff = nothing yet
+  const bool tie = kHigh ? (i > b.i || b.i == 0x7fffffff) : (i < b.i);
+  if (d2 < b.d || (d2 == b.d && tie)) { b.d = d2; b.i = i; b.x = a.x; b.y = a.y; b.z = w.x; }
 }
 
 // candidates [j0, j1) of the cell-ordered model; two records (four 128-bit loads) in flight
-template <bool kSqrt = false>
+template <bool kSqrt = false, bool kHigh = false>
 __device__ __forceinline__ void icp_scan_range(const double4* __restrict__ spts, int j0, int j1, double px, double py,
                                                double pz, NnBest& b) {
   const double2* s2 = reinterpret_cast<const double2*>(spts);
@@ -197,8 +199,8 @@ __device__ __forceinline__ void icp_scan_range(const double4* __restrict__ spts,
     const int j2 = min(j + 1, j1 - 1);
     const double2 a0 = __ldg(s2 + 2 * j), w0 = __ldg(s2 + 2 * j + 1);
     const double2 a1 = __ldg(s2 + 2 * j2), w1 = __ldg(s2 + 2 * j2 + 1);
-    icp_consider<kSqrt>(b, a0, w0, px, py, pz);
-    icp_consider<kSqrt>(b, a1, w1, px, py, pz);   // j2 == j repeats a record: harmless for an argmin
+    icp_consider<kSqrt, kHigh>(b, a0, w0, px, py, pz);
+    icp_consider<kSqrt, kHigh>(b, a1, w1, px, py, pz);   // j2 == j repeats a record: harmless for an argmin
   }
 }
 
@@ -221,7 +223,7 @@ __device__ __forceinline__ bool icp_box_done(const IcpGridCtrl& c, const double*
 // Exact argmin_j d2(p, model[j]) with ties to the lowest j (ICP.cs:229-248) for a finite p over the
 // finite model points.  Search order: the 2x2x2 block of cells nearest to p, then the 3x3x3 block, then
 // shells of cells outward -- each time until nothing outside the searched box can beat or tie the best.
-template <bool kSqrt = false>
+template <bool kSqrt = false, bool kHigh = false>
 __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl& c, double px, double py, double pz,
                                             NnBest& b) {
   b.d = INFINITY; b.i = 0x7fffffff; b.x = b.y = b.z = 0.0;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
   {  // stage 0: the query's own cell.  Once ICP has (nearly) converged the match is much closer than the cell
      // walls for most points, and one cell (about one 32-byte record) is all that has to be read.
     const int own = (cc[2] * c.nc[1] + cc[1]) * c.nc[0] + cc[0];
-    icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + own), __ldg(g.cell_start + own + 1), px, py, pz, b);
+    icp_scan_range<kSqrt, kHigh>(g.spts, __ldg(g.cell_start + own), __ldg(g.cell_start + own + 1), px, py, pz, b);
     if (b.i != 0x7fffffff && icp_box_done<kSqrt>(c, p, cc, cc, b, slack)) return;
   }
   {  // stage 1: nearest octant block, at most 4 row segments; all range loads first
@@ -264,10 +266,10 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        if (j0[r] + k < j1[r]) icp_consider<kSqrt>(b, ra[r], rw[r], px, py, pz);
+        if (j0[r] + k < j1[r]) icp_consider<kSqrt, kHigh>(b, ra[r], rw[r], px, py, pz);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) icp_scan_range<kSqrt>(g.spts, j0[r] + 2, j1[r], px, py, pz, b);
+    for (int r = 0; r < 4; ++r) icp_scan_range<kSqrt, kHigh>(g.spts, j0[r] + 2, j1[r], px, py, pz, b);
     if (icp_box_done<kSqrt>(c, p, lo, hi, b, slack)) return;
   }
   const int rmax = max(c.nc[0], max(c.nc[1], c.nc[2]));
@@ -286,7 +288,7 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
           a1[t] = ok ? __ldg(g.cell_start + row + hi[0] + 1) : 0;
         }
 #pragma unroll
-        for (int t = 0; t < 3; ++t) icp_scan_range<kSqrt>(g.spts, a0[t], a1[t], px, py, pz, b);
+        for (int t = 0; t < 3; ++t) icp_scan_range<kSqrt, kHigh>(g.spts, a0[t], a1[t], px, py, pz, b);
       }
       if (icp_box_done<kSqrt>(c, p, lo, hi, b, slack)) return;
       continue;
@@ -296,10 +298,10 @@ __device__ __forceinline__ void icp_nearest(const IcpModel& g, const IcpGridCtrl
         const int row = (z * c.nc[1] + y) * c.nc[0];
         const bool shell_row = (r == 1) || (abs(z - cc[2]) == r) || (abs(y - cc[1]) == r);
         if (shell_row) {
-          icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + row + lo[0]), __ldg(g.cell_start + row + hi[0] + 1), px, py, pz, b);
+          icp_scan_range<kSqrt, kHigh>(g.spts, __ldg(g.cell_start + row + lo[0]), __ldg(g.cell_start + row + hi[0] + 1), px, py, pz, b);
         } else {
-          if (cc[0] - r >= 0) icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + row + cc[0] - r), __ldg(g.cell_start + row + cc[0] - r + 1), px, py, pz, b);
-          if (cc[0] + r <= c.nc[0] - 1) icp_scan_range<kSqrt>(g.spts, __ldg(g.cell_start + row + cc[0] + r), __ldg(g.cell_start + row + cc[0] + r + 1), px, py, pz, b);
+          if (cc[0] - r >= 0) icp_scan_range<kSqrt, kHigh>(g.spts, __ldg(g.cell_start + row + cc[0] - r), __ldg(g.cell_start + row + cc[0] - r + 1), px, py, pz, b);
+          if (cc[0] + r <= c.nc[0] - 1) icp_scan_range<kSqrt, kHigh>(g.spts, __ldg(g.cell_start + row + cc[0] + r), __ldg(g.cell_start + row + cc[0] + r + 1), px, py, pz, b);
         }
       }
     }
@@ -349,6 +351,28 @@ k_match_within(IcpModel g, const double* __restrict__ data, int n, double match_
   icp_match<true>(g, c, __ldg(data + i), __ldg(data + n + i), __ldg(data + 2ll * n + i), b);
   matched_id[i] = (b.d < match_distance) ? b.i : -1;
   if (dist) dist[i] = b.d;
+}
+
+// ---- nearest truth point in 2-D: MainForm.refreshClusList (FrmMain.cs:3446-3467) ---------------------------------
+// id = trues.Select(DISTANCE = Math.Sqrt((tx-mx)*(tx-mx) + (ty-my)*(ty-my))).Where(DISTANCE < radius)
+//           .OrderByDescending(DISTANCE).Reverse().Select(ID).FirstOrDefault()
+// OrderByDescending is stable and Reverse flips equal keys too, so the winner is the smallest DISTANCE and, among equal
+// DISTANCEs, the truth with the HIGHEST index; no truth inside the radius gives 0.  The truths are the model (set with
+// z = 0, so (dx*dx + dy*dy) + 0*0 is the 2-D expression bit for bit); truth_id == nullptr means ID = index + 1.
+__global__ void __launch_bounds__(kIcpBlock)
+k_nearest_truth_2d(IcpModel g, const int* __restrict__ truth_id, const double* __restrict__ px, const double* __restrict__ py, int n,
+                   double radius, int* __restrict__ out_id, int* __restrict__ out_idx, double* __restrict__ out_dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const IcpGridCtrl c = *g.ctrl;
+  const double x = __ldg(px + i), y = __ldg(py + i);
+  NnBest b;
+  b.d = INFINITY; b.i = 0x7fffffff;
+  if (c.n_valid > 0 && finite_d(x) && finite_d(y)) icp_nearest<true, true>(g, c, x, y, 0.0, b);
+  const bool hit = (b.i != 0x7fffffff) && (b.d < radius);
+  out_id[i] = hit ? (truth_id ? __ldg(truth_id + b.i) : b.i + 1) : 0;
+  if (out_idx) out_idx[i] = hit ? b.i : -1;
+  if (out_dist) out_dist[i] = hit ? b.d : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // One cyclic-Jacobi rotation on the symmetric 4x4 A (annihilates A[P][Q]) with static indices so that

@@ -81,6 +81,11 @@ k_rs_scatter(const unsigned long long* __restrict__ keys_in, const int* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) k_rs_iota(int* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
 // key builders -------------------------------------------------------------------------------------------
 // ascending order of doubles like IComparable<double>: NaN sorts first in .NET (Double.CompareTo), then -inf .. +inf;
 // -0.0 and +0.0 compare equal there, so both map to the key of +0.0.
@@ -88,6 +93,12 @@ __device__ __forceinline__ unsigned long long rs_key_double(double v) {
   if (v != v) return 0ull;
   if (v == 0.0) v = 0.0;
   return ord_encode(v);
+}
+
+// keys of doubles for an ascending sort (the caller sorts all 64 bits)
+__global__ void __launch_bounds__(256) k_rs_keys_from_double(const double* __restrict__ v, int n, unsigned long long* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = rs_key_double(__ldg(v + i));
 }
 
 }  // namespace vpc

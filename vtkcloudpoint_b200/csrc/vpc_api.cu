@@ -16,6 +16,9 @@
 #include "common.cuh"
 #include "dbscan.cuh"
 #include "icp.cuh"
+#include "ingest.cuh"
+#include "sort.cuh"
+#include "stats.cuh"
 
 using namespace vpc;
 
@@ -49,6 +52,7 @@ struct vpc_ctx {
   Arena io;        // device copies of host inputs / outputs (host-pointer entry points)
   Arena icp_model; // model cell list (persists between calls)
   Arena icp_work;  // per-call ICP workspace
+  Arena st;        // sort / cluster statistics / ingest workspace
   // ICP model state
   IcpModel model{};
   bool model_set = false;
@@ -263,6 +267,55 @@ int icp_enqueue_rounds(vpc_ctx* ctx, const double* d_data, int64_t n, double e, 
   return VPC_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// stable radix sort of (u64 key, i32 value) pairs on key bits [begin_bit, end_bit) -- sort.cuh
+// ---------------------------------------------------------------------------------------
+struct SortWs {
+  unsigned long long* keys_alt; int* vals_alt; int* hist; unsigned long long* tile_state; int* counter; int n_tiles; int scan_tiles_;
+};
+size_t sort_ws_bytes(int64_t n) {
+  const int nt = rs_tiles(n);
+  return al256(8ull * n) + al256(4ull * n) + al256(4ull * kRsDigits * (size_t)nt) + al256(8ull * scan_tiles((long long)kRsDigits * nt)) + 256 + 1024;
+}
+SortWs sort_ws_take(Arena& w, int64_t n) {
+  SortWs ws{};
+  ws.n_tiles = rs_tiles(n);
+  ws.scan_tiles_ = scan_tiles((long long)kRsDigits * ws.n_tiles);
+  ws.keys_alt = w.take<unsigned long long>(n);
+  ws.vals_alt = w.take<int>(n);
+  ws.hist = w.take<int>((size_t)kRsDigits * ws.n_tiles);
+  ws.tile_state = w.take<unsigned long long>(ws.scan_tiles_);
+  ws.counter = w.take<int>(1);
+  return ws;
+}
+// keys/vals: caller's buffers (vals_in_identity: the first pass generates 0..n-1 instead of reading vals).
+// The sorted pairs end up in (*keys_out, *vals_out), which are either the caller's buffers or the workspace's.
+int sort_pairs_enqueue(vpc_ctx* ctx, cudaStream_t s, unsigned long long* keys, int* vals, bool vals_in_identity, int64_t n, int begin_bit,
+                       int end_bit, const SortWs& ws, unsigned long long** keys_out, int** vals_out) {
+  unsigned long long* ka = keys; int* va = vals;
+  unsigned long long* kb = ws.keys_alt; int* vb = ws.vals_alt;
+  bool first = true;
+  for (int shift = begin_bit; shift < end_bit; shift += 8) {
+    VPC_CUDA(ctx, cudaMemsetAsync(ws.tile_state, 0, 8ull * ws.scan_tiles_, s));
+    VPC_CUDA(ctx, cudaMemsetAsync(ws.counter, 0, 4, s));
+    VPC_LAUNCH(ctx, k_rs_hist, ws.n_tiles, kRsBlock, s, ka, (int)n, shift, ws.n_tiles, ws.hist);
+    VPC_LAUNCH(ctx, k_scan_exclusive<false>, ws.scan_tiles_, kScanBlock, s, ws.hist, ws.hist, (const int*)nullptr, kRsDigits * ws.n_tiles,
+               ws.tile_state, ws.counter, (int*)nullptr);
+    VPC_LAUNCH(ctx, k_rs_scatter, ws.n_tiles, kRsBlock, s, ka, (first && vals_in_identity) ? (const int*)nullptr : va, (int)n, shift, ws.n_tiles,
+               ws.hist, kb, vb);
+    std::swap(ka, kb); std::swap(va, vb);
+    first = false;
+  }
+  if (first && vals_in_identity) {   // no pass ran (end_bit <= begin_bit): the caller still wants the identity permutation
+    VPC_LAUNCH(ctx, k_rs_iota, blocks_for(n, 256), 256, s, va, (int)n);
+  }
+  *keys_out = ka; *vals_out = va;
+  return VPC_OK;
+}
+
+inline int bits_for(long long max_value) { int b = 0; while (b < 63 && (1ll << b) <= max_value) ++b; return b; }
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -302,7 +355,7 @@ void vpc_destroy(vpc_ctx* ctx) {
   {
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
-    for (Arena* a : {&ctx->db, &ctx->io, &ctx->icp_model, &ctx->icp_work})
+    for (Arena* a : {&ctx->db, &ctx->io, &ctx->icp_model, &ctx->icp_work, &ctx->st})
       if (a->base) cudaFree(a->base);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   }
@@ -786,6 +839,330 @@ int vpc_icp_rigid(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double
     VPC_CUDA(ctx, cudaStreamSynchronize(s));
   }
   ctx->model_set = false;
+  return VPC_OK;
+}
+
+// ---- sort / cluster statistics / matching / ingest (see include/vpc.h) ---------------------
+int vpc_sort_pairs_dev(vpc_ctx* ctx, uint64_t* d_keys, int32_t* d_vals, int64_t n, int32_t begin_bit, int32_t end_bit, int32_t vals_identity,
+                       void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || (n > 0 && (!d_keys || !d_vals)) || begin_bit < 0 || end_bit > 64 || begin_bit > end_bit) return fail(ctx, VPC_E_BADARG, "bad sort arguments");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  if (n == 0) return VPC_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = arena_reserve(ctx, ctx->st, sort_ws_bytes(n));
+  if (rc) return rc;
+  SortWs ws = sort_ws_take(ctx->st, n);
+  unsigned long long* ko; int* vo;
+  rc = sort_pairs_enqueue(ctx, s, reinterpret_cast<unsigned long long*>(d_keys), d_vals, vals_identity != 0, n, begin_bit, end_bit, ws, &ko, &vo);
+  if (rc) return rc;
+  if (ko != reinterpret_cast<unsigned long long*>(d_keys)) {   // odd number of passes: bring the result home
+    VPC_CUDA(ctx, cudaMemcpyAsync(d_keys, ko, 8ull * n, cudaMemcpyDeviceToDevice, s));
+    VPC_CUDA(ctx, cudaMemcpyAsync(d_vals, vo, 4ull * n, cudaMemcpyDeviceToDevice, s));
+  }
+  return VPC_OK;
+}
+
+int vpc_argsort_f64_dev(vpc_ctx* ctx, const double* d_vals, int64_t n, int32_t* d_order, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || (n > 0 && (!d_vals || !d_order))) return fail(ctx, VPC_E_BADARG, "bad argsort arguments");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  if (n == 0) return VPC_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = arena_reserve(ctx, ctx->st, sort_ws_bytes(n) + al256(8ull * n) + al256(4ull * n));
+  if (rc) return rc;
+  SortWs ws = sort_ws_take(ctx->st, n);
+  unsigned long long* keys = ctx->st.take<unsigned long long>(n);
+  int* vals = ctx->st.take<int>(n);
+  VPC_LAUNCH(ctx, k_rs_keys_from_double, blocks_for(n, 256), 256, s, d_vals, (int)n, keys);
+  unsigned long long* ko; int* vo;
+  rc = sort_pairs_enqueue(ctx, s, keys, vals, true, n, 0, 64, ws, &ko, &vo);
+  if (rc) return rc;
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_order, vo, 4ull * n, cudaMemcpyDeviceToDevice, s));
+  return VPC_OK;
+}
+
+static int cluster_groups_dev_locked(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, int32_t* d_members, int32_t* d_offsets,
+                           void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n == 0) { VPC_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, 4ull * (n_clusters + 2ull), s)); return VPC_OK; }
+  int rc = arena_reserve(ctx, ctx->st, sort_ws_bytes(n) + al256(8ull * n) + al256(4ull * n));
+  if (rc) return rc;
+  SortWs ws = sort_ws_take(ctx->st, n);
+  unsigned long long* keys = ctx->st.take<unsigned long long>(n);
+  int* vals = ctx->st.take<int>(n);
+  VPC_LAUNCH(ctx, k_st_keys, blocks_for(n, kStBlock), kStBlock, s, d_cluster_id, (int)n, n_clusters, keys);
+  const int bits = ((bits_for(n_clusters) + 7) / 8) * 8;
+  unsigned long long* ko; int* vo;
+  rc = sort_pairs_enqueue(ctx, s, keys, vals, true, n, 0, bits, ws, &ko, &vo);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_st_offsets, blocks_for(n_clusters + 2ll, kStBlock), kStBlock, s, ko, (int)n, n_clusters, d_offsets);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_members, vo, 4ull * n, cudaMemcpyDeviceToDevice, s));
+  return VPC_OK;
+}
+int vpc_cluster_groups_dev(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, int32_t* d_members, int32_t* d_offsets,
+                           void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || n_clusters < 0 || !d_offsets || (n > 0 && (!d_cluster_id || !d_members))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return cluster_groups_dev_locked(ctx, d_cluster_id, n, n_clusters, d_members, d_offsets, stream);
+}
+
+static int cluster_means_ordered_dev_locked(vpc_ctx* ctx, const int32_t* d_members, const int32_t* d_offsets, int32_t n_clusters, const double* d_vals,
+                                  int64_t n, int32_t n_fields, double* d_means, int32_t* d_counts, void* stream) {
+  const long long total = (long long)(n_clusters + 1) * n_fields;
+  VPC_LAUNCH(ctx, k_st_means_ordered, blocks_for(total, kStBlock), kStBlock, static_cast<cudaStream_t>(stream), d_members, d_offsets, n_clusters,
+             d_vals, (long long)n, n_fields, d_means, d_counts);
+  return VPC_OK;
+}
+int vpc_cluster_means_ordered_dev(vpc_ctx* ctx, const int32_t* d_members, const int32_t* d_offsets, int32_t n_clusters, const double* d_vals,
+                                  int64_t n, int32_t n_fields, double* d_means, int32_t* d_counts, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || n_clusters < 0 || n_fields <= 0 || !d_offsets || !d_means || !d_counts || (n > 0 && (!d_members || !d_vals))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return cluster_means_ordered_dev_locked(ctx, d_members, d_offsets, n_clusters, d_vals, n, n_fields, d_means, d_counts, stream);
+}
+
+static int cluster_circles_dev_locked(vpc_ctx* ctx, const int32_t* d_members, const int32_t* d_offsets, int32_t n_clusters, int64_t n, const double* d_hx,
+                            const double* d_hy, double* d_cx, double* d_cy, double* d_radius, int32_t* d_status, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = arena_reserve(ctx, ctx->st, al256(4ull * (n + 1)) + al256(16ull * (n + 1)) + 1024);
+  if (rc) return rc;
+  int* alive = ctx->st.take<int>(n + 1);
+  double2* hull = ctx->st.take<double2>(n + 1);
+  VPC_LAUNCH(ctx, k_st_circles, blocks_for(32ll * (n_clusters + 1ll), kStBlock), kStBlock, s, d_members, d_offsets, n_clusters, d_hx, d_hy, alive, hull,
+             d_cx, d_cy, d_radius, d_status);
+  return VPC_OK;
+}
+int vpc_cluster_circles_dev(vpc_ctx* ctx, const int32_t* d_members, const int32_t* d_offsets, int32_t n_clusters, int64_t n, const double* d_hx,
+                            const double* d_hy, double* d_cx, double* d_cy, double* d_radius, int32_t* d_status, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || n_clusters < 0 || !d_offsets || !d_cx || !d_cy || !d_radius || !d_status || (n > 0 && (!d_members || !d_hx || !d_hy))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return cluster_circles_dev_locked(ctx, d_members, d_offsets, n_clusters, n, d_hx, d_hy, d_cx, d_cy, d_radius, d_status, stream);
+}
+
+int vpc_radius_filter_dev(vpc_ctx* ctx, const double* d_radius, const int32_t* d_status, int32_t n_clusters, double threshold, uint8_t* d_flag,
+                          void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n_clusters < 0 || !d_radius || !d_status || !d_flag) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_st_radius_filter, blocks_for(n_clusters + 1ll, kStBlock), kStBlock, static_cast<cudaStream_t>(stream), d_radius, d_status, n_clusters,
+             threshold, d_flag);
+  return VPC_OK;
+}
+
+// Host-pointer form of the statistics block of CompleteWork3 (FrmMain.cs:1521-1540): GetClusList + getCircles(3-D) + getCircles(2-D).
+int vpc_cluster_stats(vpc_ctx* ctx, const int32_t* cluster_id, int64_t n, int32_t n_clusters, const double* xyz, const double* mx, const double* my,
+                      double* means5, int32_t* counts, double* circle3d, int32_t* status3d, double* circle2d, int32_t* status2d) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || n_clusters < 0 || !means5 || !counts || (n > 0 && (!cluster_id || !xyz || !mx || !my))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if ((circle3d && !status3d) || (circle2d && !status2d)) return fail(ctx, VPC_E_BADARG, "a circle output needs its status array");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  const size_t k1 = (size_t)n_clusters + 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->own_stream;
+  int rc = arena_reserve(ctx, ctx->io, al256(40ull * (n + 1)) + al256(4ull * (n + 1)) * 2 + al256(4ull * (k1 + 1)) + al256(40ull * k1) + al256(4ull * k1) * 3 +
+                                           al256(24ull * k1) * 2 + 4096);
+  if (rc) return rc;
+  double* d_vals = ctx->io.take<double>(5 * (size_t)(n + 1));     // X Y Z motor_x motor_y, planar with stride n
+  int* d_cid = ctx->io.take<int>(n + 1);
+  int* d_mem = ctx->io.take<int>(n + 1);
+  int* d_off = ctx->io.take<int>(k1 + 1);
+  double* d_means = ctx->io.take<double>(5 * k1);
+  int* d_cnt = ctx->io.take<int>(k1);
+  double* d_c3 = ctx->io.take<double>(3 * k1); int* d_s3 = ctx->io.take<int>(k1);
+  double* d_c2 = ctx->io.take<double>(3 * k1); int* d_s2 = ctx->io.take<int>(k1);
+  if (n > 0) {
+    VPC_CUDA(ctx, cudaMemcpyAsync(d_vals, xyz, 24ull * n, cudaMemcpyHostToDevice, s));
+    VPC_CUDA(ctx, cudaMemcpyAsync(d_vals + 3 * n, mx, 8ull * n, cudaMemcpyHostToDevice, s));
+    VPC_CUDA(ctx, cudaMemcpyAsync(d_vals + 4 * n, my, 8ull * n, cudaMemcpyHostToDevice, s));
+    VPC_CUDA(ctx, cudaMemcpyAsync(d_cid, cluster_id, 4ull * n, cudaMemcpyHostToDevice, s));
+  }
+  rc = cluster_groups_dev_locked(ctx, d_cid, n, n_clusters, d_mem, d_off, s);
+  if (rc) return rc;
+  rc = cluster_means_ordered_dev_locked(ctx, d_mem, d_off, n_clusters, d_vals, n, 5, d_means, d_cnt, s);
+  if (rc) return rc;
+  if (circle3d) { rc = cluster_circles_dev_locked(ctx, d_mem, d_off, n_clusters, n, d_vals, d_vals + n, d_c3, d_c3 + k1, d_c3 + 2 * k1, d_s3, s); if (rc) return rc; }
+  // both circle passes use the same scratch of ctx->st; the stream orders them
+  if (circle2d) { rc = cluster_circles_dev_locked(ctx, d_mem, d_off, n_clusters, n, d_vals + 3 * n, d_vals + 4 * n, d_c2, d_c2 + k1, d_c2 + 2 * k1, d_s2, s); if (rc) return rc; }
+  VPC_CUDA(ctx, cudaMemcpyAsync(means5, d_means, 40ull * k1, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt, 4ull * k1, cudaMemcpyDeviceToHost, s));
+  if (circle3d) { VPC_CUDA(ctx, cudaMemcpyAsync(circle3d, d_c3, 24ull * k1, cudaMemcpyDeviceToHost, s)); VPC_CUDA(ctx, cudaMemcpyAsync(status3d, d_s3, 4ull * k1, cudaMemcpyDeviceToHost, s)); }
+  if (circle2d) { VPC_CUDA(ctx, cudaMemcpyAsync(circle2d, d_c2, 24ull * k1, cudaMemcpyDeviceToHost, s)); VPC_CUDA(ctx, cudaMemcpyAsync(status2d, d_s2, 4ull * k1, cudaMemcpyDeviceToHost, s)); }
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  return VPC_OK;
+}
+
+int vpc_nearest_truth_2d_dev(vpc_ctx* ctx, const int32_t* d_truth_id, const double* d_px, const double* d_py, int64_t n, double radius,
+                             int32_t* d_id, int32_t* d_index, double* d_dist, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || (n > 0 && (!d_px || !d_py || !d_id))) return fail(ctx, VPC_E_BADARG, "bad points/id");
+  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->model_set) return fail(ctx, VPC_E_STATE, "vpc_icp_set_model_dev (the truth points, z = 0) has not been called");
+  if (n == 0) return VPC_OK;
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_nearest_truth_2d, blocks_for(n, kIcpBlock), kIcpBlock, static_cast<cudaStream_t>(stream), ctx->model, d_truth_id, d_px, d_py, (int)n,
+             radius, d_id, d_index, d_dist);
+  return VPC_OK;
+}
+
+int vpc_nearest_truth_2d(vpc_ctx* ctx, const double* truth_x, const double* truth_y, const int32_t* truth_id, int64_t m, const double* px,
+                         const double* py, int64_t n, double radius, int32_t* id) {
+  if (!ctx) return VPC_E_BADARG;
+  if (m < 0 || n < 0 || (m > 0 && (!truth_x || !truth_y)) || (n > 0 && (!px || !py || !id))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (m > 2147483646ll || n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "size exceeds 2^31-2");
+  if (n == 0) return VPC_OK;
+  if (m == 0) { std::memset(id, 0, 4ull * n); return VPC_OK; }   // FirstOrDefault over an empty sequence (FrmMain.cs:3456)
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->own_stream;
+  int rc = arena_reserve(ctx, ctx->io, al256(24ull * m) + al256(4ull * m) + al256(8ull * n) * 2 + al256(4ull * n) + 1024);
+  if (rc) return rc;
+  double* d_model = ctx->io.take<double>(3 * m);
+  int* d_tid = ctx->io.take<int>(m);
+  double* d_px = ctx->io.take<double>(n);
+  double* d_py = ctx->io.take<double>(n);
+  int* d_id = ctx->io.take<int>(n);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_model, truth_x, 8ull * m, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_model + m, truth_y, 8ull * m, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemsetAsync(d_model + 2 * m, 0, 8ull * m, s));
+  if (truth_id) VPC_CUDA(ctx, cudaMemcpyAsync(d_tid, truth_id, 4ull * m, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_px, px, 8ull * n, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_py, py, 8ull * n, cudaMemcpyHostToDevice, s));
+  rc = icp_set_model(ctx, d_model, m, s);
+  if (rc) return rc;
+  VPC_LAUNCH(ctx, k_nearest_truth_2d, blocks_for(n, kIcpBlock), kIcpBlock, s, ctx->model, truth_id ? (const int*)d_tid : (const int*)nullptr, d_px, d_py,
+             (int)n, radius, d_id, (int*)nullptr, (double*)nullptr);
+  VPC_CUDA(ctx, cudaMemcpyAsync(id, d_id, 4ull * n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  ctx->model_set = false;
+  return VPC_OK;
+}
+
+int vpc_polar_to_xyz_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, const double* d_dist, int64_t n, double x_angle, double y_angle,
+                         int32_t xdir, int32_t ydir, double* d_xyz, uint8_t* d_keep, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || (n > 0 && (!d_mx || !d_my || !d_dist || !d_xyz || !d_keep))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (xdir < 1 || xdir > 4 || ydir < 1 || ydir > 4) return fail(ctx, VPC_E_BADARG, "xdir / ydir are 1..4 (ImportPts radio buttons)");
+  if (n == 0) return VPC_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_in_polar_to_xyz, blocks_for(n, kInBlock), kInBlock, static_cast<cudaStream_t>(stream), d_mx, d_my, d_dist, (long long)n, x_angle,
+             y_angle, xdir, ydir, d_xyz, d_xyz + n, d_xyz + 2 * n, d_keep);
+  return VPC_OK;
+}
+
+static int dedupe_xyz_dev_locked(vpc_ctx* ctx, const double* d_xyz, const uint8_t* d_live, int64_t n, uint8_t* d_keep, int32_t* d_first_of, int32_t* d_n_dup,
+                       void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d_n_dup) VPC_CUDA(ctx, cudaMemsetAsync(d_n_dup, 0, 4, s));
+  if (n == 0) return VPC_OK;
+  long long slots = 1024;
+  while (slots < 2 * n) slots <<= 1;
+  int rc = arena_reserve(ctx, ctx->st, al256(4ull * slots) + 1024);
+  if (rc) return rc;
+  int* table = ctx->st.take<int>(slots);
+  VPC_LAUNCH(ctx, k_in_table_clear, blocks_for(slots, kInBlock), kInBlock, s, table, slots);
+  VPC_LAUNCH(ctx, k_in_dedupe_insert, blocks_for(n, kInBlock), kInBlock, s, d_xyz, d_xyz + n, d_xyz + 2 * n, d_live, (int)n, table, (unsigned)(slots - 1));
+  VPC_LAUNCH(ctx, k_in_dedupe_resolve, blocks_for(n, kInBlock), kInBlock, s, d_xyz, d_xyz + n, d_xyz + 2 * n, d_live, (int)n, table, (unsigned)(slots - 1),
+             d_keep, d_first_of, d_n_dup);
+  return VPC_OK;
+}
+int vpc_dedupe_xyz_dev(vpc_ctx* ctx, const double* d_xyz, const uint8_t* d_live, int64_t n, uint8_t* d_keep, int32_t* d_first_of, int32_t* d_n_dup,
+                       void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (n < 0 || (n > 0 && (!d_xyz || !d_keep))) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (n > 1073741824ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^30 rows per call");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return dedupe_xyz_dev_locked(ctx, d_xyz, d_live, n, d_keep, d_first_of, d_n_dup, stream);
+}
+
+// Host-pointer ingest of a scan file held in memory: rows -> (motor_x, motor_y, Distance) -> gate -> XYZ -> duplicate removal.
+int vpc_ingest_text(vpc_ctx* ctx, const char* text, int64_t len, double x_angle, double y_angle, int32_t xdir, int32_t ydir, int32_t remove_duplicates,
+                    int64_t row_cap, double* mx, double* my, double* dist, double* xyz, uint8_t* keep, uint8_t* row_status, int64_t* n_rows,
+                    int64_t* n_kept, int64_t* n_duplicates) {
+  if (!ctx) return VPC_E_BADARG;
+  if (len < 0 || (len > 0 && !text) || row_cap < 0 || !n_rows || (row_cap > 0 && (!mx || !my || !dist || !xyz || !keep || !row_status)))
+    return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (xdir < 1 || xdir > 4 || ydir < 1 || ydir > 4) return fail(ctx, VPC_E_BADARG, "xdir / ydir are 1..4 (ImportPts radio buttons)");
+  if (remove_duplicates && !(xdir == 2 && ydir == 1))
+    return fail(ctx, VPC_E_BADARG, "duplicate removal is defined for the default orientation xdir = 2, ydir = 1 (the C# compares p.X with tmpx, FrmMain.cs:1065)");
+  *n_rows = 0;
+  if (n_kept) *n_kept = 0;
+  if (n_duplicates) *n_duplicates = 0;
+  if (len == 0) return VPC_OK;
+  if (len > (1ll << 40)) return fail(ctx, VPC_E_TOOBIG, "text exceeds 1 TiB");
+  const long long tiles = (len + kTxTile - 1) / kTxTile;
+  if (tiles > 2147483000ll) return fail(ctx, VPC_E_TOOBIG, "text too large for one call");
+  const int stiles = scan_tiles(tiles + 1);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->own_stream;
+  int rc = arena_reserve(ctx, ctx->io, al256((size_t)len + 16) + al256(4ull * (tiles + 1)) + al256(8ull * stiles) + 512 + al256(8ull * (row_cap + 2)) +
+                                           al256(8ull * (row_cap + 1)) * 6 + al256((size_t)row_cap + 1) * 3 + 4096);
+  if (rc) return rc;
+  unsigned char* d_text = ctx->io.take<unsigned char>((size_t)len + 16);
+  int* d_tile = ctx->io.take<int>(tiles + 1);
+  unsigned long long* d_state = ctx->io.take<unsigned long long>(stiles);
+  int* d_counter = ctx->io.take<int>(1);
+  int* d_total = ctx->io.take<int>(1);
+  VPC_CUDA(ctx, cudaMemcpyAsync(d_text, text, (size_t)len, cudaMemcpyHostToDevice, s));
+  VPC_CUDA(ctx, cudaMemsetAsync(d_state, 0, 8ull * stiles, s));
+  VPC_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 4, s));
+  VPC_LAUNCH(ctx, k_in_count_lines, (int)tiles, 256, s, d_text, (long long)len, d_tile);
+  VPC_LAUNCH(ctx, k_scan_exclusive<false>, stiles, kScanBlock, s, d_tile, d_tile, (const int*)nullptr, (int)tiles, d_state, d_counter, d_total);
+  int newlines = 0;
+  VPC_CUDA(ctx, cudaMemcpyAsync(&newlines, d_total, 4, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  const long long n_lines = (long long)newlines + (text[len - 1] != '\n' ? 1 : 0);
+  const long long rows = n_lines > 0 ? n_lines - 1 : 0;             // line 0 is the header (FrmMain.cs:991)
+  *n_rows = rows;
+  if (rows > row_cap) return fail(ctx, VPC_E_BADARG, "row_cap is smaller than the number of rows (n_rows holds the count)");
+  if (rows == 0) return VPC_OK;
+  if (rows > 1073741824ll) return fail(ctx, VPC_E_TOOBIG, "more than 2^30 rows in one call");
+  long long* d_ls = ctx->io.take<long long>(row_cap + 2);
+  double* d_mx = ctx->io.take<double>(row_cap + 1);
+  double* d_my = ctx->io.take<double>(row_cap + 1);
+  double* d_ds = ctx->io.take<double>(row_cap + 1);
+  double* d_xyz = ctx->io.take<double>(3 * (size_t)(row_cap + 1));
+  unsigned char* d_keep = ctx->io.take<unsigned char>(row_cap + 1);
+  unsigned char* d_keep2 = ctx->io.take<unsigned char>(row_cap + 1);
+  unsigned char* d_st = ctx->io.take<unsigned char>(row_cap + 1);
+  VPC_LAUNCH(ctx, k_in_line_starts, (int)tiles, 256, s, d_text, (long long)len, d_tile, d_ls, n_lines);
+  VPC_LAUNCH(ctx, k_in_parse_rows, blocks_for(rows, kInBlock), kInBlock, s, d_text, (long long)len, d_ls, n_lines, d_mx, d_my, d_ds, d_st);
+  VPC_LAUNCH(ctx, k_in_polar_to_xyz, blocks_for(rows, kInBlock), kInBlock, s, d_mx, d_my, d_ds, rows, x_angle, y_angle, xdir, ydir, d_xyz, d_xyz + rows,
+             d_xyz + 2 * rows, d_keep);
+  unsigned char* d_final = d_keep;
+  if (remove_duplicates) {
+    rc = dedupe_xyz_dev_locked(ctx, d_xyz, d_keep, rows, d_keep2, nullptr, d_total, s);
+    if (rc) return rc;
+    d_final = d_keep2;
+  }
+  int ndup = 0;
+  VPC_CUDA(ctx, cudaMemcpyAsync(mx, d_mx, 8ull * rows, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(my, d_my, 8ull * rows, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(dist, d_ds, 8ull * rows, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(xyz, d_xyz, 24ull * rows, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(keep, d_final, (size_t)rows, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaMemcpyAsync(row_status, d_st, (size_t)rows, cudaMemcpyDeviceToHost, s));
+  if (remove_duplicates) VPC_CUDA(ctx, cudaMemcpyAsync(&ndup, d_total, 4, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, cudaStreamSynchronize(s));
+  if (n_duplicates) *n_duplicates = ndup;
+  if (n_kept) { long long k = 0; for (long long i = 0; i < rows; ++i) k += keep[i]; *n_kept = k; }
   return VPC_OK;
 }
 
