@@ -69,7 +69,9 @@ struct DbArgs {
   int* cell_count;   // [cell_cap+1]  zero on entry and on exit (k_db_scatter clears what k_db_hist counted)
   int* cell_start;   // [cell_cap+1]
   DbRec* rec;        // [n]  per sorted position: coordinates, original index, parent, cell/component info
-  unsigned char* core;  // [n] by sorted position: 0 = not core, 1 = core, 2 = still to be counted
+  unsigned char* core;  // [n] by sorted position: 1 = core, 2 = still to be counted, 0 = not core, 8 + k = not core and its k <= kNbrCap
+                        //     neighbours (all of them, self excluded) are listed in nbr[]
+  int* nbr;             // [n * kNbrCap] by sorted position: neighbour positions of the non-core points (written by k_db_count)
   // segmented mode (vpc_dbscan_l1_2d_cells): independent clouds in one launch, points of a segment are
   // contiguous in the input (CSR offsets); neighbours must share the segment, ids are segment-local
   const int* seg_off;   // [n_seg+1] device, nullptr = one cloud
@@ -93,6 +95,7 @@ struct DbArgs {
 };
 
 constexpr int kDbBlock = 256;
+constexpr int kNbrCap = 8;   // one 32-byte sector of neighbour positions per non-core point
 constexpr int kNone = 0x7fffffff;
 
 // one-time initialisation of a fresh workspace (cell_count must be all zero, ctrl keys armed)
@@ -285,9 +288,22 @@ __device__ __forceinline__ DbStencil db_stencil(const DbCtrl& c, double2 p) {
 
 __device__ __forceinline__ double2 db_xy(const DbRec* __restrict__ rec, int j) { return __ldg(reinterpret_cast<const double2*>(rec + j)); }
 
-// number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight
+// The positions of a point's neighbours, kept in registers while k_db_count runs (static indices only) and written as
+// one 32-byte sector at the end, for non-core points only.
+struct DbNbrList {
+  int v[kNbrCap];
+  int n;     // neighbours seen (may exceed kNbrCap: then the list is not usable)
+  __device__ __forceinline__ void push(int j) {
+#pragma unroll
+    for (int t = 0; t < kNbrCap; ++t) if (n == t) v[t] = j;
+    ++n;
+  }
+};
+
+// number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight.  Hits other than `self`
+// are appended to `list` for the border rule of k_db_resolve.
 __device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int j0, int j1, int s, int e, double2 me, double eps,
-                                              const int* __restrict__ sseg, int myseg) {
+                                              const int* __restrict__ sseg, int myseg, int self, DbNbrList& list) {
   int cnt = 0;
   for (int j = j0; j < j1; j += 4) {
     double2 q[4];
@@ -296,7 +312,9 @@ __device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int jj = j + k;
-      cnt += (jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj] == myseg)) ? 1 : 0;
+      const bool hit = jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj] == myseg);
+      cnt += hit ? 1 : 0;
+      if (hit && jj != self) list.push(jj);
     }
   }
   return cnt;
@@ -340,7 +358,15 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
   const int s = __ldg(a.cell_start + own), e = __ldg(a.cell_start + own + 1);
   const int myseg = a.seg_off ? a.sseg[p] : 0;
   int cnt = 0, es = 0, ee = 0;         // [es, ee): range excluded from the tests because it is already counted
-  if (c.clique) { cnt = e - s; es = s; ee = e; }   // every point of the own cell is a neighbour (self included)
+  DbNbrList list;
+  list.n = 0;
+#pragma unroll
+  for (int t = 0; t < kNbrCap; ++t) list.v[t] = 0;
+  if (c.clique) {                      // every point of the own cell is a neighbour (self included); the cell is not dense,
+    cnt = e - s; es = s; ee = e;       // so it holds fewer than min_pts points
+    for (int j = s; j < e; ++j)
+      if (j != p) list.push(j);
+  }
   for (int rb = st.vlo; rb <= st.vhi && cnt < need; rb += 4) {
     int j0[4], j1[4];
 #pragma unroll
@@ -352,10 +378,17 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-      if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg);
+      if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg, p, list);
   }
   const bool core = cnt >= need;       // only 'count >= minPts' matters (:47)
-  a.core[p] = core ? 1 : 0;
+  // a non-core point has seen ALL its neighbours (no early exit): its list is complete unless it overflowed
+  const bool listed = !core && list.n <= kNbrCap;
+  a.core[p] = core ? 1 : (listed ? 8 + list.n : 0);
+  if (listed && list.n > 0) {
+    int4* lp = reinterpret_cast<int4*>(a.nbr + (long long)p * kNbrCap);
+    lp[0] = make_int4(list.v[0], list.v[1], list.v[2], list.v[3]);
+    if (list.n > 4) lp[1] = make_int4(list.v[4], list.v[5], list.v[6], list.v[7]);
+  }
   if (core && c.clique) atomicMin(&a.rec[s].cinfo.x, p);   // first core position of the cell, at the cell's first slot
 }
 
@@ -400,7 +433,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const DbCtrl c = *a.ctrl;
   if (p >= c.n_valid) return;
-  if (!a.core[p]) return;
+  if (a.core[p] != 1) return;
   const double2 me = db_xy(a.rec, p);
   const DbStencil st = db_stencil(c, me);
   const RecParent par{a.rec};
@@ -430,7 +463,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
           const int root = uf_find(par, lB[k]);
           if (root == rp) continue;
           for (int j = lB[k]; j < sB[k + 1]; ++j)
-            if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps)) { rp = uf_unite_roots(par, rp, root); break; }
+            if (a.core[j] == 1 && db_near(me, db_xy(a.rec, j), a.eps)) { rp = uf_unite_roots(par, rp, root); break; }
         }
       }
     }
@@ -439,7 +472,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
       const int j0 = __ldg(a.cell_start + row * c.ncu + st.ulo);
       const int j1 = min(__ldg(a.cell_start + row * c.ncu + st.uhi + 1), p);  // each edge once: partners before p
       for (int j = j0; j < j1; ++j) {
-        if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p])) {
+        if (a.core[j] == 1 && db_near(me, db_xy(a.rec, j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p])) {
           const int rj = uf_find(par, j);
           if (rj != rp) rp = uf_unite_roots(par, rp, rj);
         }
@@ -452,7 +485,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
 __global__ void __launch_bounds__(kDbBlock) k_db_flatten(DbArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_valid = a.ctrl->n_valid;
-  const bool active = (p < n_valid) && a.core[p];
+  const bool active = (p < n_valid) && a.core[p] == 1;
   int root = -1, orig = kNone;
   if (active) {
     root = uf_find_ro(RecParent{a.rec}, p);
@@ -476,7 +509,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
   if (blockIdx.x * blockDim.x >= c.n_valid) return;
   bool border = false;
   if (p0 < c.n_valid) {
-    if (a.core[p0]) {
+    if (a.core[p0] == 1) {
       const int me_i = a.rec[p0].sidx;
       const int key = a.rec[a.rec[p0].parent].cinfo.y;
       // one scattered store per point: in the full pipeline the core flag rides in the key (core: -2 - key)
@@ -494,9 +527,30 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
   // border rule: the reference relabels unconditionally (:87), so the cluster expanded
   // last -- the one with the largest id = largest minimum core index -- wins.
   const int me_i = a.rec[p].sidx;
+  int key = -1;
+  const int code = a.core[p];
+  if (code >= 8) {
+    // k_db_count listed every neighbour of this point: no second region query, just their core flags and cluster keys
+    const int k = code - 8;
+    if (k > 0) {
+      const int4* lp = reinterpret_cast<const int4*>(a.nbr + (long long)p * kNbrCap);
+      const int4 l0 = lp[0], l1 = (k > 4) ? lp[1] : make_int4(0, 0, 0, 0);
+      const int nb[kNbrCap] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+      bool is_core[kNbrCap];
+      int par[kNbrCap];
+#pragma unroll
+      for (int t = 0; t < kNbrCap; ++t) is_core[t] = (t < k) && a.core[nb[t]] == 1;
+#pragma unroll
+      for (int t = 0; t < kNbrCap; ++t) par[t] = is_core[t] ? a.rec[nb[t]].parent : -1;
+#pragma unroll
+      for (int t = 0; t < kNbrCap; ++t) if (par[t] >= 0) key = max(key, a.rec[par[t]].cinfo.y);
+    }
+    if (!a.cluster_id) a.is_key[me_i] = 0;
+    a.compkey[me_i] = key;
+    return;
+  }
   const double2 me = db_xy(a.rec, p);
   const DbStencil st = db_stencil(c, me);
-  int key = -1;
   for (int row = st.vlo; row <= st.vhi; ++row) {
     const int base = row * c.ncu;
     if (c.clique) {
@@ -512,13 +566,13 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
         for (int k = 0; k < 4; ++k) {
           if (kB[k] <= key) continue;
           for (int j = lB[k]; j < sB[k + 1]; ++j)
-            if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps)) { key = kB[k]; break; }
+            if (a.core[j] == 1 && db_near(me, db_xy(a.rec, j), a.eps)) { key = kB[k]; break; }
         }
       }
     } else {
       const int j0 = __ldg(a.cell_start + base + st.ulo), j1 = __ldg(a.cell_start + base + st.uhi + 1);
       for (int j = j0; j < j1; ++j)
-        if (a.core[j] && db_near(me, db_xy(a.rec, j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p]))
+        if (a.core[j] == 1 && db_near(me, db_xy(a.rec, j), a.eps) && (!a.seg_off || a.sseg[j] == a.sseg[p]))
           key = max(key, a.rec[a.rec[j].parent].cinfo.y);
     }
   }
@@ -560,7 +614,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_export_core(DbArgs a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.ctrl->n_valid) return;
   const int i = a.rec[p].sidx;
-  const bool core = a.core[p] != 0;
+  const bool core = a.core[p] == 1;
   a.is_key[i] = core ? 1 : 0;
   a.compkey[i] = core ? a.rec[a.rec[p].parent].cinfo.y : -1;
 }
@@ -569,7 +623,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_export_core(DbArgs a) {
 __global__ void __launch_bounds__(kDbBlock)
 k_db_remap_roots(DbArgs a, const int* __restrict__ map_from, const int* __restrict__ map_to, int n_map) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.ctrl->n_valid || !a.core[p] || a.rec[p].parent != p) return;
+  if (p >= a.ctrl->n_valid || a.core[p] != 1 || a.rec[p].parent != p) return;
   const int key = a.rec[p].cinfo.y;
   int lo = 0, hi = n_map;
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(map_from + mid) < key) lo = mid + 1; else hi = mid; }

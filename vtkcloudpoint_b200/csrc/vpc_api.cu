@@ -140,7 +140,7 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   const int cell_cap = (int)cap_ll;
   const long long nwords = (n >> 5) + 1;   // cluster-head bitmap
   const int tiles0 = scan_tiles((long long)cell_cap + 1), tiles1 = scan_tiles(nwords);
-  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * (d_seg_off ? 3 : 1) + al256(8ull * n) + al256(32ull * n) + al256(4ull * nwords) * 2 +
+  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * (d_seg_off ? 3 : 1) + al256(8ull * n) + al256(32ull * n) + al256(4ull * kNbrCap * (size_t)n) + al256(4ull * nwords) * 2 +
                  al256(4ull * (cell_cap + 1ull)) * 2 +
                  al256((size_t)n) + al256(8ull * tiles0) + al256(8ull * tiles1) + 4096;
   const char* base_before = ctx->db.base;
@@ -156,6 +156,7 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   a.keyslot = w.take<int2>(n);
   a.rec = w.take<DbRec>(n);
   a.core = w.take<unsigned char>(n);
+  a.nbr = w.take<int>((size_t)kNbrCap * n);
   a.compkey = w.take<int>(n);
   a.headbits = w.take<unsigned>(nwords);
   a.rank = w.take<int>(nwords);
