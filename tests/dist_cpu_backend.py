@@ -116,3 +116,29 @@ class CpuCheckerIcpBackend:
                 self.done = True
         st = np.concatenate([self.R.ravel(), self.T, [self.d, self.round, float(self.converged), 0.0]])
         return torch.from_numpy(st)
+
+
+class CpuPipelineBackend:
+    """Checker-backed stand-in for vtkcloudpoint_b200.pipeline.GpuPipelineBackend (CPU oracle underneath)."""
+
+    def __init__(self):
+        self.db = CpuCheckerBackend()
+        self.icp = CpuCheckerIcpBackend()
+
+    def dbscan_single(self, mx, my, eps, min_pts):
+        cid, key, cls, amount = oracle_py.dbscan(mx.numpy(), my.numpy(), eps, min_pts, 0, variant="grid")
+        return torch.from_numpy(cid), torch.from_numpy(key), amount
+
+    def cluster_stats(self, cid_local, k_local, vals5):
+        v = vals5.numpy()
+        r = oracle_py.cluster_stats(cid_local.numpy(), k_local, v[0:3], v[3], v[4], circles3d=True, circles2d=False)
+        return torch.from_numpy(r["means"]), torch.from_numpy(r["counts"]), torch.from_numpy(r["circle3d"]), torch.from_numpy(r["status3d"])
+
+    def radius_flag(self, circ, status, k, thr):
+        f = (status.numpy() == 1) & (circ.numpy()[2] > thr)
+        f[0] = False
+        return torch.from_numpy(f.astype(np.uint8))
+
+    def match_within(self, truth_planar, centres_planar, match_distance):
+        mid, d = oracle_py.match_within(truth_planar.numpy(), centres_planar.numpy(), match_distance)
+        return torch.from_numpy(mid), torch.from_numpy(d)
