@@ -16,7 +16,7 @@ def scene(seed: int, grid: int, n_total: int, fat_every: int = 17):
     near = (np.abs(mx - (149.0 + 0.5 * cx)) < 0.06) & (np.abs(my - (307.0 + 0.5 * cy)) < 0.06)
     fat = near & ((cx + grid * cy) % fat_every == 0)
     mx = np.where(fat, 149.0 + 0.5 * cx + (mx - (149.0 + 0.5 * cx)) * 2.6, mx)
-    dist = 41.7 + 0.42 * synth.uniform(seed, 40, np.arange(len(mx), dtype=np.uint64))
+    dist = 41.91 + 0.004 * (synth.uniform(seed, 40, np.arange(len(mx), dtype=np.uint64)) - 0.5)   # a flat target: range spread << pitch
     xyz, keep = oracle_py.polar_to_xyz(mx, my, dist, 149.0, 307.0)
     assert keep.all()
     return mx, my, np.ascontiguousarray(xyz)

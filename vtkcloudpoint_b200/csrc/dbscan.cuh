@@ -288,22 +288,9 @@ __device__ __forceinline__ DbStencil db_stencil(const DbCtrl& c, double2 p) {
 
 __device__ __forceinline__ double2 db_xy(const DbRec* __restrict__ rec, int j) { return __ldg(reinterpret_cast<const double2*>(rec + j)); }
 
-// The positions of a point's neighbours, kept in registers while k_db_count runs (static indices only) and written as
-// one 32-byte sector at the end, for non-core points only.
-struct DbNbrList {
-  int v[kNbrCap];
-  int n;     // neighbours seen (may exceed kNbrCap: then the list is not usable)
-  __device__ __forceinline__ void push(int j) {
-#pragma unroll
-    for (int t = 0; t < kNbrCap; ++t) if (n == t) v[t] = j;
-    ++n;
-  }
-};
-
-// number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight.  Hits other than `self`
-// are appended to `list` for the border rule of k_db_resolve.
+// number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight
 __device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int j0, int j1, int s, int e, double2 me, double eps,
-                                              const int* __restrict__ sseg, int myseg, int self, DbNbrList& list) {
+                                              const int* __restrict__ sseg, int myseg) {
   int cnt = 0;
   for (int j = j0; j < j1; j += 4) {
     double2 q[4];
@@ -312,9 +299,7 @@ __device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int jj = j + k;
-      const bool hit = jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj] == myseg);
-      cnt += hit ? 1 : 0;
-      if (hit && jj != self) list.push(jj);
+      cnt += (jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj] == myseg)) ? 1 : 0;
     }
   }
   return cnt;
@@ -358,15 +343,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
   const int s = __ldg(a.cell_start + own), e = __ldg(a.cell_start + own + 1);
   const int myseg = a.seg_off ? a.sseg[p] : 0;
   int cnt = 0, es = 0, ee = 0;         // [es, ee): range excluded from the tests because it is already counted
-  DbNbrList list;
-  list.n = 0;
-#pragma unroll
-  for (int t = 0; t < kNbrCap; ++t) list.v[t] = 0;
-  if (c.clique) {                      // every point of the own cell is a neighbour (self included); the cell is not dense,
-    cnt = e - s; es = s; ee = e;       // so it holds fewer than min_pts points
-    for (int j = s; j < e; ++j)
-      if (j != p) list.push(j);
-  }
+  if (c.clique) { cnt = e - s; es = s; ee = e; }   // every point of the own cell is a neighbour (self included)
   for (int rb = st.vlo; rb <= st.vhi && cnt < need; rb += 4) {
     int j0[4], j1[4];
 #pragma unroll
@@ -378,17 +355,10 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-      if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg, p, list);
+      if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg);
   }
   const bool core = cnt >= need;       // only 'count >= minPts' matters (:47)
-  // a non-core point has seen ALL its neighbours (no early exit): its list is complete unless it overflowed
-  const bool listed = !core && list.n <= kNbrCap;
-  a.core[p] = core ? 1 : (listed ? 8 + list.n : 0);
-  if (listed && list.n > 0) {
-    int4* lp = reinterpret_cast<int4*>(a.nbr + (long long)p * kNbrCap);
-    lp[0] = make_int4(list.v[0], list.v[1], list.v[2], list.v[3]);
-    if (list.n > 4) lp[1] = make_int4(list.v[4], list.v[5], list.v[6], list.v[7]);
-  }
+  a.core[p] = core ? 1 : 0;
   if (core && c.clique) atomicMin(&a.rec[s].cinfo.x, p);   // first core position of the cell, at the cell's first slot
 }
 
