@@ -190,3 +190,41 @@ def test_slab_lean_single_rank(ctx, oracle):
         np.testing.assert_array_equal(cid.cpu().numpy(), ocid)
         np.testing.assert_array_equal(key.cpu().numpy(), okey)
         np.testing.assert_array_equal(cls.cpu().numpy(), ocls)
+
+
+@pytest.fixture
+def banded_mode():
+    """Force the band-partitioned counting sort (normally taken by clouds of >= 3M points) at any size."""
+    import os
+    os.environ["VPC_DB_BAND_MIN"] = "1"
+    yield
+    os.environ.pop("VPC_DB_BAND_MIN", None)
+
+
+def test_banded_path_small_cases(ctx, oracle, banded_mode):
+    # the same semantics through the band partition: C1, lattice ties, non-finite points, min_pts <= 0, eps < 0, huge extents
+    mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000, decimals=3)
+    assert _check(ctx, oracle, mx, my, 0.07, 7, variant="literal").cluster_amount == 196
+    rng = np.random.default_rng(21)
+    lx, ly = rng.integers(0, 60, 4000) * 0.25, rng.integers(0, 60, 4000) * 0.25
+    _check(ctx, oracle, lx, ly, 0.5, 4, variant="literal")
+    x, y = rng.uniform(0, 1, 700), rng.uniform(0, 1, 700)
+    x[[3, 77]] = np.nan; y[5] = np.inf; x[9] = -np.inf
+    for eps, min_pts in ((0.05, 4), (0.05, 1), (0.05, 0), (0.05, -3), (-1.0, 3), (-1.0, 0), (float("nan"), 2), (0.0, 1), (5.0, 3)):
+        _check(ctx, oracle, x, y, eps, min_pts, 7, variant="literal")
+    x = np.concatenate([rng.uniform(0, 1, 300), 1e9 + rng.uniform(0, 1, 300)])
+    _check(ctx, oracle, x, rng.uniform(0, 1, 600), 0.05, 3, variant="literal")
+    for n in (1, 2, 255, 257, 4097):
+        _check(ctx, oracle, rng.uniform(0, 1, n), rng.uniform(0, 1, n), 0.05, 2, variant="literal")
+
+
+def test_banded_equals_direct_at_c2(ctx, oracle, banded_mode):
+    mx, my = synth.dbscan_cloud(0xC2, 140, n_total=1_000_000)
+    banded = ctx.dbscan(mx, my, 0.07, 7, 0)
+    import os
+    os.environ.pop("VPC_DB_BAND_MIN", None)
+    direct = ctx.dbscan(mx, my, 0.07, 7, 0)
+    assert banded.cluster_amount == direct.cluster_amount >= 19600
+    np.testing.assert_array_equal(banded.cluster_id, direct.cluster_id)
+    np.testing.assert_array_equal(banded.is_key, direct.is_key)
+    np.testing.assert_array_equal(banded.is_classed, direct.is_classed)

@@ -9,7 +9,7 @@ from vtkcloudpoint_b200 import Context, synth
 ctx = Context(0)
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for n in [int(a) for a in sys.argv[1:]] or [1_000_000, 4_000_000, 16_000_000]:
+for n in [int(a) for a in sys.argv[1:] if a.isdigit()] or [1_000_000, 4_000_000, 16_000_000]:
     grid = int(round((n * 0.784 / 40) ** 0.5))
     xs, ys = [], []
     for s in range(0, n, 4_000_000):

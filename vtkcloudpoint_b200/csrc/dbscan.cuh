@@ -43,7 +43,8 @@ struct DbCtrl {
   int n_valid;   // points that take part in the grid
   int n_roots;   // number of clusters found
   unsigned blocks_done;
-  int scan_counter[2];
+  int scan_counter[3];
+  int n_banded;  // banded mode: points that went through the band partition (= points in the grid)
 };
 
 // Everything a sorted position owns, in ONE 32-byte sector: the scatter writes a full sector per point and
@@ -86,7 +87,14 @@ struct DbArgs {
   int* rank;         // [n/32 + 1] exclusive scan of popc(headbits)
   unsigned long long* tile_state0;  // scan states (cells)
   unsigned long long* tile_state1;  // scan states (bitmap words)
-  int tiles0, tiles1;
+  unsigned long long* tile_state2;  // scan states (band histogram), banded mode only
+  int tiles0, tiles1, tiles2;
+  // banded mode (large clouds): the points are first partitioned into 256 bands of consecutive cells so that the cell
+  // histogram and the scatter into rec[] work on an L2-sized window instead of the whole array
+  int banded;
+  DbRec* tmp;        // [n] band-ordered staging records {x, y, original index, cell key}
+  int* band_hist;    // [256 * band_tiles] digit-major per-tile band counts -> offsets
+  int band_tiles;
   // outputs (device)
   int* cluster_id;
   unsigned char* is_key;
@@ -106,8 +114,8 @@ __global__ void __launch_bounds__(kDbBlock) k_db_ws_init(DbArgs a) {
   if (tid == 0) {
     DbCtrl* c = a.ctrl;
     c->umin_k = ~0ull; c->vmin_k = ~0ull; c->umax_k = 0ull; c->vmax_k = 0ull;
-    c->blocks_done = 0; c->scan_counter[0] = 0; c->scan_counter[1] = 0;
-    c->n_valid = 0; c->n_roots = 0;
+    c->blocks_done = 0; c->scan_counter[0] = 0; c->scan_counter[1] = 0; c->scan_counter[2] = 0;
+    c->n_valid = 0; c->n_roots = 0; c->n_banded = 0;
   }
 }
 
@@ -126,6 +134,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long i = tid; i < a.tiles0; i += nth) a.tile_state0[i] = 0;
   for (long long i = tid; i < a.tiles1; i += nth) a.tile_state1[i] = 0;
+  if (a.banded) for (long long i = tid; i < a.tiles2; i += nth) a.tile_state2[i] = 0;
   for (long long i = tid; i <= (a.n >> 5); i += nth) a.headbits[i] = 0u;
   auto take = [&](double x, double y) {
     if (db_valid(x, y, eps_ok)) {
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
   const unsigned long long kv0 = ld_relaxed_u64(&c->vmin_k), kv1 = ld_relaxed_u64(&c->vmax_k);
   // re-arm the control block for the next invocation
   c->umin_k = ~0ull; c->vmin_k = ~0ull; c->umax_k = 0ull; c->vmax_k = 0ull;
-  c->blocks_done = 0; c->scan_counter[0] = 0; c->scan_counter[1] = 0;
+  c->blocks_done = 0; c->scan_counter[0] = 0; c->scan_counter[1] = 0; c->scan_counter[2] = 0;
   double h = 1.0, u0 = 0.0, v0 = 0.0, E = 0.0;
   int ncu = 1, ncv = 1, clique = 0;
   if (ku0 <= ku1) {
@@ -215,9 +224,108 @@ __device__ __forceinline__ int db_cell1(double t, double o, double inv_h, int nc
   return (int)fmin(fmax(q, 0.0), (double)(nc - 1));
 }
 
+// A point outside the grid: NaN/inf coordinate (or eps < 0 / NaN): every getDisP(..) <= e is false, even against
+// itself (DBImproved.cs:41).  Zero neighbours: core only when 0 >= min_pts, and then a one-point cluster whose
+// isClassed stays false (the point is not in its own nei list).
+__device__ __forceinline__ void db_settle_outside(const DbArgs& a, long long i) {
+  const bool key_pt = (0 >= a.min_pts);
+  const int gi = a.gidx ? __ldg(a.gidx + i) : (int)i;
+  if (a.cluster_id) a.compkey[i] = key_pt ? -2 - gi : -1;           // full pipeline: core flag folded into the key (see k_db_label)
+  else { a.is_key[i] = key_pt ? 1 : 0; a.compkey[i] = key_pt ? gi : -1; }
+  if (key_pt && !a.gidx) atomicOr(&a.headbits[i >> 5], 1u << (i & 31));
+}
+
+__device__ __forceinline__ int db_cell_key(const DbCtrl& c, double x, double y) {
+  const int cu = db_cell1(x + y, c.u0, c.inv_h, c.ncu);
+  const int cv = db_cell1(x - y, c.v0, c.inv_h, c.ncv);
+  return cv * c.ncu + cu;
+}
+
+// ---- banded mode, pass 1: 256 bands of consecutive cell keys; per-tile band histogram (digit-major like sort.cuh) ----
+constexpr int kBandTile = 4096;
+constexpr int kBands = 256;
+__device__ __forceinline__ int db_band_of(const DbCtrl& c, int key) { return (int)(((long long)key * kBands) / c.ncells); }
+
+__global__ void __launch_bounds__(kDbBlock) k_db_band_hist(DbArgs a) {
+  __shared__ int s_cnt[kBands];
+  s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const DbCtrl c = *a.ctrl;
+  const bool eps_ok = a.eps >= 0.0;
+  const long long base = (long long)blockIdx.x * kBandTile;
+  constexpr int kBatch = 4;
+  for (int r0 = 0; r0 < kBandTile / kDbBlock; r0 += kBatch) {
+    double x[kBatch], y[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const long long i = base + (long long)(r0 + k) * kDbBlock + threadIdx.x;
+      x[k] = (i < a.n) ? __ldg(a.x + i) : __longlong_as_double(0x7ff8000000000000ll);
+      y[k] = (i < a.n) ? __ldg(a.y + i) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k)
+      if (db_valid(x[k], y[k], eps_ok)) atomicAdd(&s_cnt[db_band_of(c, db_cell_key(c, x[k], y[k]))], 1);
+  }
+  __syncthreads();
+  a.band_hist[(long long)threadIdx.x * a.band_tiles + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// pass 2: points move to band order as staging records {x, y, original index, cell key} -- one full 32-byte sector
+// per point; points outside the grid are settled here.  Ranking inside a tile as in k_rs_scatter (per-warp match groups
+// + running per-band slots).  (A variant ranking with shared-memory atomics and a separate key array was slower: the
+// extra 8-byte scattered stores cost more than the barriers saved.)
+__global__ void __launch_bounds__(kDbBlock) k_db_band_scatter(DbArgs a) {
+  __shared__ int s_run[kBands];
+  __shared__ int s_warp[kDbBlock / kWarp][kBands];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DbCtrl c = *a.ctrl;
+  const bool eps_ok = a.eps >= 0.0;
+  s_run[threadIdx.x] = a.band_hist[(long long)threadIdx.x * a.band_tiles + blockIdx.x];
+  const long long base = (long long)blockIdx.x * kBandTile;
+  for (int r = 0; r < kBandTile / kDbBlock; ++r) {
+    if (base + (long long)r * kDbBlock >= a.n) break;
+#pragma unroll
+    for (int w = 0; w < kDbBlock / kWarp; ++w) s_warp[w][threadIdx.x] = 0;
+    __syncthreads();
+    const long long i = base + r * kDbBlock + threadIdx.x;
+    double x = 0.0, y = 0.0;
+    int key = 0, band = kBands;                    // kBands = not in the grid / past the end
+    if (i < a.n) {
+      x = __ldg(a.x + i); y = __ldg(a.y + i);
+      if (db_valid(x, y, eps_ok)) { key = db_cell_key(c, x, y); band = db_band_of(c, key); }
+      else db_settle_outside(a, i);
+    }
+    const unsigned peers = __match_any_sync(kFull, band);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (band < kBands && rank_in_warp == 0) s_warp[warp][band] = __popc(peers);
+    __syncthreads();
+    {
+      int acc = s_run[threadIdx.x];
+#pragma unroll
+      for (int w = 0; w < kDbBlock / kWarp; ++w) { const int cnt = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = acc; acc += cnt; }
+      s_run[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (band < kBands) {
+      double2* t2 = reinterpret_cast<double2*>(a.tmp + s_warp[warp][band] + rank_in_warp);
+      t2[0] = make_double2(x, y);
+      reinterpret_cast<int4*>(t2)[1] = make_int4((int)i, key, 0, 0);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- k_db_hist: cell key + slot per point (occupancy histogram); settles points outside the grid ----
+// kBanded: thread t handles staging record t (the band partition already dropped the points outside the grid)
+template <bool kBanded>
 __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kBanded) {
+    if (i >= a.ctrl->n_banded) return;
+    const int key = a.tmp[i].parent;
+    a.keyslot[i] = make_int2(key, atomicAdd(&a.cell_count[key], 1));
+    return;
+  }
   if (i >= a.n) return;
   const DbCtrl c = *a.ctrl;
   const double x = __ldg(a.x + i), y = __ldg(a.y + i);
@@ -227,30 +335,29 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
     a.segof[i] = lo;
   }
   if (db_valid(x, y, a.eps >= 0.0)) {
-    const int cu = db_cell1(x + y, c.u0, c.inv_h, c.ncu);
-    const int cv = db_cell1(x - y, c.v0, c.inv_h, c.ncv);
-    const int key = cv * c.ncu + cu;
+    const int key = db_cell_key(c, x, y);
     a.keyslot[i] = make_int2(key, atomicAdd(&a.cell_count[key], 1));
   } else {
-    // NaN/inf coordinate (or eps < 0 / NaN): every getDisP(..) <= e is false, even against
-    // itself (DBImproved.cs:41).  Zero neighbours: core only when 0 >= min_pts, and then a
-    // one-point cluster whose isClassed stays false (the point is not in its own nei list).
     a.keyslot[i] = make_int2(-1, 0);
-    const bool key_pt = (0 >= a.min_pts);
-    const int gi = a.gidx ? __ldg(a.gidx + i) : (int)i;
-    if (a.cluster_id) a.compkey[i] = key_pt ? -2 - gi : -1;           // full pipeline: core flag folded into the key (see k_db_label)
-    else { a.is_key[i] = key_pt ? 1 : 0; a.compkey[i] = key_pt ? gi : -1; }
-    if (key_pt && !a.gidx) atomicOr(&a.headbits[i >> 5], 1u << (i & 31));
+    db_settle_outside(a, i);
   }
 }
 
 // ---- k_db_scatter: physical reorder by cell; classifies dense cells on the way ------------------
+template <bool kBanded>
 __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const int2 ks = a.keyslot[i];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (kBanded ? (long long)a.ctrl->n_banded : (long long)a.n)) return;
+  const int2 ks = a.keyslot[t];
   if (ks.x < 0) return;
-  const double x = __ldg(a.x + i), y = __ldg(a.y + i);
+  double x, y;
+  int i;
+  if (kBanded) {
+    const double2 xy = __ldg(reinterpret_cast<const double2*>(a.tmp + t));
+    x = xy.x; y = xy.y; i = a.tmp[t].sidx;
+  } else {
+    x = __ldg(a.x + t); y = __ldg(a.y + t); i = (int)t;
+  }
   const int s = __ldg(a.cell_start + ks.x), e = __ldg(a.cell_start + ks.x + 1);
   const int pos = s + ks.y;
   if (ks.y == 0) a.cell_count[ks.x] = 0;          // leave the histogram clean for the next call
@@ -260,7 +367,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
   a.core[pos] = dense ? 1 : 2;
   double2* r2 = reinterpret_cast<double2*>(a.rec + pos);   // two 128-bit stores = one full sector
   r2[0] = make_double2(x, y);
-  reinterpret_cast<int4*>(r2)[1] = make_int4((int)i, dense ? s : pos, (dense && pos == s) ? s : kNone, kNone);
+  reinterpret_cast<int4*>(r2)[1] = make_int4(i, dense ? s : pos, (dense && pos == s) ? s : kNone, kNone);
 }
 
 // exact reference predicate: Math.Abs(dx) + Math.Abs(dy) <= e   (DBImproved.cs:16-21, :41)
@@ -288,9 +395,10 @@ __device__ __forceinline__ DbStencil db_stencil(const DbCtrl& c, double2 p) {
 
 __device__ __forceinline__ double2 db_xy(const DbRec* __restrict__ rec, int j) { return __ldg(reinterpret_cast<const double2*>(rec + j)); }
 
-// number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight
+// number of candidates in [j0, j1) within eps of `me`, skipping [s, e); four loads in flight.  The positions of the
+// hits are appended to list[] (first kNbrCap of them; n_list keeps counting) for the border rule of k_db_resolve.
 __device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int j0, int j1, int s, int e, double2 me, double eps,
-                                              const int* __restrict__ sseg, int myseg) {
+                                              const int* __restrict__ sseg, int myseg, int self, int* __restrict__ list, int& n_list) {
   int cnt = 0;
   for (int j = j0; j < j1; j += 4) {
     double2 q[4];
@@ -299,7 +407,9 @@ __device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int jj = j + k;
-      cnt += (jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj] == myseg)) ? 1 : 0;
+      const bool hit = jj < j1 && !(jj >= s && jj < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj] == myseg);
+      cnt += hit ? 1 : 0;
+      if (hit && jj != self) { if (n_list < kNbrCap) list[n_list] = jj; ++n_list; }
     }
   }
   return cnt;
@@ -343,7 +453,13 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
   const int s = __ldg(a.cell_start + own), e = __ldg(a.cell_start + own + 1);
   const int myseg = a.seg_off ? a.sseg[p] : 0;
   int cnt = 0, es = 0, ee = 0;         // [es, ee): range excluded from the tests because it is already counted
-  if (c.clique) { cnt = e - s; es = s; ee = e; }   // every point of the own cell is a neighbour (self included)
+  int* list = a.nbr + (long long)p * kNbrCap;   // streamed out as found: one 32-byte sector per point
+  int n_list = 0;
+  if (c.clique) {                      // every point of the own cell is a neighbour (self included); the cell is not dense,
+    cnt = e - s; es = s; ee = e;       // so it holds fewer than min_pts points
+    for (int j = s; j < e; ++j)
+      if (j != p) { if (n_list < kNbrCap) list[n_list] = j; ++n_list; }
+  }
   for (int rb = st.vlo; rb <= st.vhi && cnt < need; rb += 4) {
     int j0[4], j1[4];
 #pragma unroll
@@ -355,10 +471,11 @@ __global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-      if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg);
+      if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg, p, list, n_list);
   }
   const bool core = cnt >= need;       // only 'count >= minPts' matters (:47)
-  a.core[p] = core ? 1 : 0;
+  // a non-core point has seen ALL its neighbours (no early exit): its list is complete unless it overflowed
+  a.core[p] = core ? 1 : (n_list <= kNbrCap ? 8 + n_list : 0);
   if (core && c.clique) atomicMin(&a.rec[s].cinfo.x, p);   // first core position of the cell, at the cell's first slot
 }
 
@@ -574,8 +691,11 @@ __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
     if (a.seg_amount && i == o0) a.seg_amount[sg] = db_rank_of(a, o1) - r0;
   }
   a.cluster_id[i] = (key < 0) ? 0 : base + 1 + db_rank_of(a, key);
-  // isClassed is set when a point is taken from a nei list (:65); a point outside the grid is in nobody's list
-  a.is_classed[i] = (key >= 0 && a.keyslot[i].x >= 0) ? 1 : 0;
+  // isClassed is set when a point is taken from a nei list (:65); a point outside the grid is in nobody's list -- such a
+  // point can only carry a key when min_pts <= 0 made it a one-point cluster
+  bool classed = key >= 0;
+  if (classed && a.min_pts <= 0) classed = db_valid(__ldg(a.x + i), __ldg(a.y + i), a.eps >= 0.0);
+  a.is_classed[i] = classed ? 1 : 0;
 }
 
 // ---- distributed mode (one slab per GPU, vtkcloudpoint_b200/distributed.py) ----------------------

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -64,6 +65,7 @@ struct vpc_ctx {
   DbArgs db_slab{};       // arguments of the last vpc_dbscan_slab_local_dev, for ..._finish_dev
   bool db_slab_valid = false;
   int64_t db_ws_n = -1;  // n the DBSCAN workspace is currently laid out and initialised for
+  bool db_ws_banded = false;
   // optional per-kernel CUDA-event timing (bench.py's roofline leg)
   bool profile = false;
   struct ProfRec { const char* name; cudaEvent_t a, b; };
@@ -123,6 +125,12 @@ int arena_reserve(vpc_ctx* ctx, Arena& a, size_t bytes) {
   return VPC_OK;
 }
 
+// Clouds of at least this many points take the band-partitioned counting sort (VPC_DB_BAND_MIN overrides, for tests)
+long long band_min_n() {
+  const char* e = std::getenv("VPC_DB_BAND_MIN");
+  return e ? std::atoll(e) : 24000000ll;
+}
+
 inline int blocks_for(long long n, int block) { return (int)std::max<long long>(1, (n + block - 1) / block); }
 
 // ---------------------------------------------------------------------------------------
@@ -140,7 +148,12 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   const int cell_cap = (int)cap_ll;
   const long long nwords = (n >> 5) + 1;   // cluster-head bitmap
   const int tiles0 = scan_tiles((long long)cell_cap + 1), tiles1 = scan_tiles(nwords);
-  size_t bytes = al256(sizeof(DbCtrl)) + al256(4ull * n) * (d_seg_off ? 3 : 1) + al256(8ull * n) + al256(32ull * n) + al256(4ull * kNbrCap * (size_t)n) + al256(4ull * nwords) * 2 +
+  // large clouds: band partition first, so that the cell histogram and the scatter stay inside an L2-sized window
+  const bool banded = !d_seg_off && n >= band_min_n();
+  const int band_tiles = banded ? (int)((n + kBandTile - 1) / kBandTile) : 0;
+  const int tiles2 = banded ? scan_tiles((long long)kBands * band_tiles) : 0;
+  size_t bytes = (banded ? al256(32ull * n) + al256(4ull * kBands * (size_t)band_tiles) + al256(8ull * tiles2) : 0) +
+                 al256(sizeof(DbCtrl)) + al256(4ull * n) * (d_seg_off ? 3 : 1) + al256(8ull * n) + al256(32ull * n) + al256(4ull * kNbrCap * (size_t)n) + al256(4ull * nwords) * 2 +
                  al256(4ull * (cell_cap + 1ull)) * 2 +
                  al256((size_t)n) + al256(8ull * tiles0) + al256(8ull * tiles1) + 4096;
   const char* base_before = ctx->db.base;
@@ -166,7 +179,13 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   if (d_seg_off) { a.segof = w.take<int>(n); a.sseg = w.take<int>(n); }
   a.tile_state0 = w.take<unsigned long long>(tiles0);
   a.tile_state1 = w.take<unsigned long long>(tiles1);
-  a.tiles0 = tiles0; a.tiles1 = tiles1;
+  a.tiles0 = tiles0; a.tiles1 = tiles1; a.tiles2 = tiles2;
+  a.banded = banded ? 1 : 0; a.band_tiles = band_tiles;
+  if (banded) {
+    a.tmp = w.take<DbRec>(n);
+    a.band_hist = w.take<int>((size_t)kBands * band_tiles);
+    a.tile_state2 = w.take<unsigned long long>(tiles2);
+  }
   a.cluster_id = d_cluster_id; a.is_key = d_is_key; a.is_classed = d_is_classed; a.cluster_amount = d_cluster_amount;
 
   const int gpts = blocks_for(n, kDbBlock);
@@ -174,16 +193,26 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   // The control block and the cell counters clean up after themselves (k_db_bounds / k_db_scatter); they
   // are initialised only when the workspace is new or its layout (n) changed.
   if (d_seg_off && d_seg_amount) VPC_CUDA(ctx, cudaMemsetAsync(d_seg_amount, 0, 4ull * n_seg, s));
-  if (base_before != ctx->db.base || ctx->db_ws_n != n) {
+  if (base_before != ctx->db.base || ctx->db_ws_n != n || ctx->db_ws_banded != banded) {
     ctx->db_ws_n = -1;
     VPC_LAUNCH(ctx, k_db_ws_init, std::min(blocks_for((long long)cell_cap + 1, kDbBlock), ctx->sm_count * 16), kDbBlock, s, a);
   }
   ctx->db_ws_n = -1;  // stays invalid if any launch below fails
   VPC_LAUNCH(ctx, k_db_bounds, gstride, kDbBlock, s, a);
-  VPC_LAUNCH(ctx, k_db_hist, gpts, kDbBlock, s, a);
+  if (banded) {
+    VPC_LAUNCH(ctx, k_db_band_hist, band_tiles, kDbBlock, s, a);
+    VPC_LAUNCH(ctx, k_scan_exclusive<false>, tiles2, kScanBlock, s, a.band_hist, a.band_hist, (const int*)nullptr, kBands * band_tiles,
+               a.tile_state2, &a.ctrl->scan_counter[2], &a.ctrl->n_banded);
+    VPC_LAUNCH(ctx, k_db_band_scatter, band_tiles, kDbBlock, s, a);
+    VPC_LAUNCH(ctx, k_db_hist<true>, gpts, kDbBlock, s, a);
+  } else {
+    VPC_LAUNCH(ctx, k_db_hist<false>, gpts, kDbBlock, s, a);
+  }
   VPC_LAUNCH(ctx, k_scan_exclusive<false>, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0,
              a.tile_state0, &a.ctrl->scan_counter[0], &a.ctrl->n_valid);
-  VPC_LAUNCH(ctx, k_db_scatter, gpts, kDbBlock, s, a);
+  if (banded) VPC_LAUNCH(ctx, k_db_scatter<true>, gpts, kDbBlock, s, a);
+  else VPC_LAUNCH(ctx, k_db_scatter<false>, gpts, kDbBlock, s, a);
+  ctx->db_ws_banded = banded;
   VPC_LAUNCH(ctx, k_db_count, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_union, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_flatten, gpts, kDbBlock, s, a);
