@@ -38,6 +38,16 @@ METRIC = "dbscan_mpts_per_s"
 UNIT = "Mpts/s"
 
 
+def load_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (tools/ncu_traffic.py), or None."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        k = json.loads(p.read_text())["kernels"][kernel]
+        return float(k["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -315,7 +325,8 @@ def run_ours(args):
         units_per_launch = n_loc
         achieved = DB_ALGO_BYTES_PER_PT * units_per_launch / (top_launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                    "traffic": None, "peak_source": peak_src, "kernel_ms": top_launch_ms, "kernel_share_of_step": per_step[top] / step_ms,
+                    "traffic": load_traffic(top) if world == 1 else None, "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, C2)",
+                    "algorithmic_bytes_per_launch": DB_ALGO_BYTES_PER_PT * units_per_launch, "peak_source": peak_src, "kernel_ms": top_launch_ms, "kernel_share_of_step": per_step[top] / step_ms,
                     "pipeline_frac": DB_ALGO_BYTES_PER_PT * n_all / (dev_ms / args.steps * 1e-3) / 1e9 / (peak_gbs * world)}
         kernels = {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}
 

@@ -39,6 +39,27 @@ namespace vtkPointCloud
         internal static extern int vpc_icp_rigid(IntPtr ctx, double[] modelXyz, long m, double[] dataXyz, long n, double e,
             int maxIters, [In, Out] double[] R, [In, Out] double[] T, out int itersDone, out double sseLast, [Out] int[] orderLast);
 
+        // MainForm.RecorrectMatchingPtsByDistance's search (FrmMain.cs:3588-3618)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_match_within(IntPtr ctx, double[] truthXyz, long m, double[] centersXyz, long n, double matchDistance,
+            [Out] int[] matchedId, [Out] double[] dist);
+
+        // Tools.GetClusList + Tools.getCircles(3-D) + getCircles(2-D): the statistics block of CompleteWork3 (FrmMain.cs:1521-1540)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_cluster_stats(IntPtr ctx, int[] clusterId, long n, int nClusters, double[] xyz, double[] mx, double[] my,
+            [Out] double[] means5, [Out] int[] counts, [Out] double[] circle3d, [Out] int[] status3d, [Out] double[] circle2d, [Out] int[] status2d);
+
+        // the LINQ query of MainForm.refreshClusList (FrmMain.cs:3446-3467)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_nearest_truth_2d(IntPtr ctx, double[] truthX, double[] truthY, int[] truthId, long m, double[] px, double[] py,
+            long n, double radius, [Out] int[] id);
+
+        // the import loop (FrmMain.cs:975-1068): text rows -> motor_x, motor_y, Distance -> gate -> XYZ -> duplicate removal
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_ingest_text(IntPtr ctx, byte[] text, long len, double xAngle, double yAngle, int xdir, int ydir, int removeDuplicates,
+            long rowCap, [Out] double[] mx, [Out] double[] my, [Out] double[] dist, [Out] double[] xyz, [Out] byte[] keep, [Out] byte[] rowStatus,
+            out long nRows, out long nKept, out long nDuplicates);
+
         internal static void Check(IntPtr ctx, int rc)
         {
             if (rc != 0)   // the reference signals errors with MException (Matrix.cs:710-715)
