@@ -44,7 +44,8 @@ def nvcc_path() -> str:
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB) + ".tmp", str(CSRC / "vpc_api.cu")]
+    extra = os.environ.get("VPC_NVCC_EXTRA", "").split()      # developer knob for A/B builds (e.g. -DVPC_ICP_ITER_BLOCK=128)
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(LIB) + ".tmp", str(CSRC / "vpc_api.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -569,9 +569,29 @@ __device__ __forceinline__ void icp_solve_round(const double* S, int n, double e
   if (!go_on || (max_iters > 0 && round >= max_iters)) st->done = 1;
 }
 
+// Sum of partial[b * kIcpSums + q] over b = slice, slice + kSlices, ... in that fixed order (deterministic), with eight
+// loads in flight: the plain loop serialises an L2 round trip per addend because the adds are in order.
+template <int kSlices>
+__device__ __forceinline__ double icp_partial_sum(const double* __restrict__ partial, int n_blocks, int slice, int q) {
+  double acc = 0.0;
+  int b = slice;
+  for (; b + 7 * kSlices < n_blocks; b += 8 * kSlices) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(partial + (long long)(b + k * kSlices) * kIcpSums + q);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
+  }
+  for (; b < n_blocks; b += kSlices) acc += __ldcg(partial + (long long)b * kIcpSums + q);
+  return acc;
+}
+
 // ---- one ICP round in ONE launch: transform + correspondences + block sums; the last block to finish
 // reduces the per-block partials in a fixed order (deterministic) and performs the rigid solve.
-constexpr int kIterBlock = 256;
+#ifndef VPC_ICP_ITER_BLOCK
+#define VPC_ICP_ITER_BLOCK 256
+#endif
+constexpr int kIterBlock = VPC_ICP_ITER_BLOCK;
 __global__ void __launch_bounds__(kIterBlock)
 k_icp_iter(IcpModel g, const double* __restrict__ data, int n, double e, int max_iters, IcpState* st,
            int* __restrict__ order, double* __restrict__ partial, unsigned* ticket) {
@@ -626,9 +646,7 @@ k_icp_iter(IcpModel g, const double* __restrict__ data, int n, double e, int max
   // ---- last block: partials -> S in a fixed order, then the solve ----
   constexpr int kSlices = kIterBlock / kIcpSums;
   const int q = threadIdx.x % kIcpSums, slice = threadIdx.x / kIcpSums;
-  double acc = 0.0;
-  for (int b = slice; b < (int)gridDim.x; b += kSlices) acc += __ldcg(partial + (long long)b * kIcpSums + q);
-  sm[q][slice] = acc;
+  sm[q][slice] = icp_partial_sum<kSlices>(partial, (int)gridDim.x, slice, q);
   __syncthreads();
   if (threadIdx.x < kIcpSums) {
     double v = 0.0;
@@ -726,9 +744,7 @@ k_icp_accumulate(IcpModel g, const double* __restrict__ data, int n, const IcpSt
   __threadfence();
   constexpr int kSlices = kIterBlock / kIcpSums;
   const int q = threadIdx.x % kIcpSums, slice = threadIdx.x / kIcpSums;
-  double acc = 0.0;
-  for (int b = slice; b < (int)gridDim.x; b += kSlices) acc += __ldcg(partial + (long long)b * kIcpSums + q);
-  sm[q][slice] = acc;
+  sm[q][slice] = icp_partial_sum<kSlices>(partial, (int)gridDim.x, slice, q);
   __syncthreads();
   if (threadIdx.x < kIcpSums) {
     double v = 0.0;
