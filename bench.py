@@ -227,21 +227,36 @@ def run_ours(args):
     out_dev = (torch.empty(n_loc, dtype=torch.int32, device=dev), torch.empty(n_loc, dtype=torch.uint8, device=dev),
                torch.empty(n_loc, dtype=torch.uint8, device=dev), torch.empty(1, dtype=torch.int32, device=dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    backend, plan = None, None
+    backend, plan, graph = None, None, None
     if world > 1:
-        from vtkcloudpoint_b200.distributed import GpuBackend, LeanSlabPlan, dbscan_slabs, dbscan_slabs_lean
+        from vtkcloudpoint_b200.distributed import GpuBackend, calibrated_lean_plan, dbscan_slabs, dbscan_slabs_lean
         backend = GpuBackend(ctx)
-        # pre-cut slabs: the sync-free path (fixed-capacity exchange buffers); the general path is the fallback
+        # pre-cut slabs: the sync-free path (fixed-capacity exchange buffers sized by one probe step at plan creation);
+        # the general path is the fallback
         try:
-            plan = LeanSlabPlan(ctx, n_loc, qs.tolist(), EPS, coord_bound, dev)
+            plan = calibrated_lean_plan(ctx, d_x, d_y, gidx0, qs.tolist(), EPS, coord_bound, MIN_PTS, dev)
         except ValueError:
             plan = None
+        # the whole step (kernels + glue + NCCL) as one CUDA graph; eager issue is the fallback
+        if plan is not None and not args.no_graph:
+            from vtkcloudpoint_b200.distributed import LeanSlabGraph
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                graph = LeanSlabGraph(plan, d_x, d_y, gidx0, MIN_PTS, 0)
+            except Exception as exc:  # noqa: BLE001
+                print(f"rank {rank}: CUDA-graph capture of the slab step failed ({type(exc).__name__}: {exc}); issuing eagerly", file=sys.stderr, flush=True)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                graph = None
 
-    def step_dev():
+    def step_dev(eager: bool = False):
         if world == 1:
             ctx.dbscan_dev(d_x, d_y, EPS, MIN_PTS, 0, out=out_dev)
         else:
-            if plan is not None:
+            if graph is not None and not eager:
+                graph.replay()
+            elif plan is not None:
                 dbscan_slabs_lean(plan, d_x, d_y, gidx0, MIN_PTS, 0)
             else:
                 dbscan_slabs(backend, d_x, d_y, gidx0, EPS, MIN_PTS, 0, splitters=splitters)
@@ -268,6 +283,8 @@ def run_ours(args):
     if plan is not None and int(plan.overflow.item()) != 0:
         raise SystemExit("slab exchange buffer overflow: enlarge LeanSlabPlan *_frac")
     launches = ctx.launch_count - launches0
+    if graph is not None:
+        launches += graph.launches * args.steps          # replayed launches do not pass through the library's counter
     dev_ms = max_over_ranks(dev_ms)
     value = n_all * args.steps / (dev_ms * 1e-3) / 1e6
 
@@ -283,10 +300,14 @@ def run_ours(args):
         if world == 1:
             ctx.dbscan(hx_np, hy_np, EPS, MIN_PTS, 0, out=res)
         else:
-            tx, ty = h_x.to(dev, non_blocking=True), h_y.to(dev, non_blocking=True)
-            if plan is not None:
+            if graph is not None:
+                d_x.copy_(h_x, non_blocking=True); d_y.copy_(h_y, non_blocking=True)      # the graph's static input buffers
+                cid, key, cls, _, _ = graph.replay()
+            elif plan is not None:
+                tx, ty = h_x.to(dev, non_blocking=True), h_y.to(dev, non_blocking=True)
                 cid, key, cls, _, _ = dbscan_slabs_lean(plan, tx, ty, gidx0, MIN_PTS, 0)
             else:
+                tx, ty = h_x.to(dev, non_blocking=True), h_y.to(dev, non_blocking=True)
                 cid, key, cls, _ = dbscan_slabs(backend, tx, ty, gidx0, EPS, MIN_PTS, 0, splitters=splitters)
             r_cid.copy_(cid, non_blocking=True); r_key.copy_(key, non_blocking=True); r_cls.copy_(cls, non_blocking=True)
             torch.cuda.synchronize()
@@ -309,7 +330,7 @@ def run_ours(args):
         ctx.profile(True)
     for _ in range(max(3, min(args.steps, 10))):     # every rank takes part (the multi-GPU step has collectives)
         flush.zero_()
-        step_dev()
+        step_dev(eager=True)                         # per-kernel events need the library's own launches, not a graph replay
     torch.cuda.synchronize()
     if rank == 0:
         rep = ctx.profile_report()
@@ -407,7 +428,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": (WORKLOAD_C2 if world == 1 else
                                     f"C2 recipe scaled to {n_all} points (1M per GPU), one cloud clustered exactly across {world} GPUs: u-slabs + 2*eps halo exchange + cross-slab union-find merge (NCCL)"),
-                       "points_total": n_all, "points_per_gpu": DB_N, "parallelism": f"{world} spatial slabs, one process per GPU" if world > 1 else "single GPU",
+                       "points_total": n_all, "points_per_gpu": DB_N, "parallelism": (f"{world} spatial slabs, one process per GPU, step replayed as one CUDA graph" if graph is not None else
+                                       f"{world} spatial slabs, one process per GPU") if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_all, "d2h_bytes_per_step": 6 * n_all + 4 * (world == 1),
@@ -420,10 +442,18 @@ def run_ours(args):
             "kernel_ms_per_step": kernels,
         }
         print(json.dumps(line), flush=True)
+    # teardown: release the captured graph (it holds NCCL work) before the communicator goes away, and never let a stuck
+    # teardown keep the job alive after the result line is out
+    import threading
+    threading.Timer(30.0, lambda: os._exit(0)).start() if world > 1 else None
+    graph = None
+    plan = None
+    torch.cuda.synchronize()
     barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
@@ -434,6 +464,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: issue the slab step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -40,5 +40,19 @@ if n <= 20_000_000:
           and np.array_equal(cls.cpu().numpy(), ocls[a:b]))
     print(f"rank {rank}: parity vs oracle on the whole cloud: {'OK' if ok else 'MISMATCH'} (clusters {amount} vs {oamount})", flush=True)
     assert ok
+else:
+    # full size (config C4): the oracle cannot finish this, so every rank clusters the WHOLE cloud on its own GPU with the
+    # single-GPU entry point and compares its chunk of the distributed result with it, bit for bit
+    del tx, ty
+    xs, ys = [], []
+    for s0 in range(0, n, 5_000_000):
+        fx, fy = synth.dbscan_cloud(0xC4, grid, n_total=n, start=s0, count=min(5_000_000, n - s0))
+        xs.append(torch.from_numpy(fx).to(dev)); ys.append(torch.from_numpy(fy).to(dev))
+    wx, wy = torch.cat(xs), torch.cat(ys)
+    del xs, ys
+    scid, skey, scls, samount = ctx.dbscan_dev(wx, wy, 0.07, 7, 0)
+    ok = (int(samount.item()) == amount and bool((scid[a:b] == cid).all()) and bool((skey[a:b] == key).all()) and bool((scls[a:b] == cls).all()))
+    print(f"rank {rank}: {world}-GPU result vs single-GPU clustering of the whole {n}-point cloud: {'OK' if ok else 'MISMATCH'} (clusters {amount} vs {int(samount.item())})", flush=True)
+    assert ok
 ctx.close()
 dist.destroy_process_group()

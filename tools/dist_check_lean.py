@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
 import oracle_py  # noqa: E402  (checker)
 from vtkcloudpoint_b200 import Context, synth  # noqa: E402
-from vtkcloudpoint_b200.distributed import LeanSlabPlan, dbscan_slabs_lean  # noqa: E402
+from vtkcloudpoint_b200.distributed import calibrated_lean_plan, dbscan_slabs_lean  # noqa: E402
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
@@ -31,7 +31,9 @@ fx, fy, band = fx[order], fy[order], band[order]
 a, b = int(np.searchsorted(band, rank, "left")), int(np.searchsorted(band, rank, "right"))
 ctx = Context(local)
 tx, ty = torch.from_numpy(fx[a:b].copy()).to(dev), torch.from_numpy(fy[a:b].copy()).to(dev)
-plan = LeanSlabPlan(ctx, b - a, list(qs), 0.07, float(np.abs(fu).max() + np.abs(fx - fy).max()), dev)
+plan = calibrated_lean_plan(ctx, tx, ty, a, list(qs), 0.07, float(np.abs(fu).max() + np.abs(fx - fy).max()), 7, dev)
+if rank == 0:
+    print(f"calibrated capacities: halo {plan.cap}, pairs {plan.cap_pairs}, heads {plan.cap_heads}", flush=True)
 for it in range(6):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
     cid, key, cls, amount, overflow = dbscan_slabs_lean(plan, tx, ty, a, 7, 0)

@@ -350,7 +350,7 @@ class LeanSlabPlan:
     INT_MAX = 2 ** 31 - 1
 
     def __init__(self, ctx, n: int, splitters, eps: float, coord_bound: float, device, group=None, halo_frac: float = 0.05,
-                 pair_frac: float = 0.03, head_frac: float = 0.04):
+                 pair_frac: float = 0.05, head_frac: float = 0.05, caps=None):
         self.ctx, self.group = ctx, group
         self.rank, self.world = _world(group)
         self.n, self.eps, self.dev = int(n), float(eps), device
@@ -363,9 +363,12 @@ class LeanSlabPlan:
         self.has_left, self.has_right = self.rank > 0, self.rank < self.world - 1
         self.s_lo = s[self.rank - 1] if self.has_left else -math.inf
         self.s_hi = s[self.rank] if self.has_right else math.inf
-        self.cap = max(1024, int(n * halo_frac))
-        self.cap_pairs = max(1024, int(n * pair_frac))
-        self.cap_heads = max(1024, int(n * head_frac))
+        if caps is not None:          # explicit capacities (identical on every rank), e.g. from LeanSlabPlan.calibrated
+            self.cap, self.cap_pairs, self.cap_heads = (max(1024, int(c)) for c in caps)
+        else:
+            self.cap = max(1024, int(n * halo_frac))
+            self.cap_pairs = max(1024, int(n * pair_frac))
+            self.cap_heads = max(1024, int(n * head_frac))
         f64, i32, u8 = torch.float64, torch.int32, torch.uint8
         z = lambda k, dt: torch.zeros(k, dtype=dt, device=device)  # noqa: E731
         self.bufL, self.bufR = z(1 + 3 * self.cap, f64), z(1 + 3 * self.cap, f64)
@@ -385,6 +388,27 @@ class LeanSlabPlan:
         self.n_nodes = self.world * self.cap_pairs
         self.root = z(self.n_nodes, i32)
         self.cid, self.is_key, self.is_classed = z(self.n, i32), z(self.n, u8), z(self.n, u8)
+
+
+def calibrated_lean_plan(ctx, x, y, gidx0: int, splitters, eps: float, coord_bound: float, min_pts: int, device, group=None,
+                         margin: float = 1.5) -> LeanSlabPlan:
+    """A LeanSlabPlan whose exchange capacities are MEASURED: one probe step with generous buffers, the halo / pair / head
+    counts of all ranks are read back once (the only host synchronisation, at plan creation), and the plan that is returned
+    holds `margin` times the largest of them -- the same on every rank, as the all_gathers need.  How many points sit within
+    2*eps of a slab boundary depends on how the clusters line up with it, so a fixed fraction of n is either wasteful or, as
+    with 8 slabs of the C2 recipe, too small; the overflow flag still guards every later step."""
+    n = x.numel()
+    probe = LeanSlabPlan(ctx, n, splitters, eps, coord_bound, device, group, halo_frac=0.25, pair_frac=0.5, head_frac=0.5)
+    _, _, _, _, overflow = dbscan_slabs_lean(probe, x, y, gidx0, min_pts)
+    need = torch.stack([probe.counters.max(), probe.pairs[0], probe.heads[0], overflow[0]]).to(torch.int64)
+    if probe.world > 1:
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=group)
+    halo, pairs, heads, ovf = (int(v) for v in need.tolist())
+    if ovf:
+        raise ValueError("the probe step overflowed even generous buffers: use dbscan_slabs (general path)")
+    del probe
+    caps = (int(halo * margin) + 1024, int(pairs * margin) + 1024, int(heads * margin) + 1024)
+    return LeanSlabPlan(ctx, n, splitters, eps, coord_bound, device, group, caps=caps)
 
 
 def dbscan_slabs_lean(plan: LeanSlabPlan, x, y, gidx0: int, min_pts: int, first_cluster_id: int = 0):
@@ -452,3 +476,29 @@ def dbscan_slabs_lean(plan: LeanSlabPlan, x, y, gidx0: int, min_pts: int, first_
         dist.all_reduce(p.overflow, op=dist.ReduceOp.MAX, group=p.group)
     return p.cid, p.is_key, p.is_classed, amount, p.overflow
 
+
+
+class LeanSlabGraph:
+    """dbscan_slabs_lean captured ONCE into a CUDA graph (its kernels, the torch glue ops and the NCCL exchanges) and replayed
+    per step: the step has ~55 small operations, so issued one by one from Python it is bound by the host's launch rate, not by
+    the GPUs.  x, y are static device buffers (copy new coordinates into them before replay()); every rank must construct and
+    replay the graph in lockstep.  The outputs are the plan's tensors, as with dbscan_slabs_lean."""
+
+    def __init__(self, plan: LeanSlabPlan, x, y, gidx0: int, min_pts: int, first_cluster_id: int = 0, warmup: int = 3):
+        self.plan, self.x, self.y = plan, x, y
+        side = torch.cuda.Stream(device=plan.dev)
+        side.wait_stream(torch.cuda.current_stream(plan.dev))
+        with torch.cuda.stream(side):                       # workspaces reach their final size before the capture
+            for _ in range(warmup):
+                dbscan_slabs_lean(plan, x, y, gidx0, min_pts, first_cluster_id)
+        torch.cuda.current_stream(plan.dev).wait_stream(side)
+        torch.cuda.synchronize(plan.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before = plan.ctx.launch_count
+        with torch.cuda.graph(self.graph):
+            self.out = dbscan_slabs_lean(plan, x, y, gidx0, min_pts, first_cluster_id)
+        self.launches = plan.ctx.launch_count - before      # libvpc kernels per replay
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
