@@ -502,3 +502,27 @@ class LeanSlabGraph:
     def replay(self):
         self.graph.replay()
         return self.out
+
+
+class IcpShardedGraph:
+    """icp_rigid_sharded (model cell-list build + max_iters rounds with their collectives) captured once into a CUDA graph.
+    model_shard and data are static device buffers; replay() returns (state, order) like icp_rigid_sharded."""
+
+    def __init__(self, backend, model_shard, idx_offset: int, data, e: float, max_iters: int, group=None, warmup: int = 2):
+        dev = data.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                icp_rigid_sharded(backend, model_shard, idx_offset, data, e, max_iters, group=group)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before = backend.ctx.launch_count
+        with torch.cuda.graph(self.graph):
+            self.out = icp_rigid_sharded(backend, model_shard, idx_offset, data, e, max_iters, group=group)
+        self.launches = backend.ctx.launch_count - before
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
