@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def test_blocked_flow_gpu_equals_oracle(ctx, pts_in_cell):
     mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000, decimals=3)
     xyz = np.stack([mx * 2.0, my * 3.0, mx - my], axis=1)
-    got = blocked.cluster_blocked(mx, my, 0.07, 7, pts_in_cell, ctx.dbscan, ctx.dbscan_cells, points_xyz=xyz)
+    got = blocked.cluster_blocked(mx, my, 0.07, 7, pts_in_cell, ctx.dbscan, ctx.dbscan_cells, points_xyz=xyz, argsort=ctx.argsort_f64)
     exp = blocked.cluster_blocked(mx, my, 0.07, 7, pts_in_cell, oracle_dbscan, oracle_dbscan_cells, points_xyz=xyz)
     assert got.cluster_amount == exp.cluster_amount and got.del_sum == exp.del_sum and got.cluster_sum_cells == exp.cluster_sum_cells
     np.testing.assert_array_equal(got.cluster_id, exp.cluster_id)

@@ -213,3 +213,40 @@ def test_ingest_text(ctx, oracle):
     assert len(empty["mx"]) == 0
     hdr = ctx.ingest_text(b"motor_x\tmotor_y\tDistance\n", 149.0, 307.0)
     assert len(hdr["mx"]) == 0
+
+
+def test_circles_large_clusters(ctx, oracle):
+    # clusters of thousands of points with hulls of 100+ vertices (points on and inside circles / ellipses): the pair and
+    # triple loops stride past one warp, the gift wrap runs for hundreds of rounds
+    rng = np.random.default_rng(19)
+    xs, ys, cs = [], [], []
+    for c, (m, ring) in enumerate(((3000, 150), (800, 40), (5000, 0), (64, 64), (33, 33)), start=1):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, ring))
+        rx, ry = 3.0 * np.cos(ang) + 20 * c, 2.0 * np.sin(ang) - 7 * c
+        r = np.sqrt(rng.uniform(0, 0.97, m - ring))
+        th = rng.uniform(0, 2 * np.pi, m - ring)
+        xs.append(np.concatenate([rx, 3.0 * r * np.cos(th) + 20 * c])); ys.append(np.concatenate([ry, 2.0 * r * np.sin(th) - 7 * c]))
+        cs.append(np.full(m, c, np.int32))
+    x, y, cid = np.concatenate(xs), np.concatenate(ys), np.concatenate(cs)
+    perm = rng.permutation(len(x))
+    x, y, cid = x[perm], y[perm], cid[perm]
+    xyz = np.stack([x, y, np.zeros_like(x)])
+    got = ctx.cluster_stats(cid, 5, xyz, y, x)
+    want = oracle.cluster_stats(cid, 5, xyz, y, x)
+    _eq(got["status3d"], want["status3d"]); _eq(got["status2d"], want["status2d"])
+    _eq(got["circle3d"][:, 1:].view(np.int64), want["circle3d"][:, 1:].view(np.int64))
+    _eq(got["circle2d"][:, 1:].view(np.int64), want["circle2d"][:, 1:].view(np.int64))
+    _eq(got["means"][:, 1:].view(np.int64), want["means"][:, 1:].view(np.int64))
+
+
+def test_nearest_truth_more_truths_than_points(ctx, oracle):
+    rng = np.random.default_rng(20)
+    tx, ty = rng.uniform(0, 50, 40_000), rng.uniform(0, 50, 40_000)
+    tid = rng.integers(0, 5000, 40_000).astype(np.int32)
+    px, py = rng.uniform(-5, 55, 3000), rng.uniform(-5, 55, 3000)
+    for radius in (0.05, 0.3, 100.0):
+        _eq(ctx.nearest_truth_2d(tx, ty, tid, px, py, radius), oracle.nearest_truth_2d(tx, ty, tid, px, py, radius))
+    # a single truth, and truths that are all non-finite
+    _eq(ctx.nearest_truth_2d([1.0], [2.0], [9], px, py, 60.0), oracle.nearest_truth_2d([1.0], [2.0], [9], px, py, 60.0))
+    nan = np.full(5, np.nan)
+    _eq(ctx.nearest_truth_2d(nan, nan, None, px, py, 60.0), np.zeros(len(px), np.int32))

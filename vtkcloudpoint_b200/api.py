@@ -285,6 +285,13 @@ class Context:
         return {"mx": mx[:r], "my": my[:r], "dist": ds[:r], "xyz": xyz[:3 * r].reshape(3, r), "keep": keep[:r], "row_status": st[:r],
                 "n_kept": int(n_kept.value), "n_duplicates": int(n_dup.value)}
 
+    def argsort_f64(self, vals) -> np.ndarray:
+        """Stable ascending permutation of a host array of doubles on the device (vpc_argsort_f64_dev): the sort of
+        MainForm.getClusterFromMotor (FrmMain.cs:1229-1233)."""
+        import torch
+        v = torch.from_numpy(np.ascontiguousarray(vals, np.float64)).to(f"cuda:{self.device}")
+        return self.argsort_f64_dev(v).cpu().numpy()
+
     # device-tensor forms ---------------------------------------------------------------------------------------------
     def _stream(self, t):
         import torch

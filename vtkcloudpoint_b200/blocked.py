@@ -32,14 +32,15 @@ class CellPartition:
     dropped: np.ndarray        # indices that fall into no cell (strict lower bounds / ties at the cell-0 cut)
 
 
-def partition_cells(mx: np.ndarray, my: np.ndarray, pts_in_cell: int) -> CellPartition:
-    """MainForm.getClusterFromMotor, FrmMain.cs:1224-1285."""
+def partition_cells(mx: np.ndarray, my: np.ndarray, pts_in_cell: int, argsort=None) -> CellPartition:
+    """MainForm.getClusterFromMotor, FrmMain.cs:1224-1285.  argsort(key) -> stable ascending permutation; the product passes
+    Context.argsort_f64 (the device radix sort, vpc_argsort_f64_dev), the default is NumPy's stable sort."""
     n = len(mx)
     if n == 0:
         raise ValueError("empty cloud (the C# returns early, FrmMain.cs:1228)")
     x_min, y_min, x_max, y_max = mx.min(), my.min(), mx.max(), my.max()                 # :1224-1227
     key = np.maximum(mx - x_min, my - y_min)                                            # :1232-1233
-    srt = np.argsort(key, kind="stable")                                                # :1229 (List.Sort: ties pinned to index order)
+    srt = np.asarray(argsort(key), np.int64) if argsort is not None else np.argsort(key, kind="stable")   # :1229 (List.Sort: ties pinned to index order)
     cell0 = srt[:pts_in_cell]                                                           # :1253
     cell_x = mx[cell0].max() - x_min                                                    # :1255
     cell_y = my[cell0].max() - y_min                                                    # :1256
@@ -150,13 +151,13 @@ def centroids(points_xyz, mx, my, cid_of_point, order_idx, cluster_amount):
     return (np.asarray(centers) if points_xyz is not None else None), np.asarray(centers2d).reshape(-1, 2), np.asarray(center_ids, np.int64)
 
 
-def cluster_blocked(mx, my, eps: float, min_pts: int, pts_in_cell: int, dbscan, dbscan_cells, points_xyz=None) -> BlockedResult:
+def cluster_blocked(mx, my, eps: float, min_pts: int, pts_in_cell: int, dbscan, dbscan_cells, points_xyz=None, argsort=None) -> BlockedResult:
     """The whole Clustering.DoClusteringBtn_Click path (Clustering.cs:78-98 -> FrmMain.cs:1214 -> 1340 -> 1432).
     dbscan(mx, my, eps, min_pts, first_cluster_id) -> object with .cluster_id, .cluster_amount;
     dbscan_cells(mx, my, offsets, eps, min_pts) -> (object with .cluster_id (cell-local), per_cell_amount)."""
     mx = np.ascontiguousarray(mx, np.float64)
     my = np.ascontiguousarray(my, np.float64)
-    part = partition_cells(mx, my, pts_in_cell)
+    part = partition_cells(mx, my, pts_in_cell, argsort)
     res, per_cell = dbscan_cells(mx[part.order], my[part.order], part.offsets, eps, min_pts)   # every StartCode work item
     cid_sorted, amount, merge, del_sum, cluster_sum = complete_work3(part, res.cluster_id, per_cell, mx, my, eps, min_pts, dbscan)
     cluster_id = np.zeros(len(mx), np.int32)
