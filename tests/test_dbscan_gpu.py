@@ -228,3 +228,23 @@ def test_banded_equals_direct_at_c2(ctx, oracle, banded_mode):
     np.testing.assert_array_equal(banded.cluster_id, direct.cluster_id)
     np.testing.assert_array_equal(banded.is_key, direct.is_key)
     np.testing.assert_array_equal(banded.is_classed, direct.is_classed)
+
+
+def test_big_adjacent_cells(ctx, oracle):
+    # cells holding hundreds of core points next to each other (many candidate pairs per cell pair): connected and
+    # unconnected variants, plus a one-pair bridge
+    rng = np.random.default_rng(31)
+    eps = 1.0
+    for gap, bridge in ((1.85, False), (1.85, True), (0.9, False), (1.02, False)):
+        a = rng.uniform(0, 0.08, (400, 2))
+        b = rng.uniform(0, 0.08, (400, 2)) + [gap, 0.0]
+        pts = [a, b, rng.uniform(-3, 5, (300, 2))]
+        if bridge:
+            pts.append(np.array([[0.08 + 0.9, 0.04]]))         # within eps of both blobs' near edges
+        pts = np.vstack(pts)
+        perm = rng.permutation(len(pts))
+        _check(ctx, oracle, pts[perm, 0].copy(), pts[perm, 1].copy(), eps, 5)
+    # lattice data with eps on the lattice: pairs at exactly eps across cell boundaries two cells apart
+    g = rng.integers(0, 40, (6000, 2)) * 0.5
+    _check(ctx, oracle, g[:, 0].copy(), g[:, 1].copy(), 1.0, 3)
+    _check(ctx, oracle, g[:, 0].copy(), g[:, 1].copy(), 0.5, 2)
