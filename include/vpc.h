@@ -154,6 +154,24 @@ int vpc_slab_ids_dev(vpc_ctx* ctx, const int32_t* d_gkey, const uint8_t* d_is_ke
                      const int32_t* d_heads_sorted, int64_t n_heads_cap, int32_t first_cluster_id, int32_t* d_cluster_id,
                      uint8_t* d_is_key, uint8_t* d_is_classed, void* stream);
 
+/* The same merge without sorting, for the sync-free slab step (vtkcloudpoint_b200/distributed.py, dbscan_slabs_lean):
+ *   vpc_slab_pairs_ws_dev            like vpc_slab_pairs_dev, but the core flag and local key of a boundary point are read from
+ *                                    the workspace vpc_dbscan_slab_local_dev kept (call that with d_local_key = NULL: no
+ *                                    per-point export pass); direct (non-banded) layout only
+ *   vpc_slab_merge_table_bytes       size of the scratch table for `world` gathered pair buffers of capacity cap_pairs
+ *   vpc_dbscan_slab_finish_merge_dev replaces sort + edge list + vpc_uf_edges_dev + vpc_dbscan_slab_finish_dev: the gathered pairs
+ *                                    int32[world][1 + 2*cap_pairs] go through two open-addressing tables (point -> first key
+ *                                    reported; key -> parent, hooked by key so that a merged set's root carries its minimum
+ *                                    key), local roots are re-keyed by table lookup, then the border rule runs */
+int vpc_slab_pairs_ws_dev(vpc_ctx* ctx, const double* d_lx, const double* d_ly, const int32_t* d_lg, int64_t n_local, int64_t n_own,
+                          double s_lo, double s_hi, double H, int32_t has_left, int32_t has_right, int32_t cap, int32_t* d_buf,
+                          int32_t* d_overflow, void* stream);
+int64_t vpc_slab_merge_table_bytes(int32_t world, int32_t cap_pairs);
+/* 1 when a DBSCAN call over n points takes the band-partitioned layout (where vpc_slab_pairs_ws_dev is not available) */
+int vpc_dbscan_takes_banded_path(int64_t n);
+int vpc_dbscan_slab_finish_merge_dev(vpc_ctx* ctx, const int32_t* d_pairs_all, int32_t world, int32_t cap_pairs, void* d_table,
+                                     int64_t table_bytes, int32_t* d_key_out, void* stream);
+
 /* ---- ICP ------------------------------------------------------------------------ */
 
 /* Point sets are PLANAR: xyz = x[0..k) y[0..k) z[0..k) (one H2D copy, coalesced). */

@@ -37,6 +37,64 @@ int main() {
   if (dbb.clusterAmount != amount || dbb.cf != amount || dbb.pointsAmount != n) { std::printf("FAIL amount %d vs %d\n", dbb.clusterAmount, amount); return 1; }
   for (int i = 0; i < n; ++i)
     if (pts[i].clusterId != cid[i] || pts[i].isClassed != (cls[i] != 0) || pts[i].isKeyPoint != (key[i] != 0)) { std::printf("FAIL point %d\n", i); return 1; }
+  // ---- blocked clustering (getClusterFromMotor -> DoWork3 -> CompleteWork3): the same host flow driven by libvpc and by the oracle
+  {
+    struct OracleEngine : MainForm::Engine {
+      int dbscan(const double* x, const double* y, int64_t k, double eps, int minPts, int cf, int32_t* id) override {
+        std::vector<uint8_t> a(k), b(k); int32_t amount = cf;
+        vpco_dbscan_l1_2d_literal(x, y, k, eps, minPts, cf, id, a.data(), b.data(), &amount, 0, nullptr);
+        return amount;
+      }
+      void dbscan_cells(const double* x, const double* y, int64_t, const int64_t* off, int n_cells, double eps, int minPts, int32_t* id, int32_t* per_cell) override {
+        for (int c2 = 0; c2 < n_cells; ++c2) {
+          const int64_t a0 = off[c2], k = off[c2 + 1] - a0;
+          std::vector<uint8_t> a(k), b(k); int32_t amount = 0;
+          if (k > 0) vpco_dbscan_l1_2d_literal(x + a0, y + a0, k, eps, minPts, 0, id + a0, a.data(), b.data(), &amount, 0, nullptr);
+          per_cell[c2] = amount;
+        }
+      }
+    } oracle_engine;
+    MainForm::VpcEngine vpc_engine(ctx);
+    for (int ptsInCell : {200, 650}) {
+      MainForm::BlockedResult g = MainForm::ClusterBlocked(vpc_engine, mx, my, 0.07, 7, ptsInCell);
+      MainForm::BlockedResult o = MainForm::ClusterBlocked(oracle_engine, mx, my, 0.07, 7, ptsInCell);
+      if (g.clusterSum != o.clusterSum || g.delSum != o.delSum || g.rows != o.rows || g.cols != o.cols || g.clusterId != o.clusterId) {
+        std::printf("FAIL blocked flow (ptsInCell %d): %d vs %d clusters\n", ptsInCell, g.clusterSum, o.clusterSum); return 1;
+      }
+    }
+  }
+  // ---- statistics block: Tools.ClusterStatistics vs the literal oracle, FilterClustersByRadius, NearestTruth
+  {
+    for (int i = 0; i < n; ++i) { pts[i].X = 40.0 * pts[i].motor_x + urand(seed) * 0.01; pts[i].Y = 40.0 * pts[i].motor_y; pts[i].Z = urand(seed); pts[i].clusterId -= (pts[i].clusterId ? 17 : 0); }
+    const int k = dbb.clusterAmount - 17;
+    std::vector<Point3D> centers, centers2D; std::vector<Point2D> circles, circles2D;
+    Tools::ClusterStatistics(ctx, pts, k, centers, centers2D, circles, circles2D);
+    std::vector<int32_t> lab(n), counts(k + 1), s3(k + 1), s2(k + 1);
+    std::vector<double> xyz(3 * n), means(5 * (k + 1)), c3(3 * (k + 1)), c2(3 * (k + 1));
+    for (int i = 0; i < n; ++i) { lab[i] = pts[i].clusterId; xyz[i] = pts[i].X; xyz[n + i] = pts[i].Y; xyz[2 * n + i] = pts[i].Z; }
+    vpco_cluster_stats_literal(lab.data(), n, k, xyz.data(), mx.data(), my.data(), means.data(), counts.data(), c3.data(), s3.data(), c2.data(), s2.data());
+    size_t ci = 0, qi = 0;
+    for (int c2i = 1; c2i <= k; ++c2i) {
+      if (counts[c2i] > 0) {
+        if (ci >= centers.size() || centers[ci].X != means[c2i] || centers[ci].Y != means[(k + 1) + c2i] || centers2D[ci].X != means[3 * (k + 1) + c2i]) { std::printf("FAIL centre %d\n", c2i); return 1; }
+        ++ci;
+      }
+      if (s3[c2i] == 1) {
+        if (qi >= circles.size() || circles[qi].clusID != c2i || circles[qi].radius != c3[2 * (k + 1) + c2i] || circles[qi].x != c3[c2i]) { std::printf("FAIL circle %d\n", c2i); return 1; }
+        ++qi;
+      }
+    }
+    if (ci != centers.size() || qi != circles.size()) { std::printf("FAIL statistics sizes\n"); return 1; }
+    std::vector<int> filterID = MainForm::FilterClustersByRadius(circles, (int)circles.size(), 1.3);
+    std::vector<Point3D> trues(centers2D.size());
+    for (size_t t = 0; t < trues.size(); ++t) { trues[t].tmp_X = centers2D[t].X; trues[t].tmp_Y = centers2D[t].Y; trues[t].clusterId = centers2D[t].clusterId; }
+    std::vector<int32_t> near_id = MainForm::NearestTruth(ctx, trues, pts, 0.05), want(n);
+    std::vector<double> tx(trues.size()), ty(trues.size()); std::vector<int32_t> tid(trues.size());
+    for (size_t t = 0; t < trues.size(); ++t) { tx[t] = trues[t].tmp_X; ty[t] = trues[t].tmp_Y; tid[t] = trues[t].clusterId; }
+    vpco_nearest_truth_2d_literal(tx.data(), ty.data(), tid.data(), (int64_t)trues.size(), mx.data(), my.data(), n, 0.05, want.data());
+    if (near_id != want) { std::printf("FAIL nearest truth\n"); return 1; }
+    std::printf("statistics ok: %zu centres, %zu circles, %zu filtered\n", centers.size(), circles.size(), filterID.size());
+  }
   // ---- ICP like the test menu handler: R = ZeroMatrix(3,3), T = ZeroMatrix(3,1), e = 1e-4
   const int m = 400, nd = 300;
   std::vector<Point3D> model(m), data(nd);

@@ -41,6 +41,10 @@ SIGNATURES = {
     "vpc_slab_pairs_dev": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _f64, _f64, _f64, _i32, _i32, _i32, _p, _p, _p]),
     "vpc_slab_heads_dev": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _p]),
     "vpc_slab_ids_dev": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _i32, _p, _p, _p, _p]),
+    "vpc_slab_pairs_ws_dev": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _f64, _f64, _f64, _i32, _i32, _i32, _p, _p, _p]),
+    "vpc_slab_merge_table_bytes": (_i64, [_i32, _i32]),
+    "vpc_dbscan_takes_banded_path": (C.c_int, [_i64]),
+    "vpc_dbscan_slab_finish_merge_dev": (C.c_int, [_p, _p, _i32, _i32, _p, _i64, _p, _p]),
     "vpc_closest_point_set": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p]),
     "vpc_icp_rigid": (C.c_int, [_p, _p, _i64, _p, _i64, _f64, _i32, _p, _p, _p, _p, _p]),
     "vpc_icp_set_model_dev": (C.c_int, [_p, _p, _i64, _p]),

@@ -82,6 +82,8 @@ struct DbArgs {
   int* seg_amount;      // [n_seg] out: clusters per segment (nullable)
   // distributed mode: component keys are minima of GLOBAL point indices (gidx[i] of local point i)
   const int* gidx;      // [n] device, nullptr = the local index
+  int slab_export;      // slab phase 1: 1 = write is_key / local keys for every point (general driver), 0 = the lean driver
+                        //               reads them from the workspace where it needs them (k_slab_pairs_ws)
   int* compkey;      // [n]  by ORIGINAL index: min original core index of the point's cluster, -1 = noise
   unsigned* headbits;   // [n/32 + 1] bit i set <=> original point i is the minimum core index of its cluster
   int* rank;         // [n/32 + 1] exclusive scan of popc(headbits)
@@ -818,6 +820,98 @@ k_slab_heads(const int* __restrict__ lg, const unsigned char* __restrict__ is_ke
   const bool want = (i < n_own) && is_key[i] && gkey[i] == lg[i];
   const int s = db_append_slot(want, buf);
   if (s >= 0) { if (s < cap) buf[1 + s] = lg[i]; else *overflow = 1; }
+}
+
+// ---- cross-slab merge without sorting: two open-addressing tables (EMPTY = -1; keys and global indices are >= 0) ------------
+// The gathered (global index G, local component key K) pairs name the same point twice when two ranks hold it (owner + halo
+// copy): their two keys are one cluster.  Table G remembers the key slot first reported for a point; the second report unites
+// the two key slots.  Table K holds the distinct keys with a parent slot each (-1 = root, so the memset is the initialisation);
+// roots are hooked by KEY (larger key under smaller), so the root of a merged set carries its minimum key.
+struct MergeTables {
+  int* g_key;   // [slots] global point index
+  int* g_val;   // [slots] key slot first reported for that point
+  int* k_key;   // [slots] component key
+  int* k_par;   // [slots] parent slot, -1 = root
+  unsigned mask;
+};
+__device__ __forceinline__ unsigned mg_hash(int v) { unsigned h = (unsigned)v * 0x9E3779B1u; return h ^ (h >> 15); }
+__device__ __forceinline__ int mg_insert(int* keys, unsigned mask, int key) {     // slot of key, inserted if absent
+  unsigned s = mg_hash(key) & mask;
+  for (;;) {
+    int cur = ld_relaxed_s32(keys + s);
+    if (cur == -1) { cur = atomicCAS(keys + s, -1, key); if (cur == -1) return (int)s; }
+    if (cur == key) return (int)s;
+    s = (s + 1) & mask;
+  }
+}
+__device__ __forceinline__ int mg_lookup(const int* keys, unsigned mask, int key) {   // slot of key or -1
+  unsigned s = mg_hash(key) & mask;
+  for (;;) {
+    const int cur = __ldg(keys + s);
+    if (cur == key) return (int)s;
+    if (cur == -1) return -1;
+    s = (s + 1) & mask;
+  }
+}
+__device__ __forceinline__ int mg_find(int* par, int x) {
+  for (;;) {
+    const int p = ld_relaxed_s32(par + x);
+    if (p < 0) return x;
+    const int gp = ld_relaxed_s32(par + p);
+    if (gp >= 0) st_relaxed_s32(par + x, gp);     // path halving
+    x = p;
+  }
+}
+__device__ __forceinline__ void mg_unite(const MergeTables& t, int a, int b) {
+  int ra = mg_find(t.k_par, a), rb = mg_find(t.k_par, b);
+  while (ra != rb) {
+    if (ld_relaxed_s32(t.k_key + ra) < ld_relaxed_s32(t.k_key + rb)) { const int x = ra; ra = rb; rb = x; }   // ra holds the larger key
+    if (atomicCAS(t.k_par + ra, -1, rb) == -1) return;
+    ra = mg_find(t.k_par, ra); rb = mg_find(t.k_par, rb);
+  }
+}
+// pairs_all: per rank int32[1 + 2 * cap] = {count, gidx[cap], key[cap]} (the all_gathered k_slab_pairs buffers)
+__global__ void __launch_bounds__(kDbBlock) k_slab_merge(const int* __restrict__ pairs_all, int world, int cap, MergeTables t) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (long long)world * cap) return;
+  const int r = (int)(j / cap), q = (int)(j % cap);
+  const int* buf = pairs_all + (long long)r * (1 + 2 * cap);
+  if (q >= min(__ldg(buf), cap)) return;
+  const int G = __ldg(buf + 1 + q), K = __ldg(buf + 1 + cap + q);
+  const int sk = mg_insert(t.k_key, t.mask, K);
+  const int sg = mg_insert(t.g_key, t.mask, G);
+  const int first = atomicCAS(t.g_val + sg, -1, sk);
+  if (first != -1 && first != sk) mg_unite(t, sk, first);
+}
+// every local root whose key appears in the table takes the minimum key of its merged set
+__global__ void __launch_bounds__(kDbBlock) k_db_remap_roots_table(DbArgs a, MergeTables t) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.ctrl->n_valid || a.core[p] != 1 || a.rec[p].parent != p) return;
+  const int s = mg_lookup(t.k_key, t.mask, a.rec[p].cinfo.y);
+  if (s >= 0) a.rec[p].cinfo.y = ld_relaxed_s32(t.k_key + mg_find(t.k_par, s));
+}
+
+// k_slab_pairs without the export pass: core flag and local component key of a boundary point are read from the kept
+// workspace (sorted position = cell_start[cell] + slot), only for the few points that need them
+__global__ void __launch_bounds__(kDbBlock)
+k_slab_pairs_ws(DbArgs a, const double* __restrict__ lx, const double* __restrict__ ly, const int* __restrict__ lg, int n_local, int n_own,
+                double s_lo, double s_hi, double H, int has_left, int has_right, int cap, int* buf, int* overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool want = false;
+  int key = -1;
+  if (i < n_local) {
+    bool cand = i >= n_own;                                          // a halo copy: its owner reports it too
+    if (!cand) { const double u = lx[i] + ly[i]; cand = (has_left && (u - H < s_lo)) || (has_right && (u + H >= s_hi)); }
+    if (cand) {
+      const int2 ks = a.keyslot[i];
+      if (ks.x >= 0) {
+        const int pos = __ldg(a.cell_start + ks.x) + ks.y;
+        if (a.core[pos] == 1) { want = true; key = a.rec[a.rec[pos].parent].cinfo.y; }
+      }
+    }
+  }
+  const int s = db_append_slot(want, buf);
+  if (s >= 0) { if (s < cap) { buf[1 + s] = lg[i]; buf[1 + cap + s] = key; } else *overflow = 1; }
 }
 
 // cluster id = first + 1 + rank of the key among all (sorted) cluster heads

@@ -139,7 +139,7 @@ inline int blocks_for(long long n, int block) { return (int)std::max<long long>(
 int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, double eps, int32_t min_pts,
                    int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
                    int32_t* d_cluster_amount, cudaStream_t s, const int32_t* d_seg_off = nullptr, int32_t n_seg = 0,
-                   int32_t* d_seg_amount = nullptr, const int32_t* d_gidx = nullptr, int32_t* d_local_keys = nullptr) {
+                   int32_t* d_seg_amount = nullptr, const int32_t* d_gidx = nullptr, int32_t* d_local_keys = nullptr, bool slab = false) {
   const int ni = (int)n;
   ctx->db_slab_valid = false;
   // (u, v) cells of side ~eps: about 4 x (bounding area / eps^2); 8 per point covers clustered clouds,
@@ -175,6 +175,7 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   a.rank = w.take<int>(nwords);
   a.seg_off = d_seg_off; a.n_seg = n_seg; a.seg_amount = d_seg_amount;
   a.gidx = d_gidx;
+  a.slab_export = d_local_keys ? 1 : 0;
   if (d_local_keys) a.compkey = d_local_keys;   // distributed mode: keys go straight to the caller's array
   if (d_seg_off) { a.segof = w.take<int>(n); a.sseg = w.take<int>(n); }
   a.tile_state0 = w.take<unsigned long long>(tiles0);
@@ -216,8 +217,8 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   VPC_LAUNCH(ctx, k_db_count, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_union, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_flatten, gpts, kDbBlock, s, a);
-  if (d_local_keys) {   // slab phase 1 ends here; vpc_dbscan_slab_finish_dev continues from the kept workspace
-    VPC_LAUNCH(ctx, k_db_export_core, gpts, kDbBlock, s, a);
+  if (slab) {   // slab phase 1 ends here; vpc_dbscan_slab_finish*_dev continues from the kept workspace
+    if (d_local_keys) VPC_LAUNCH(ctx, k_db_export_core, gpts, kDbBlock, s, a);
     ctx->db_slab = a;
     ctx->db_slab_valid = true;
     ctx->db_ws_n = n;
@@ -533,13 +534,14 @@ int vpc_dbscan_l1_2d_cells(vpc_ctx* ctx, const double* mx, const double* my, int
 
 int vpc_dbscan_slab_local_dev(vpc_ctx* ctx, const double* d_mx, const double* d_my, const int32_t* d_gidx, int64_t n, double eps,
                               int32_t min_pts, uint8_t* d_is_key, int32_t* d_local_key, void* stream) {
-  int rc = dbscan_check(ctx, d_mx, d_my, n, eps, d_local_key, d_is_key, d_is_key);
+  int rc = dbscan_check(ctx, d_mx, d_my, n, eps, d_is_key, d_is_key, d_is_key);   // d_local_key may be NULL: no export pass
   if (rc) return rc;
   if (n <= 0) return fail(ctx, VPC_E_BADARG, "a slab needs at least one point");
+  if (!d_gidx) return fail(ctx, VPC_E_BADARG, "d_gidx is required");
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   return dbscan_enqueue(ctx, d_mx, d_my, n, eps, min_pts, 0, nullptr, d_is_key, nullptr, nullptr, static_cast<cudaStream_t>(stream),
-                        nullptr, 0, nullptr, d_gidx, d_local_key);
+                        nullptr, 0, nullptr, d_gidx, d_local_key, true);
 }
 
 int vpc_dbscan_slab_finish_dev(vpc_ctx* ctx, const int32_t* d_map_from, const int32_t* d_map_to, int64_t n_map, int32_t* d_key_out,
@@ -1193,6 +1195,54 @@ int vpc_ingest_text(vpc_ctx* ctx, const char* text, int64_t len, double x_angle,
   VPC_CUDA(ctx, cudaStreamSynchronize(s));
   if (n_duplicates) *n_duplicates = ndup;
   if (n_kept) { long long k = 0; for (long long i = 0; i < rows; ++i) k += keep[i]; *n_kept = k; }
+  return VPC_OK;
+}
+
+// ---- lean slab step without sorts (see include/vpc.h) -------------------------------------------------------------------------
+int vpc_slab_pairs_ws_dev(vpc_ctx* ctx, const double* d_lx, const double* d_ly, const int32_t* d_lg, int64_t n_local, int64_t n_own, double s_lo,
+                          double s_hi, double H, int32_t has_left, int32_t has_right, int32_t cap, int32_t* d_buf, int32_t* d_overflow, void* stream) {
+  if (!ctx || n_local <= 0 || cap <= 0 || !d_lx || !d_ly || !d_lg || !d_buf || !d_overflow) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->db_slab_valid || ctx->db_slab.n != n_local) return fail(ctx, VPC_E_STATE, "vpc_dbscan_slab_local_dev on the same local cloud must be the previous DBSCAN call");
+  if (ctx->db_slab.banded) return fail(ctx, VPC_E_STATE, "the workspace lookup needs the direct (non-banded) layout: pass d_local_key to vpc_dbscan_slab_local_dev and use vpc_slab_pairs_dev");
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_slab_pairs_ws, blocks_for(n_local, kDbBlock), kDbBlock, static_cast<cudaStream_t>(stream), ctx->db_slab, d_lx, d_ly, d_lg, (int)n_local,
+             (int)n_own, s_lo, s_hi, H, has_left, has_right, cap, d_buf, d_overflow);
+  return VPC_OK;
+}
+
+int vpc_dbscan_takes_banded_path(int64_t n) { return n >= band_min_n() ? 1 : 0; }
+
+int64_t vpc_slab_merge_table_bytes(int32_t world, int32_t cap_pairs) {
+  if (world <= 0 || cap_pairs <= 0) return 0;
+  long long slots = 1024;
+  while (slots < 2ll * world * cap_pairs) slots <<= 1;
+  return 16 * slots;
+}
+
+int vpc_dbscan_slab_finish_merge_dev(vpc_ctx* ctx, const int32_t* d_pairs_all, int32_t world, int32_t cap_pairs, void* d_table, int64_t table_bytes,
+                                     int32_t* d_key_out, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (world <= 0 || cap_pairs <= 0 || !d_pairs_all || !d_table || !d_key_out) return fail(ctx, VPC_E_BADARG, "bad arguments");
+  if (table_bytes < vpc_slab_merge_table_bytes(world, cap_pairs)) return fail(ctx, VPC_E_BADARG, "table smaller than vpc_slab_merge_table_bytes");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->db_slab_valid) return fail(ctx, VPC_E_STATE, "vpc_dbscan_slab_local_dev must be the previous DBSCAN call on this context");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long slots = vpc_slab_merge_table_bytes(world, cap_pairs) / 16;
+  MergeTables t{};
+  t.g_key = static_cast<int*>(d_table); t.g_val = t.g_key + slots; t.k_key = t.g_val + slots; t.k_par = t.k_key + slots;
+  t.mask = (unsigned)(slots - 1);
+  VPC_CUDA(ctx, cudaMemsetAsync(d_table, 0xff, 16ull * slots, s));        // every field -1: empty keys, root parents
+  DbArgs a = ctx->db_slab;
+  a.compkey = d_key_out;
+  const int gpts = blocks_for(a.n, kDbBlock);
+  if (world > 1) {
+    VPC_LAUNCH(ctx, k_slab_merge, blocks_for((long long)world * cap_pairs, kDbBlock), kDbBlock, s, d_pairs_all, world, cap_pairs, t);
+    VPC_LAUNCH(ctx, k_db_remap_roots_table, gpts, kDbBlock, s, a, t);
+  }
+  VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
+  ctx->db_slab_valid = false;
   return VPC_OK;
 }
 

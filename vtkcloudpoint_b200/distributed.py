@@ -387,6 +387,10 @@ class LeanSlabPlan:
         self.heads_all = z(self.world * (1 + self.cap_heads), i32)
         self.n_nodes = self.world * self.cap_pairs
         self.root = z(self.n_nodes, i32)
+        # sort-free merge (hash tables in libvpc) unless the local cloud is large enough for the banded layout
+        self.table_merge = not bool(ctx._lib.vpc_dbscan_takes_banded_path(self.n_max))
+        self.table_bytes = int(ctx._lib.vpc_slab_merge_table_bytes(self.world, self.cap_pairs))
+        self.table = torch.empty(self.table_bytes if self.table_merge else 8, dtype=torch.uint8, device=device)
         self.cid, self.is_key, self.is_classed = z(self.n, i32), z(self.n, u8), z(self.n, u8)
 
 
@@ -409,6 +413,34 @@ def calibrated_lean_plan(ctx, x, y, gidx0: int, splitters, eps: float, coord_bou
     del probe
     caps = (int(halo * margin) + 1024, int(pairs * margin) + 1024, int(heads * margin) + 1024)
     return LeanSlabPlan(ctx, n, splitters, eps, coord_bound, device, group, caps=caps)
+
+
+def _lean_merge_sorted(p, lib, h, chk, st, min_pts):
+    """The sort-based variant of the merge (banded layout: the workspace lookup of vpc_slab_pairs_ws_dev is not available)."""
+    chk(lib.vpc_dbscan_slab_local_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.n_max, p.eps, int(min_pts),
+                                      p.is_key_l.data_ptr(), p.key_l.data_ptr(), st))
+    if p.world > 1:
+        p.pairs.copy_(p.pairs_tpl)
+        chk(lib.vpc_slab_pairs_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.is_key_l.data_ptr(), p.key_l.data_ptr(), p.n_max, p.n,
+                                   p.s_lo, p.s_hi, p.H, int(p.has_left), int(p.has_right), p.cap_pairs, p.pairs.data_ptr(),
+                                   p.overflow.data_ptr(), st))
+        dist.all_gather_into_tensor(p.pairs_all, p.pairs, group=p.group)
+        pa = p.pairs_all.view(p.world, 1 + 2 * p.cap_pairs)
+        G = pa[:, 1:1 + p.cap_pairs].reshape(-1)
+        K = pa[:, 1 + p.cap_pairs:].reshape(-1)
+        srt = torch.sort(G)                                     # equal global indices become adjacent
+        Gs, Ks = srt.values, K[srt.indices]
+        nodes = torch.sort(K).values                            # node id of a key = its first slot in the sorted keys
+        ia = torch.searchsorted(nodes, Ks[:-1].contiguous()).to(torch.int32)
+        ib = torch.searchsorted(nodes, Ks[1:].contiguous()).to(torch.int32)
+        ib = torch.where((Gs[1:] == Gs[:-1]) & (Gs[1:] != LeanSlabPlan.INT_MAX), ib, ia).contiguous()   # no edge -> self loop
+        chk(lib.vpc_uf_edges_dev(h, ia.data_ptr(), ib.data_ptr(), ia.numel(), p.n_nodes, p.root.data_ptr(), st))
+        map_from, map_to = nodes, nodes[p.root.long()].contiguous()
+        n_map = p.n_nodes
+    else:
+        map_from = map_to = p.root
+        n_map = 0
+    chk(lib.vpc_dbscan_slab_finish_dev(h, map_from.data_ptr(), map_to.data_ptr(), n_map, p.gkey.data_ptr(), st))
 
 
 def dbscan_slabs_lean(plan: LeanSlabPlan, x, y, gidx0: int, min_pts: int, first_cluster_id: int = 0):
@@ -436,30 +468,20 @@ def dbscan_slabs_lean(plan: LeanSlabPlan, x, y, gidx0: int, min_pts: int, first_
             r.wait()
     chk(lib.vpc_slab_assemble_dev(h, x.data_ptr(), y.data_ptr(), p.n, int(gidx0), p.recvL.data_ptr(), p.recvR.data_ptr(), p.cap,
                                   p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), st))
-    chk(lib.vpc_dbscan_slab_local_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.n_max, p.eps, int(min_pts),
-                                      p.is_key_l.data_ptr(), p.key_l.data_ptr(), st))
-    if p.world > 1:
-        p.pairs.copy_(p.pairs_tpl)
-        chk(lib.vpc_slab_pairs_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.is_key_l.data_ptr(), p.key_l.data_ptr(), p.n_max, p.n,
-                                   p.s_lo, p.s_hi, p.H, int(p.has_left), int(p.has_right), p.cap_pairs, p.pairs.data_ptr(),
-                                   p.overflow.data_ptr(), st))
-        dist.all_gather_into_tensor(p.pairs_all, p.pairs, group=p.group)
-        pa = p.pairs_all.view(p.world, 1 + 2 * p.cap_pairs)
-        G = pa[:, 1:1 + p.cap_pairs].reshape(-1)
-        K = pa[:, 1 + p.cap_pairs:].reshape(-1)
-        srt = torch.sort(G)                                     # equal global indices become adjacent
-        Gs, Ks = srt.values, K[srt.indices]
-        nodes = torch.sort(K).values                            # node id of a key = its first slot in the sorted keys
-        ia = torch.searchsorted(nodes, Ks[:-1].contiguous()).to(torch.int32)
-        ib = torch.searchsorted(nodes, Ks[1:].contiguous()).to(torch.int32)
-        ib = torch.where((Gs[1:] == Gs[:-1]) & (Gs[1:] != LeanSlabPlan.INT_MAX), ib, ia).contiguous()   # no edge -> self loop
-        chk(lib.vpc_uf_edges_dev(h, ia.data_ptr(), ib.data_ptr(), ia.numel(), p.n_nodes, p.root.data_ptr(), st))
-        map_from, map_to = nodes, nodes[p.root.long()].contiguous()
-        n_map = p.n_nodes
+    if p.table_merge:
+        # no per-point export, no sorts: boundary pairs are read from the kept workspace, the gathered pairs are merged through
+        # hash tables inside the library, local roots are re-keyed by lookup
+        chk(lib.vpc_dbscan_slab_local_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.n_max, p.eps, int(min_pts),
+                                          p.is_key_l.data_ptr(), None, st))
+        if p.world > 1:
+            p.pairs[0:1].zero_()
+            chk(lib.vpc_slab_pairs_ws_dev(h, p.lx.data_ptr(), p.ly.data_ptr(), p.lg.data_ptr(), p.n_max, p.n, p.s_lo, p.s_hi, p.H,
+                                          int(p.has_left), int(p.has_right), p.cap_pairs, p.pairs.data_ptr(), p.overflow.data_ptr(), st))
+            dist.all_gather_into_tensor(p.pairs_all, p.pairs, group=p.group)
+        chk(lib.vpc_dbscan_slab_finish_merge_dev(h, p.pairs_all.data_ptr(), p.world, p.cap_pairs, p.table.data_ptr(), p.table_bytes,
+                                                 p.gkey.data_ptr(), st))
     else:
-        map_from = map_to = p.root
-        n_map = 0
-    chk(lib.vpc_dbscan_slab_finish_dev(h, map_from.data_ptr(), map_to.data_ptr(), n_map, p.gkey.data_ptr(), st))
+        _lean_merge_sorted(p, lib, h, chk, st, min_pts)
     p.heads.copy_(p.heads_tpl)
     chk(lib.vpc_slab_heads_dev(h, p.lg.data_ptr(), p.is_key_l.data_ptr(), p.gkey.data_ptr(), p.n, p.cap_heads, p.heads.data_ptr(),
                                p.overflow.data_ptr(), st))
