@@ -147,6 +147,18 @@ def run_reference(args):
     oracle.icp_rigid(model, data, -1.0, 2, use_grid=True, n_threads=cores)
     icp_s = time.perf_counter() - t0
     sample = f"full cloud ({n_pts} pts), {len(times)} passes of the grid-accelerated C++ port of DBImproved.dbscan, {cores} threads for the region queries"
+    # what the reference ACTUALLY runs is Theta(n^2): the literal restatement on config C1 (10k points), with and without the
+    # no-op de-dup scan of DBImproved.cs:70-83, and one brute-force FindClosestPointSet pass of C3 (1e11 pair evaluations)
+    literal = None
+    if args.gpus <= 1 and not args.no_literal:
+        c1x, c1y = synth.dbscan_cloud(0xC1, 14, n_total=10_000, decimals=3)
+        t0 = time.perf_counter(); oracle.dbscan(c1x, c1y, EPS, MIN_PTS, 0, variant="literal"); t_lit = time.perf_counter() - t0
+        t0 = time.perf_counter(); oracle.dbscan(c1x, c1y, EPS, MIN_PTS, 0, variant="literal", dedup_loop=True); t_dd = time.perf_counter() - t0
+        t0 = time.perf_counter(); oracle.closest_point_set(model, data[:, :10_000], "literal", n_threads=cores); t_nn = time.perf_counter() - t0
+        literal = {"dbscan_c1_10k_mpts_per_s": 1e4 / t_lit / 1e6, "dbscan_c1_10k_with_dedup_scan_mpts_per_s": 1e4 / t_dd / 1e6,
+                   "icp_c3_bruteforce_nn_iters_per_s": 1.0 / (t_nn * ICP_N / 10_000),
+                   "note": "literal Theta(n^2) restatement, 1 thread for DBSCAN; brute-force NN timed on 10k of the 100k data points "
+                           f"({cores} threads) and scaled to one full round"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -158,6 +170,7 @@ def run_reference(args):
         "secondary": {"metric": "icp_iters_per_s", "value": 2 / icp_s, "unit": "iters/s",
                       "sample": "2 iterations of C3 (100k vs 1M) incl. one grid build, grid-accelerated C++ port, all cores"},
         "gpu_launches": 0,
+        "literal_reference": literal,
     }
     print(json.dumps(line), flush=True)
 
@@ -479,6 +492,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-literal", action="store_true", help="reference arm: skip the Theta(n^2) literal timings")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: issue the slab step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
