@@ -577,8 +577,10 @@ __global__ void __launch_bounds__(kDbBlock) k_db_flatten(DbArgs a) {
   const bool active = (p < n_valid) && a.core[p] == 1;
   int root = -1, orig = kNone;
   if (active) {
-    root = uf_find_ro(RecParent{a.rec}, p);
-    a.rec[p].parent = root;                // readers racing with this store still see an ancestor
+    const int par0 = ld_relaxed_s32(&a.rec[p].parent);
+    root = (par0 == p) ? p : uf_find_ro(RecParent{a.rec}, par0);
+    if (root != par0) a.rec[p].parent = root;   // most points already hang directly under their root (dense cells): no store, no
+                                                // dirty sector; readers racing with this store still see an ancestor
     orig = a.rec[p].sidx;
     if (a.gidx) orig = __ldg(a.gidx + orig);
   }
