@@ -149,9 +149,17 @@ __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
     const double2* x2 = reinterpret_cast<const double2*>(a.x);
     const double2* y2 = reinterpret_cast<const double2*>(a.y);
     const long long n2 = a.n >> 1;
-    for (long long i = tid; i < n2; i += nth) {
-      const double2 xv = __ldg(x2 + i), yv = __ldg(y2 + i);
-      take(xv.x, yv.x); take(xv.y, yv.y);
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (long long i = tid; i < n2; i += 4 * nth) {      // eight 128-bit loads in flight per thread (NaN = not there)
+      double2 xv[4], yv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool in = i + k * nth < n2;
+        xv[k] = in ? __ldg(x2 + i + k * nth) : make_double2(nan, nan);
+        yv[k] = in ? __ldg(y2 + i + k * nth) : make_double2(nan, nan);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { take(xv[k].x, yv[k].x); take(xv[k].y, yv[k].y); }
     }
     if (tid == 0 && (a.n & 1)) take(__ldg(a.x + a.n - 1), __ldg(a.y + a.n - 1));
   } else {

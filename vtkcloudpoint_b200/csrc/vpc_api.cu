@@ -190,7 +190,7 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   a.cluster_id = d_cluster_id; a.is_key = d_is_key; a.is_classed = d_is_classed; a.cluster_amount = d_cluster_amount;
 
   const int gpts = blocks_for(n, kDbBlock);
-  const int gstride = std::min(gpts, ctx->sm_count * 8);
+  const int gstride = std::min(gpts, ctx->sm_count * 2);   // k_db_bounds: two resident blocks per SM (88 registers), each thread keeps 8 loads in flight
   // The control block and the cell counters clean up after themselves (k_db_bounds / k_db_scatter); they
   // are initialised only when the workspace is new or its layout (n) changed.
   if (d_seg_off && d_seg_amount) VPC_CUDA(ctx, cudaMemsetAsync(d_seg_amount, 0, 4ull * n_seg, s));
