@@ -43,6 +43,33 @@ def icp_case(name, model, data, e, max_iters):
     print(name, model.shape[1], "x", data.shape[1], "->", it, "rounds, sse", sse)
 
 
+def stats_case(name, mx, my, dist, eps, min_pts, radius):
+    """C1-style statistics block: polar -> XYZ, DBSCAN labels, centroids, both circle sets, nearest-truth ids.  Cross-checks: the
+    centroids equal NumPy's sequential sums, every circle encloses its members and no smaller circle through two members does."""
+    xyz, keep = O.polar_to_xyz(mx, my, dist, 149.0, 307.0)
+    assert keep.all()
+    cid, key, cls, k = O.dbscan(mx, my, eps, min_pts, 0, variant="literal")
+    st = O.cluster_stats(cid, k, xyz, mx, my)
+    for c in range(1, k + 1):
+        m = np.flatnonzero(cid == c)
+        assert st["counts"][c] == len(m) and st["means"][0, c] == np.cumsum(xyz[0, m])[-1] / len(m)
+        if st["status3d"][c] == 1:
+            cx, cy, r = st["circle3d"][:, c]
+            d = np.hypot(xyz[0, m] - cx, xyz[1, m] - cy)
+            assert d.max() <= r * (1 + 1e-12)
+            pd = np.hypot(xyz[0, m][:, None] - xyz[0, m][None], xyz[1, m][:, None] - xyz[1, m][None])
+            assert r >= pd.max() / 2 * (1 - 1e-12)            # at least half the diameter
+    tid = np.arange(1, k + 1, dtype=np.int32)
+    near = O.nearest_truth_2d(st["means"][3, 1:], st["means"][4, 1:], tid, mx, my, radius)
+    d = np.sqrt((st["means"][3, 1:][None] - mx[:, None]) ** 2 + (st["means"][4, 1:][None] - my[:, None]) ** 2)
+    want = np.where(d.min(1) < radius, tid[d.shape[1] - 1 - np.argmin(d[:, ::-1], axis=1)], 0)   # ties -> highest index
+    assert np.array_equal(near, want)
+    np.savez_compressed(HERE / f"stats_{name}.npz", mx=mx, my=my, dist=dist, xyz=xyz, cluster_id=cid, n_clusters=k, radius=radius,
+                        means=st["means"], counts=st["counts"], circle3d=st["circle3d"], status3d=st["status3d"],
+                        circle2d=st["circle2d"], status2d=st["status2d"], nearest=near)
+    print(name, len(mx), "pts ->", k, "clusters,", int((st["status3d"] == 1).sum()), "circles")
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(20261018)
     mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000, decimals=3)            # config C1
@@ -52,6 +79,7 @@ if __name__ == "__main__":
     bx, by = rng.uniform(0, 1, 800), rng.uniform(0, 1, 800)
     bx[[5, 99]] = np.nan; by[300] = np.inf
     db_case("nonfinite", bx, by, 0.06, 3, 0)
+    stats_case("c1", mx, my, np.round(41.7 + 0.42 * synth.uniform(0xC1, 40, np.arange(len(mx), dtype=np.uint64)), 3), 0.07, 7, 0.088)
     g = np.arange(14, dtype=np.float64) * 0.5                                     # C1 ICP: centroids vs checkerboard truth
     truth = np.stack([np.repeat(g, 14), np.tile(g, 14), np.zeros(196)])
     Rz = synth.rotation_about_axis((0, 0, 1), np.radians(3.0))

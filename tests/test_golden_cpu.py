@@ -30,3 +30,16 @@ def test_oracle_icp_golden(oracle, name):
     np.testing.assert_array_equal(olast, g["order_last"])
     np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(T, g["T"], rtol=0, atol=1e-12)
+
+
+def test_oracle_stats_golden(oracle):
+    g = np.load(GOLD / "stats_c1.npz")
+    xyz, keep = oracle.polar_to_xyz(g["mx"], g["my"], g["dist"], 149.0, 307.0)
+    np.testing.assert_allclose(xyz, g["xyz"], rtol=1e-13, atol=1e-13)      # libm's sin/cos may differ in the last bit across hosts
+    st = oracle.cluster_stats(g["cluster_id"], int(g["n_clusters"]), g["xyz"], g["mx"], g["my"])
+    for k in ("means", "circle3d", "circle2d"):
+        np.testing.assert_array_equal(st[k][:, 1:].view(np.int64), g[k][:, 1:].view(np.int64))
+    for k in ("counts", "status3d", "status2d"):
+        np.testing.assert_array_equal(st[k], g[k])
+    tid = np.arange(1, int(g["n_clusters"]) + 1, dtype=np.int32)
+    np.testing.assert_array_equal(oracle.nearest_truth_2d(g["means"][3, 1:], g["means"][4, 1:], tid, g["mx"], g["my"], float(g["radius"])), g["nearest"])
