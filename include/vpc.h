@@ -228,6 +228,21 @@ int vpc_match_within_dev(vpc_ctx* ctx, const double* d_centers_xyz, int64_t n, d
 int vpc_cluster_means_dev(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, const double* d_vals,
                           int32_t n_fields, double* d_means, int32_t* d_counts, void* stream);
 
+/* ---- the blocked ("分块") multithreaded clustering as one call -----------------------------------
+ * Replaces MainForm.getClusterFromMotor (FrmMain.cs:1214-1291) -> DoWork3 / StartCode (:1340-1361, :2782-2794) ->
+ * CompleteWork3 (:1432-1520) up to the renumbered labels, reproducing the C#'s behaviour including its quirks: no halo
+ * between cells; strict lower / inclusive upper box bounds, so points with mx == xmin or my == ymin outside the first cell
+ * and points tied at the first cell's cut fall into no cell (*n_unassigned, labelled 0); cell-local ids renumbered with a
+ * running id; clusters whose counted length is <= 3 are zeroed, with the off-by-one of :1460-1499 and without a check of
+ * a cell's last cluster; all noise re-clustered globally with cf = clusterSum - delSum - 1 (:1507-1516).  List.Sort's
+ * undefined tie order is pinned to the input order.  The sort and both DBSCAN steps run on the GPU (all cells in ONE
+ * batched launch); the box assignment and the renumbering are the C#'s host logic.  cluster_id[n] by input order,
+ * *cluster_sum = MainForm.clusterSum (:1538); del_sum / rows / cols / n_unassigned are nullable extras.
+ * Returns VPC_E_STATE where the C# would throw (clusForMerge[-1], :1487). */
+int vpc_dbscan_blocked_ref(vpc_ctx* ctx, const double* mx, const double* my, int64_t n, double eps, int32_t min_pts,
+                           int32_t pts_in_cell, int32_t* cluster_id, int32_t* cluster_sum, int32_t* del_sum, int32_t* rows,
+                           int32_t* cols, int64_t* n_unassigned);
+
 /* ---- sorting (the reference's List.Sort / OrderBy steps around the path) -----------------------------------------
  * vpc_sort_pairs_dev: stable LSD radix sort of n (uint64 key, int32 value) pairs on key bits [begin_bit, end_bit), in
  *   place (device pointers).  vals_identity != 0: d_vals is output only and starts as 0..n-1, i.e. the call returns the

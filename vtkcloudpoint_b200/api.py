@@ -285,6 +285,21 @@ class Context:
         return {"mx": mx[:r], "my": my[:r], "dist": ds[:r], "xyz": xyz[:3 * r].reshape(3, r), "keep": keep[:r], "row_status": st[:r],
                 "n_kept": int(n_kept.value), "n_duplicates": int(n_dup.value)}
 
+    def dbscan_blocked_ref(self, mx, my, eps: float, min_pts: int, pts_in_cell: int):
+        """The reference's blocked clustering (getClusterFromMotor -> DoWork3 -> CompleteWork3) as one call.
+        Returns dict(cluster_id, cluster_sum, del_sum, rows, cols, n_unassigned)."""
+        mx = np.ascontiguousarray(mx, np.float64)
+        my = np.ascontiguousarray(my, np.float64)
+        n = len(mx)
+        cid = np.zeros(n, np.int32)
+        cs, ds, r, c = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        un = C.c_int64(0)
+        ref = lambda v: C.cast(C.byref(v), C.c_void_p)   # noqa: E731
+        self._check(self._lib.vpc_dbscan_blocked_ref(self._h, _ptr(mx), _ptr(my), n, float(eps), int(min_pts), int(pts_in_cell), _ptr(cid),
+                                                     ref(cs), ref(ds), ref(r), ref(c), ref(un)))
+        return {"cluster_id": cid, "cluster_sum": int(cs.value), "del_sum": int(ds.value), "rows": int(r.value), "cols": int(c.value),
+                "n_unassigned": int(un.value)}
+
     def argsort_f64(self, vals) -> np.ndarray:
         """Stable ascending permutation of a host array of doubles on the device (vpc_argsort_f64_dev): the sort of
         MainForm.getClusterFromMotor (FrmMain.cs:1229-1233)."""

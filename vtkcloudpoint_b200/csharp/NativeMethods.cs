@@ -29,6 +29,11 @@ namespace vtkPointCloud
         internal static extern int vpc_dbscan_l1_2d_cells(IntPtr ctx, double[] mx, double[] my, long n, long[] cellOffsets, int nCells,
             double eps, int minPts, [Out] int[] clusterId, [Out] byte[] isKey, [Out] byte[] isClassed, [Out] int[] clusterAmountPerCell);
 
+        // getClusterFromMotor -> DoWork3 -> CompleteWork3 up to the renumbered labels (FrmMain.cs:1214-1291, 1340-1361, 1432-1520), one call
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_dbscan_blocked_ref(IntPtr ctx, double[] mx, double[] my, long n, double eps, int minPts, int ptsInCell,
+            [Out] int[] clusterId, out int clusterSum, out int delSum, out int rows, out int cols, out long nUnassigned);
+
         // ICP.FindClosestPointSet (BaseClass/ICP.cs:224-250); xyz arrays are planar x[0..k) y[0..k) z[0..k)
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
         internal static extern int vpc_closest_point_set(IntPtr ctx, double[] modelXyz, long m, double[] dataXyz, long n,
