@@ -1259,7 +1259,9 @@ int vpc_dbscan_blocked_ref(vpc_ctx* ctx, const double* mx, const double* my, int
   // ---- getClusterFromMotor: sort key max(mx - xmin, my - ymin) (stable: List.Sort's tie order is undefined, pinned to the input
   // order), first cell = the first pts_in_cell points, then a rows x cols grid of boxes (lo, hi] (Tools.getListByScale2, Tools.cs:510-513)
   double x_min = mx[0], x_max = mx[0], y_min = my[0], y_max = my[0];
-  for (int64_t i = 1; i < n; ++i) {                       // List.Min/Max: NaN-free data assumed, as by the C#'s sort
+  for (int64_t i = 0; i < n; ++i) {
+    // the C#'s Min/Max/Sort on NaN keys give an order-dependent partition; non-finite coordinates are rejected here
+    if (!std::isfinite(mx[i]) || !std::isfinite(my[i])) return fail(ctx, VPC_E_BADARG, "the blocked partition needs finite coordinates");
     x_min = std::min(x_min, mx[i]); x_max = std::max(x_max, mx[i]);
     y_min = std::min(y_min, my[i]); y_max = std::max(y_max, my[i]);
   }
