@@ -17,7 +17,7 @@ LIB = HERE / "libvpc_oracle.so"
 
 
 def build(force: bool = False) -> Path:
-    srcs = [HERE / "vpc_oracle.cpp", HERE / "vpc_oracle_stats.cpp", HERE / "vpc_oracle.h"]
+    srcs = [HERE / "vpc_oracle.cpp", HERE / "vpc_oracle_stats.cpp", HERE / "vpc_oracle_aswritten.cpp", HERE / "vpc_oracle.h"]
     if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
         res = subprocess.run(["make", "-C", str(HERE), "-B", "libvpc_oracle.so"], capture_output=True, text=True)
         if res.returncode != 0:
@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         "vpco_jacobi_eig": [_p, C.c_int, _p, _p, C.c_int, _f64],
         "vpco_trans_points": [_p, _i64, _p, _p, _p],
         "vpco_match_within_literal": [_p, _i64, _p, _i64, _f64, _p, _p],
+        "vpco_jacobi_eig_as_written": [_p, C.c_int, _p, _p, C.c_int, _f64],
+        "vpco_icp_as_written": [_p, _i64, _p, _i64, _f64, _i32, _p, _p, _p, _p, _p, _i32],
         "vpco_cluster_stats_literal": [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p],
         "vpco_nearest_truth_2d_literal": [_p, _p, _p, _i64, _p, _p, _i64, _f64, _p],
         "vpco_polar_to_xyz": [_p, _p, _p, _i64, _f64, _f64, _i32, _i32, _p, _p],
@@ -213,3 +215,25 @@ def parse_rows(text: bytes):
         raise RuntimeError(f"oracle parse_rows rc={rc}")
     r = int(rows.value)
     return mx[:r], my[:r], ds[:r], st[:r]
+
+
+def jacobi_eig_as_written(a, max_it=100, eps=1e-4):
+    """Matrix.ComputeEvJacobi exactly as written (Matrix.cs:571-668).  Returns (ok, eigenvalues, V, a_after)."""
+    a = np.ascontiguousarray(a, np.float64).copy()
+    n = a.shape[0]
+    w = np.zeros(n); v = np.zeros((n, n))
+    ok = lib().vpco_jacobi_eig_as_written(_ptr(a), n, _ptr(w), _ptr(v), max_it, eps)
+    return bool(ok), w, v, a
+
+
+def icp_as_written(model_xyz, data_xyz, e, max_rounds=0, max_trace=64):
+    """ICP.go_hell_ICP exactly as written.  Returns dict(rc, R, T, rounds, sse[rounds], jacobi_ok[rounds]); rc == -7 means the C#
+    throws IndexOutOfRangeException (ICP.cs:170-174)."""
+    model, data = _planar(model_xyz), _planar(data_xyz)
+    R = np.zeros(9); T = np.zeros(3)
+    rounds = C.c_int32(0)
+    sse = np.zeros(max_trace); jok = np.zeros(max_trace, np.int32)
+    rc = lib().vpco_icp_as_written(_ptr(model), model.shape[1], _ptr(data), data.shape[1], float(e), int(max_rounds), _ptr(R), _ptr(T),
+                                   C.cast(C.byref(rounds), C.c_void_p), _ptr(sse), _ptr(jok), max_trace)
+    r = min(int(rounds.value), max_trace)
+    return {"rc": rc, "R": R.reshape(3, 3), "T": T, "rounds": int(rounds.value), "sse": sse[:r], "jacobi_ok": jok[:r].astype(bool)}

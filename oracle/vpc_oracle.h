@@ -108,6 +108,13 @@ int vpco_dedupe_xyz_literal(const double* xyz, const uint8_t* live, int64_t n, u
 int vpco_parse_rows(const char* text, int64_t len, int64_t row_cap, double* mx, double* my, double* dist, uint8_t* status,
                     int64_t* n_rows);
 
+/* ---- part 3 (vpc_oracle_aswritten.cpp): the C# EXACTLY as written, defects included -- documentation of why the product
+ * implements the intended algorithm instead (ICP.cs:53, 66, 76, 170-174, 276; Matrix.cs:636-666).  See the file header. */
+int vpco_jacobi_eig_as_written(double* a, int n, double* eigval, double* v, int max_it, double eps);
+int vpco_icp_as_written(const double* model_xyz, int64_t m, const double* data_xyz, int64_t n, double e, int32_t max_rounds,
+                        double R_io[9], double T_io[3], int32_t* rounds_done, double* sse_trace, int32_t* jacobi_ok_trace,
+                        int32_t max_trace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,3 +161,36 @@ def test_trans_points_order_of_operations(oracle):
     dst = oracle.trans_points(src, R, T)
     exp = np.stack([((0.0 + R[i, 0] * src[0]) + R[i, 1] * src[1]) + R[i, 2] * src[2] + T[i] for i in range(3)])
     np.testing.assert_array_equal(dst, exp)
+
+
+# ---- the C# exactly as written: its defects as executable facts (oracle/vpc_oracle_aswritten.cpp) -------------------------
+def test_jacobi_as_written_is_wrong_on_the_references_own_test_matrix(oracle):
+    # the one fixed input in the reference (FrmMain.cs:2637-2640): true eigenvalues 2 and 2 +- sqrt(5)
+    a = np.array([[1, 0, 2], [0, 2, 0], [2, 0, 3.0]])
+    ok, w, v, _ = oracle.jacobi_eig_as_written(a, 100, 1e-4)
+    true = np.array([2 - np.sqrt(5), 2, 2 + np.sqrt(5)])
+    assert ok                                              # it even reports success ...
+    assert np.abs(np.sort(w) - true).max() > 1.0           # ... with eigenvalues that are off by more than 1
+    assert abs(np.linalg.det(v)) < 0.5                     # and "eigenvectors" that are not even orthonormal
+    ok2, w2, v2, _ = oracle.jacobi_eig(a, 100, 1e-12)      # the restored routine (indices put back) is right
+    assert ok2 and np.abs(np.sort(w2) - true).max() < 1e-9
+
+
+def test_icp_as_written_throws_on_round_two_and_is_not_rigid(oracle):
+    rng = np.random.default_rng(0)
+    model = rng.uniform(0, 10, (3, 200))
+    th = 0.05
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    data = Rz.T @ (model - np.array([[1.0], [2.0], [0.5]]))
+    r = oracle.icp_as_written(model, data, 1e-4)
+    assert r["rc"] == -7 and r["rounds"] == 2              # IndexOutOfRangeException in the composition loop (ICP.cs:170-174)
+    assert np.abs(r["R"] @ r["R"].T - np.eye(3)).max() > 0.1   # what it had written to R is not a rotation
+    Ro, To, it, sse, _ = oracle.icp_rigid(model, data, 1e-4, 50, use_grid=False)
+    assert np.abs(Ro - Rz).max() < 1e-9 and np.abs(To - [1.0, 2.0, 0.5]).max() < 1e-9 and sse < 1e-12   # the intended algorithm
+
+
+def test_icp_as_written_integer_division_zeroes_the_cross_covariance(oracle):
+    # one point: 1 / P.Count == 1, more points: == 0 -- with n = 1 and model = data the loop converges in round 2 (d == pre_d == 0)
+    p = np.array([[1.0], [2.0], [3.0]])
+    r = oracle.icp_as_written(p, p, 1e-4)
+    assert r["rc"] == 0 and r["rounds"] == 1 and r["sse"][0] == 0.0
