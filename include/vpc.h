@@ -245,8 +245,8 @@ int vpc_dbscan_blocked_ref(vpc_ctx* ctx, const double* mx, const double* my, int
 
 /* ---- sorting (the reference's List.Sort / OrderBy steps around the path) -----------------------------------------
  * vpc_sort_pairs_dev: stable LSD radix sort of n (uint64 key, int32 value) pairs on key bits [begin_bit, end_bit), in
- *   place (device pointers).  vals_identity != 0: d_vals is output only and starts as 0..n-1, i.e. the call returns the
- *   stable sorting permutation.
+ *   place (device pointers); passes take 8 bits, so the sorted range is begin_bit .. begin_bit + 8*ceil((end_bit-begin_bit)/8).
+ *   vals_identity != 0: d_vals is output only and starts as 0..n-1, i.e. the call returns the stable sorting permutation.
  * vpc_argsort_f64_dev: d_order = stable ascending permutation of n doubles in Double.CompareTo order (NaN first,
  *   -0.0 == +0.0).  Replaces `rawData.Sort(...)` on the key max(mx - xmin, my - ymin) in MainForm.getClusterFromMotor
  *   (FrmMain.cs:1229-1233); List.Sort is unstable, ties are pinned to the original order here. */
