@@ -46,5 +46,15 @@ if n <= 20_000_000:
           and np.array_equal(key.cpu().numpy(), okey[a:b]) and np.array_equal(cls.cpu().numpy(), ocls[a:b]))
     print(f"rank {rank}: lean slab path vs oracle on the whole cloud: {'OK' if ok else 'MISMATCH'} (clusters {int(amount.item())} vs {oamount})", flush=True)
     assert ok
+else:
+    # full size (config C4): every rank clusters the WHOLE slab-ordered cloud on its own GPU and compares its slab, bit for bit
+    del tx, ty
+    wx, wy = torch.from_numpy(fx).to(dev), torch.from_numpy(fy).to(dev)
+    scid, skey, scls, samount = ctx.dbscan_dev(wx, wy, 0.07, 7, 0)
+    ok = (int(samount.item()) == int(amount.item()) and int(overflow.item()) == 0 and bool((scid[a:b] == cid).all())
+          and bool((skey[a:b] == key).all()) and bool((scls[a:b] == cls).all()))
+    print(f"rank {rank}: {world}-GPU lean slab path vs single-GPU clustering of the whole {n}-point cloud: {'OK' if ok else 'MISMATCH'} "
+          f"(clusters {int(amount.item())} vs {int(samount.item())})", flush=True)
+    assert ok
 ctx.close()
 dist.destroy_process_group()
