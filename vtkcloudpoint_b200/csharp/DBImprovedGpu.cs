@@ -57,6 +57,23 @@ namespace vtkPointCloud
             return perCell;
         }
 
+        // The whole blocked clustering (MainForm.getClusterFromMotor -> DoWork3 -> CompleteWork3 up to the renumbered labels,
+        // FrmMain.cs:1214-1520) in one call.  Writes clusterId / isClassed of every point of rawData, returns MainForm.clusterSum.
+        public int dbscanBlocked(List<Point3D> rawData, double e, int minPts, int ptsInCell, out int delSum)
+        {
+            int n = rawData.Count;
+            double[] mx = new double[n], my = new double[n];
+            for (int i = 0; i < n; i++) { mx[i] = rawData[i].motor_x; my[i] = rawData[i].motor_y; }
+            int[] cid = new int[n];
+            int clusterSum, rows, cols; long unassigned;
+            NativeMethods.Check(ctx, NativeMethods.vpc_dbscan_blocked_ref(ctx, mx, my, n, e, minPts, ptsInCell, cid, out clusterSum, out delSum,
+                                                                          out rows, out cols, out unassigned));
+            for (int i = 0; i < n; i++) { rawData[i].clusterId = cid[i]; rawData[i].isClassed = cid[i] != 0; }
+            pointsAmount += n;
+            clusterAmount = clusterSum;
+            return clusterSum;
+        }
+
         public void Dispose() { if (ctx != IntPtr.Zero) { NativeMethods.vpc_destroy(ctx); ctx = IntPtr.Zero; } }
     }
 }
