@@ -17,7 +17,7 @@ LIB = HERE / "libvpc_oracle.so"
 
 
 def build(force: bool = False) -> Path:
-    srcs = [HERE / "vpc_oracle.cpp", HERE / "vpc_oracle_stats.cpp", HERE / "vpc_oracle_aswritten.cpp", HERE / "vpc_oracle.h"]
+    srcs = [HERE / "vpc_oracle.cpp", HERE / "vpc_oracle_stats.cpp", HERE / "vpc_oracle_aswritten.cpp", HERE / "vpc_oracle_blocked.cpp", HERE / "vpc_oracle.h"]
     if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
         res = subprocess.run(["make", "-C", str(HERE), "-B", "libvpc_oracle.so"], capture_output=True, text=True)
         if res.returncode != 0:
@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
         "vpco_polar_to_xyz": [_p, _p, _p, _i64, _f64, _f64, _i32, _i32, _p, _p],
         "vpco_dedupe_xyz_literal": [_p, _p, _i64, _p, _p, _p],
         "vpco_parse_rows": [C.c_char_p, _i64, _i64, _p, _p, _p, _p, _p],
+        "vpco_blocked_literal": [_p, _p, _i64, _f64, _i32, _i32, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+        "vpco_merge_ids_literal": [_p, _p, _p, _p, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     }
     for name, args in sig.items():
         fn = getattr(dll, name)
@@ -237,3 +239,52 @@ def icp_as_written(model_xyz, data_xyz, e, max_rounds=0, max_trace=64):
                                    C.cast(C.byref(rounds), C.c_void_p), _ptr(sse), _ptr(jok), max_trace)
     r = min(int(rounds.value), max_trace)
     return {"rc": rc, "R": R.reshape(3, 3), "T": T, "rounds": int(rounds.value), "sse": sse[:r], "jacobi_ok": jok[:r].astype(bool)}
+
+
+class ReferenceThrows(RuntimeError):
+    """The C# as written would throw at this point (VPCO_E_REFERENCE_THROWS)."""
+
+
+def blocked(mx, my, eps, min_pts, pts_in_cell, shared_objects=False, fast=False, n_threads=1):
+    """MainForm.getClusterFromMotor -> DoWork3/StartCode -> CompleteWork3 (vpc_oracle_blocked.cpp).  Returns a dict."""
+    mx = np.ascontiguousarray(mx, np.float64); my = np.ascontiguousarray(my, np.float64)
+    n = len(mx)
+    cid = np.zeros(n, np.int32)
+    morder = np.zeros(3 * n + 1, np.int64); mcid = np.zeros(3 * n + 1, np.int32)
+    i32 = [C.c_int32(0) for _ in range(5)]      # cluster_sum del_sum rows cols cluster_sum_cells
+    i64 = [C.c_int64(0) for _ in range(3)]      # n_unassigned n_shared n_merge
+    ref = lambda v: C.cast(C.byref(v), C.c_void_p)   # noqa: E731
+    rc = lib().vpco_blocked_literal(_ptr(mx), _ptr(my), n, float(eps), int(min_pts), int(pts_in_cell), int(shared_objects), int(fast), int(n_threads),
+                                    _ptr(cid), ref(i32[0]), ref(i32[1]), ref(i32[2]), ref(i32[3]), ref(i64[0]), ref(i64[1]), _ptr(morder), _ptr(mcid),
+                                    ref(i64[2]), ref(i32[4]))
+    if rc == -7:
+        raise ReferenceThrows("the C# throws here (degenerate first cell or clusForMerge[-1])")
+    if rc != 0:
+        raise RuntimeError(f"oracle blocked rc={rc}")
+    k = int(i64[2].value)
+    return {"cluster_id": cid, "cluster_sum": int(i32[0].value), "del_sum": int(i32[1].value), "rows": int(i32[2].value), "cols": int(i32[3].value),
+            "n_unassigned": int(i64[0].value), "n_shared": int(i64[1].value), "merge_order": morder[:k].copy(), "merge_cid": mcid[:k].copy(),
+            "cluster_sum_cells": int(i32[4].value)}
+
+
+def merge_ids(merge_cid, xyz_entries, mx_entries, my_entries, cluster_amount, thre):
+    """Tools.GetClusList -> MergeIDByDistance -> refreshCensAndClusByDictionary on the clusForMerge list (per-ENTRY arrays)."""
+    mcid = np.ascontiguousarray(merge_cid, np.int32)
+    k = len(mcid)
+    xyz = _planar(xyz_entries) if k else np.zeros((3, 0))
+    mx = np.ascontiguousarray(mx_entries, np.float64); my = np.ascontiguousarray(my_entries, np.float64)
+    new_cid = np.zeros(k, np.int32)
+    cap = max(int(cluster_amount), 1)
+    dfrom = np.zeros(cap, np.int32); dto = np.zeros(cap, np.int32)
+    c5 = np.zeros(5 * cap); cids = np.zeros(cap, np.int32); nc5 = np.zeros(5 * cap)
+    amount, nd, ncen = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    ref = lambda v: C.cast(C.byref(v), C.c_void_p)   # noqa: E731
+    rc = lib().vpco_merge_ids_literal(_ptr(mcid), _ptr(xyz), _ptr(mx), _ptr(my), k, int(cluster_amount), float(thre), _ptr(new_cid), ref(amount),
+                                      _ptr(dfrom), _ptr(dto), ref(nd), _ptr(c5), _ptr(cids), ref(ncen), _ptr(nc5))
+    if rc == -7:
+        raise ReferenceThrows("the C# throws here (id out of range or Average over an empty cluster)")
+    if rc != 0:
+        raise RuntimeError(f"oracle merge_ids rc={rc}")
+    m, a = int(ncen.value), int(amount.value)
+    return {"cluster_id": new_cid, "cluster_amount": a, "dict": list(zip(dfrom[:nd.value].tolist(), dto[:nd.value].tolist())),
+            "centers5": c5[:5 * m].reshape(5, m).copy(), "center_ids": cids[:m].copy(), "new_centers5": nc5[:5 * a].reshape(5, a).copy()}

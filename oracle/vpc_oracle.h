@@ -108,6 +108,35 @@ int vpco_dedupe_xyz_literal(const double* xyz, const uint8_t* live, int64_t n, u
 int vpco_parse_rows(const char* text, int64_t len, int64_t row_cap, double* mx, double* my, double* dist, uint8_t* status,
                     int64_t* n_rows);
 
+/* ---- part 4 (vpc_oracle_blocked.cpp): the blocked ("分块") multithreaded clustering, SURVEY.md 8a rows a5-a8, literal and
+ * List-based on Point3D objects.  vpco_blocked_literal = MainForm.getClusterFromMotor (FrmMain.cs:1214-1291, Tools.cs:510-513)
+ * -> DoWork3 / StartCode (:1340-1361, :2782-2794) -> CompleteWork3 (:1432-1520).
+ *   shared_objects 0: every cell slot is a private copy of its point (the product's defined behaviour for the C#'s data race);
+ *                  1: cells share the objects and the work items run sequentially in queue order (one legal C# schedule).
+ *   fast           0: FindAll per box and Theta(m^2) DBImproved everywhere; 1: separable box scan, grid re-cluster (same lists).
+ *   n_threads      copies mode only: the StartCode work items on a thread pool.
+ * Outputs: cluster_id[n] per input point (0 for points that fall into no cell); *cluster_sum = MainForm.clusterSum (:1538);
+ * del_sum, rows, cols, n_unassigned, n_shared (points sitting in two cells), cluster_sum_cells (1 + sum of per-cell amounts,
+ * :1346/:2789) are nullable extras; merge_order / merge_cid (nullable, capacity 3 n) = clusForMerge in its final order
+ * (:1517-1520) as input-point indices and their cluster ids, *n_merge entries.
+ * Returns VPCO_E_REFERENCE_THROWS where the C# throws (degenerate first cell :1257, clusForMerge[-1] :1487). */
+int vpco_blocked_literal(const double* mx, const double* my, int64_t n, double eps, int32_t min_pts, int32_t pts_in_cell,
+                         int shared_objects, int fast, int n_threads, int32_t* cluster_id, int32_t* cluster_sum, int32_t* del_sum,
+                         int32_t* rows, int32_t* cols, int64_t* n_unassigned, int64_t* n_shared, int64_t* merge_order,
+                         int32_t* merge_cid, int64_t* n_merge, int32_t* cluster_sum_cells);
+/* Clustering.MergeBtn_Click's chain (Clustering.cs:141-153): Tools.GetClusList (Tools.cs:162-195) over the clusForMerge list
+ * (merge_cid / xyz planar [3][n_merge] / mx / my per ENTRY, in list order), Tools.MergeIDByDistance (Tools.cs:580-621:
+ * DBImproved.dbscan(centres' (X, Y), thre, 2)), Tools.refreshCensAndClusByDictionary (Tools.cs:521-572).
+ * Outputs: new_cid[n_merge]; *new_amount; the dictionary in insertion order (dict_from -> dict_to, capacity cluster_amount);
+ * centers5 planar [5][*n_centers] (X Y Z motor_x motor_y means before the merge, list order) with center_ids;
+ * new_centers5 planar [5][*new_amount] after the merge (members = own points, then the merged clusters in ascending old id).
+ * All but new_cid nullable.  VPCO_E_REFERENCE_THROWS: an id outside 1..cluster_amount, or a surviving cluster without points
+ * (Average over an empty list, Tools.cs:565). */
+int vpco_merge_ids_literal(const int32_t* merge_cid, const double* xyz, const double* mx, const double* my, int64_t n_merge,
+                           int32_t cluster_amount, double thre, int32_t* new_cid, int32_t* new_amount, int32_t* dict_from,
+                           int32_t* dict_to, int32_t* n_dict, double* centers5, int32_t* center_ids, int32_t* n_centers,
+                           double* new_centers5);
+
 /* ---- part 3 (vpc_oracle_aswritten.cpp): the C# EXACTLY as written, defects included -- documentation of why the product
  * implements the intended algorithm instead (ICP.cs:53, 66, 76, 170-174, 276; Matrix.cs:636-666).  See the file header. */
 int vpco_jacobi_eig_as_written(double* a, int n, double* eigval, double* v, int max_it, double eps);

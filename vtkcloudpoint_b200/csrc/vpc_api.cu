@@ -557,6 +557,9 @@ int vpc_dbscan_slab_finish_dev(vpc_ctx* ctx, const int32_t* d_map_from, const in
   DbArgs a = ctx->db_slab;
   a.compkey = d_key_out;
   const int gpts = blocks_for(a.n, kDbBlock);
+  // points outside the grid (NaN / inf coordinates, NaN padding) were settled by phase 1 into the workspace's key array, and
+  // k_db_resolve walks grid positions only: they are noise here (min_pts > 0 in the slab path), DBImproved.cs:41
+  VPC_CUDA(ctx, cudaMemsetAsync(d_key_out, 0xff, 4ull * a.n, s));
   if (n_map > 0) VPC_LAUNCH(ctx, k_db_remap_roots, gpts, kDbBlock, s, a, d_map_from, d_map_to, (int)n_map);
   VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
   ctx->db_slab_valid = false;
@@ -1239,6 +1242,7 @@ int vpc_dbscan_slab_finish_merge_dev(vpc_ctx* ctx, const int32_t* d_pairs_all, i
   DbArgs a = ctx->db_slab;
   a.compkey = d_key_out;
   const int gpts = blocks_for(a.n, kDbBlock);
+  VPC_CUDA(ctx, cudaMemsetAsync(d_key_out, 0xff, 4ull * a.n, s));          // points outside the grid: noise (see vpc_dbscan_slab_finish_dev)
   if (world > 1) {
     VPC_LAUNCH(ctx, k_slab_merge, blocks_for((long long)world * cap_pairs, kDbBlock), kDbBlock, s, d_pairs_all, world, cap_pairs, t);
     VPC_LAUNCH(ctx, k_db_remap_roots_table, gpts, kDbBlock, s, a, t);
