@@ -346,6 +346,69 @@ int vpc_icp_shard_accumulate_dev(vpc_ctx* ctx, const double* d_data_xyz, int64_t
 int vpc_icp_shard_solve_dev(vpc_ctx* ctx, const double* d_sums16, int64_t n, double e, int32_t max_iters,
                             double* d_state_out, void* stream);
 
+/* ---- across GPUs over peer memory (NVLink / NVSwitch), no NCCL call on the step -----------------------------------
+ * The reference has no counterpart (one process, a thread pool over halo-less cells, FrmMain.cs:1356-1359).  Every rank (= one
+ * GPU, one vpc_ctx) owns an exchange HEAP of the same size and layout; kernels reach the other ranks' heaps through peer pointers
+ * and synchronise with epoch flags (csrc/comm.cuh).  Two ways to connect the ranks:
+ *   one process per GPU:  vpc_comm_create -> vpc_comm_handle (64 opaque bytes = cudaIpcMemHandle_t) -> exchange the handles by any
+ *                         means (torch.distributed, a pipe, a file) -> vpc_comm_connect(all handles in rank order)
+ *   one process, many GPUs: vpc_comm_create per device -> vpc_comm_connect_local(list of all comms); the same device may appear
+ *                         more than once, then the ranks must be driven PHASE BY PHASE on one stream (test / emulation mode: a
+ *                         kernel that waits for a rank whose kernel has not been enqueued yet would spin until its time-out).
+ * Plans take their heap space in creation order: create the same plans with the same sizes on every rank.
+ * vpc_comm_error: bit 0 = a bounded wait timed out (a rank did not show up), bit 1 = an exchange buffer overflowed. */
+#define VPC_COMM_HANDLE_BYTES 64
+typedef struct vpc_comm vpc_comm;
+int vpc_comm_create(vpc_ctx* ctx, int32_t rank, int32_t world, int64_t heap_bytes, vpc_comm** out);
+int vpc_comm_handle(vpc_comm* comm, void* handle_out);
+int vpc_comm_connect(vpc_comm* comm, const void* handles);
+int vpc_comm_connect_local(vpc_comm* comm, vpc_comm* const* all);
+int vpc_comm_error(vpc_comm* comm, int32_t* error_bits);
+/* closes the imported heaps; with one process per GPU: disconnect on every rank, synchronise the ranks, then destroy */
+int vpc_comm_disconnect(vpc_comm* comm);
+void vpc_comm_destroy(vpc_comm* comm);
+
+/* Exact DBSCAN (vpc_dbscan_l1_2d semantics, DBImproved.cs:14-114) of ONE cloud that is already cut into `world` slabs of
+ * u = x + y: rank r holds the n_per_rank[r] points with splitters[r-1] <= x + y < splitters[r] (global index of its point i =
+ * n_per_rank[0] + .. + n_per_rank[r-1] + i).  Replaces the reference's halo-less blocking + heuristic re-join
+ * (FrmMain.cs:1214-1291, :1507-1516).  Per step: strips within 2 eps of a slab boundary are pulled from the neighbours, every rank
+ * clusters owned + halo points, the component keys of boundary core points are merged by a union-find over everybody's pairs, the
+ * border rule runs on global keys, clusters are numbered by their minimum global core index (bitmaps + counts).
+ *   coord_bound >= max(|x + y|, |x - y|) over the whole cloud (rounding slack of the halo width)
+ *   cap_halo / cap_pairs: capacities of one halo strip / of one rank's boundary-pair list (overflow raises error bit 1)
+ * vpc_slab_plan_io: the plan's device buffers -- write the slab's coordinates into d_x / d_y (n_per_rank[rank] doubles each)
+ *   before a step; results per owned point in d_cluster_id / d_is_key / d_is_classed; d_status int32[16]: [0] cluster_amount,
+ *   [1] error bits of ANY rank, [2] largest incoming halo strip, [3] own pair count, [4] own head count, [5] step number.
+ * vpc_slab_step_dev enqueues one step (no host synchronisation, CUDA-graph capturable); vpc_slab_step_phase_dev enqueues ONE of
+ * its five phases (0 pack, 1 pull + local clustering + pairs, 2 merge + border rule + heads, 3 head ranks, 4 ids) for the
+ * emulation mode.  The context must not run other DBSCAN calls between phases 1 and 2 (they share its workspace). */
+typedef struct vpc_slab_plan vpc_slab_plan;
+int64_t vpc_slab_plan_heap_bytes(int32_t world, int64_t n_max_rank, int32_t cap_halo, int32_t cap_pairs);
+int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank, const double* splitters, double eps, int32_t min_pts,
+                         double coord_bound, int32_t cap_halo, int32_t cap_pairs, vpc_slab_plan** out);
+int vpc_slab_plan_io(vpc_slab_plan* plan, void** d_x, void** d_y, void** d_cluster_id, void** d_is_key, void** d_is_classed, void** d_status);
+int vpc_slab_step_dev(vpc_slab_plan* plan, int32_t first_cluster_id, void* stream);
+int vpc_slab_step_phase_dev(vpc_slab_plan* plan, int32_t phase, int32_t first_cluster_id, void* stream);
+void vpc_slab_plan_destroy(vpc_slab_plan* plan);
+
+/* ICP.go_hell_ICP (ICP.cs:18-181, intended algorithm like vpc_icp_rigid) across GPUs.
+ *   mode 0, TARGET sharded: the model set on this rank (vpc_icp_set_model_dev) is the rank's index range of the target, first
+ *           global index idx_offset; all n data points on every rank.  Per round: local nearest point of every data point, the
+ *           candidates {d2, index, point} pushed to the rank that reduces that slice of the data, exact argmin there (ties -> lowest
+ *           global index, ICP.cs:240), 16 sums pushed to everybody, replicated solve.
+ *   mode 1, SOURCE sharded: the whole target on every rank, rank q iterates data slice q; only the 16 sums travel.
+ * d_data_xyz (planar, all n points) must stay valid.  vpc_icp_dist_begin_dev resets the state; vpc_icp_dist_rounds_dev enqueues
+ * `rounds` rounds (no-ops once converged / max_iters reached), then exports the state (16 doubles as vpc_icp_rigid_dev) and the
+ * correspondences of the last executed round (global target indices, n, identical on every rank); no host synchronisation.
+ * vpc_icp_dist_round_phase_dev: one phase of one round (0 search, 1 reduce [mode 0 only], 2 solve) for the emulation mode. */
+typedef struct vpc_icp_dist vpc_icp_dist;
+int64_t vpc_icp_dist_heap_bytes(int32_t world, int64_t n);
+int vpc_icp_dist_create(vpc_ctx* ctx, vpc_comm* comm, int32_t mode, const double* d_data_xyz, int64_t n, int32_t idx_offset, vpc_icp_dist** out);
+int vpc_icp_dist_begin_dev(vpc_icp_dist* icp, void* stream);
+int vpc_icp_dist_round_phase_dev(vpc_icp_dist* icp, int32_t phase, double e, int32_t max_iters, void* stream);
+int vpc_icp_dist_rounds_dev(vpc_icp_dist* icp, double e, int32_t max_iters, int32_t rounds, double* d_state_out, int32_t* d_order_out, void* stream);
+void vpc_icp_dist_destroy(vpc_icp_dist* icp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,25 @@ SIGNATURES = {
     "vpc_icp_shard_select_dev": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "vpc_icp_shard_accumulate_dev": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p]),
     "vpc_icp_shard_solve_dev": (C.c_int, [_p, _p, _i64, _f64, _i32, _p, _p]),
+    "vpc_comm_create": (C.c_int, [_p, _i32, _i32, _i64, C.POINTER(_p)]),
+    "vpc_comm_handle": (C.c_int, [_p, _p]),
+    "vpc_comm_connect": (C.c_int, [_p, _p]),
+    "vpc_comm_connect_local": (C.c_int, [_p, C.POINTER(_p)]),
+    "vpc_comm_error": (C.c_int, [_p, _p]),
+    "vpc_comm_disconnect": (C.c_int, [_p]),
+    "vpc_comm_destroy": (None, [_p]),
+    "vpc_slab_plan_heap_bytes": (_i64, [_i32, _i64, _i32, _i32]),
+    "vpc_slab_plan_create": (C.c_int, [_p, _p, _p, _p, _f64, _i32, _f64, _i32, _i32, C.POINTER(_p)]),
+    "vpc_slab_plan_io": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "vpc_slab_step_dev": (C.c_int, [_p, _i32, _p]),
+    "vpc_slab_step_phase_dev": (C.c_int, [_p, _i32, _i32, _p]),
+    "vpc_slab_plan_destroy": (None, [_p]),
+    "vpc_icp_dist_heap_bytes": (_i64, [_i32, _i64]),
+    "vpc_icp_dist_create": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, C.POINTER(_p)]),
+    "vpc_icp_dist_begin_dev": (C.c_int, [_p, _p]),
+    "vpc_icp_dist_round_phase_dev": (C.c_int, [_p, _i32, _f64, _i32, _p]),
+    "vpc_icp_dist_rounds_dev": (C.c_int, [_p, _f64, _i32, _i32, _p, _p, _p]),
+    "vpc_icp_dist_destroy": (None, [_p]),
 }
 
 

@@ -1,0 +1,120 @@
+// ctx.cuh -- the context object behind vpc_ctx and the launch / error macros shared by the host-side sources of libvpc.
+#pragma once
+
+#include "../../include/vpc.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dbscan.cuh"
+#include "icp.cuh"
+
+using namespace vpc;
+
+namespace {
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+  void reset() { off = 0; }
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+inline size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
+
+}  // namespace
+
+struct vpc_ctx {
+  int device = 0;
+  std::mutex mu;
+  std::string err;
+  int64_t launches = 0;
+  cudaStream_t own_stream = nullptr;
+  Arena db;        // DBSCAN workspace
+  Arena io;        // device copies of host inputs / outputs (host-pointer entry points)
+  Arena icp_model; // model cell list (persists between calls)
+  Arena icp_work;  // per-call ICP workspace
+  Arena st;        // sort / cluster statistics / ingest workspace
+  // ICP model state
+  IcpModel model{};
+  bool model_set = false;
+  IcpState* icp_state = nullptr;
+  double* icp_partial = nullptr;
+  unsigned* icp_ticket = nullptr;
+  int icp_partial_blocks = 0;
+  int sm_count = 148;
+  DbArgs db_slab{};       // arguments of the last vpc_dbscan_slab_local_dev, for ..._finish_dev
+  bool db_slab_valid = false;
+  int64_t db_ws_n = -1;  // n the DBSCAN workspace is currently laid out and initialised for
+  bool db_ws_banded = false;
+  // optional per-kernel CUDA-event timing (bench.py's roofline leg)
+  bool profile = false;
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+};
+
+namespace {
+
+#define VPC_CUDA(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                       \
+      return (_e == cudaErrorMemoryAllocation) ? VPC_E_NOMEM : VPC_E_CUDA;                   \
+    }                                                                                        \
+  } while (0)
+
+#define VPC_LAUNCH(ctx, kernel, grid, block, stream, ...)                                    \
+  do {                                                                                       \
+    cudaEvent_t _ea = nullptr, _eb = nullptr;                                                \
+    if ((ctx)->profile) {                                                                    \
+      cudaEventCreate(&_ea); cudaEventCreate(&_eb); cudaEventRecord(_ea, (stream));          \
+    }                                                                                        \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                   \
+    if ((ctx)->profile) {                                                                    \
+      cudaEventRecord(_eb, (stream)); (ctx)->prof.push_back({#kernel, _ea, _eb});            \
+    }                                                                                        \
+    (ctx)->launches++;                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#kernel) + ": " + cudaGetErrorString(_e);                     \
+      return VPC_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+int fail(vpc_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+// Grow-only device arena.  Growing synchronises the device (old buffer may be in flight).
+int arena_reserve(vpc_ctx* ctx, Arena& a, size_t bytes) {
+  a.reset();
+  if (bytes <= a.cap) return VPC_OK;
+  VPC_CUDA(ctx, cudaDeviceSynchronize());
+  if (a.base) VPC_CUDA(ctx, cudaFree(a.base));
+  a.base = nullptr; a.cap = 0;
+  size_t want = bytes + bytes / 8 + (1u << 20);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ctx->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+    return VPC_E_NOMEM;
+  }
+  a.base = static_cast<char*>(p); a.cap = want;
+  return VPC_OK;
+}
+
+}  // namespace

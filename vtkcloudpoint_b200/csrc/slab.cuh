@@ -1,0 +1,272 @@
+// slab.cuh -- exact DBSCAN of ONE cloud across the GPUs of a box: kernels of the slab step, exchanging over peer memory (comm.cuh).
+//
+// The reference blocks the cloud without a halo and re-joins split clusters heuristically (FrmMain.cs:1214-1291, :1507-1516); this
+// is its exact replacement: the cloud is cut into slabs of u = x + y (the L1 eps-ball has half-width eps in u), one
+// per GPU.  Per step and rank:
+//   k_slb_halo_pack    owned points within H = 2 eps (+ slack) of a slab boundary -> pack buffers in the own heap; flag to the neighbours
+//   k_slb_halo_pull    wait for the neighbours' flags, PULL their strips over NVLink into the local cloud (NaN padding behind them)
+//   [local DBSCAN]     dbscan.cuh on owned + halo points, component keys = minimum GLOBAL core index
+//   k_slb_pairs_pack   (global index, local key) of the core points that also live on another rank -> own heap; flag to everybody
+//   k_slb_merge        wait for everybody, pull all pairs, union the keys reported for the same point (hash tables of dbscan.cuh)
+//   [remap + resolve]  dbscan.cuh: local roots take the merged key, border rule with global keys (DBImproved.cs:87)
+//   k_slb_heads        owned core points that head their cluster set their bit in the bitmap of the rank that is HOME to that
+//                      global index (peer atomicOr when remote); flag to everybody
+//   k_slb_heads_rank   wait for everybody, popc-scan of the own bitmap, publish the head count
+//   k_slb_ids          wait for everybody; id = first + 1 + (heads on lower homes) + rank inside the home's bitmap (DBImproved.cs:93-110)
+// A kernel waits only as its FIRST action and signals as its LAST, so the ranks can also be emulated one after the other on a single
+// GPU (phase by phase, vpc_api: lockstep mode) -- that is how the single-GPU test-suite exercises this file.
+#pragma once
+
+#include "comm.cuh"
+#include "dbscan.cuh"
+
+namespace vpc {
+
+struct SlabHeapLayout {       // byte offsets inside every rank's heap (identical on all ranks)
+  size_t pack_x[2], pack_y[2], pack_g[2];   // [0] = strip for the LEFT neighbour, [1] = for the RIGHT neighbour; cap entries each
+  size_t pairs;                             // int2[cap_pairs] {global index, local key}
+  size_t bits[2];                           // cluster-head bitmaps, double-buffered by step parity; nwords entries
+  size_t rank;                              // int[nwords] exclusive popc-scan of the current bitmap
+  size_t total;
+};
+
+struct SlabArgs {
+  Peers P;
+  SlabHeapLayout L;
+  int n_own, n_halo_cap, cap, cap_pairs, nwords;  // n_halo_cap = slots behind the owned points in the local cloud (2 * cap in pre-cut mode)
+  int gstart[kMaxWorld + 1];                // global index ranges: rank q is HOME to [gstart[q], gstart[q+1])
+  double s_lo, s_hi, H;
+  int has_left, has_right;
+  int first_cluster_id;
+  // local buffers
+  double* lx; double* ly; int* lg;          // local cloud: n_own owned points, then halo slots
+  unsigned char* is_key_l; int* gkey;       // per local point: core flag, merged cluster key
+  int* counters;                            // [0..1] halo strip counts, [2] pairs count, [3] ticket
+  unsigned long long* epoch;                // step counter (device resident: graph replays advance it)
+  int* cid; unsigned char* is_key; unsigned char* is_classed;   // outputs per owned point
+  int* status;                              // [0] cluster_amount, [1] error bits (1 timeout, 2 overflow), [2] halo-in max, [3] pairs, [4] heads (own), [5] epoch
+};
+
+__device__ __forceinline__ bool slb_finite(double x, double y) { return finite_d(x) && finite_d(y) && finite_d(x + y) && finite_d(x - y); }
+
+// ---- halo strips: pack locally, tell the neighbours -----------------------------------------------------------------
+__global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a) {
+  __shared__ bool s_last;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool toL = false, toR = false;
+  double xi = 0, yi = 0;
+  if (i < a.n_own) {
+    xi = a.lx[i]; yi = a.ly[i];
+    if (slb_finite(xi, yi)) {
+      const double u = xi + yi;
+      toL = a.has_left && (u - a.H < a.s_lo);
+      toR = a.has_right && (u + a.H >= a.s_hi);
+    }
+  }
+  const int sl = db_append_slot(toL, a.counters + 0);
+  const int sr = db_append_slot(toR, a.counters + 1);
+  const int me = a.P.rank;
+  if (sl >= 0 && sl < a.cap) { a.P.at<double>(me, a.L.pack_x[0])[sl] = xi; a.P.at<double>(me, a.L.pack_y[0])[sl] = yi; a.P.at<int>(me, a.L.pack_g[0])[sl] = a.lg[i]; }
+  if (sr >= 0 && sr < a.cap) { a.P.at<double>(me, a.L.pack_x[1])[sr] = xi; a.P.at<double>(me, a.L.pack_y[1])[sr] = yi; a.P.at<int>(me, a.L.pack_g[1])[sr] = a.lg[i]; }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence_system();
+  const unsigned long long E = *a.epoch + 1;
+  *a.epoch = E;                                           // the later kernels of this step read it
+  const int cl = ld_relaxed_s32(a.counters + 0), cr = ld_relaxed_s32(a.counters + 1);
+  if (cl > a.cap || cr > a.cap) atomicOr(&a.P.hdr(me)->error, 2);
+  a.counters[0] = 0; a.counters[1] = 0; a.counters[3] = 0;
+  if (a.has_left) comm_signal(a.P, me - 1, kPhHalo, E, (unsigned long long)min(cl, a.cap));
+  if (a.has_right) comm_signal(a.P, me + 1, kPhHalo, E, (unsigned long long)min(cr, a.cap));
+}
+
+// ---- halo strips: wait for the neighbours, pull their strips, pad with NaN (= points outside the grid, DBImproved.cs:41) ------
+__global__ void __launch_bounds__(kDbBlock) k_slb_halo_pull(SlabArgs a) {
+  const unsigned long long E = *a.epoch;
+  const int me = a.P.rank;
+  if (threadIdx.x == 0 && a.has_left) comm_wait(a.P, me - 1, kPhHalo, E);
+  if (threadIdx.x == 1 && a.has_right) comm_wait(a.P, me + 1, kPhHalo, E);
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * a.cap) return;
+  const int side = j >= a.cap ? 1 : 0, k = side ? j - a.cap : j;     // side 0: strip from the left neighbour (its RIGHT strip)
+  const int src = side ? me + 1 : me - 1;
+  const bool have = side ? a.has_right : a.has_left;
+  int cnt = 0;
+  if (have) cnt = min((int)comm_payload(a.P, src, kPhHalo), a.cap);
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  double x = nan, y = nan; int g = -1;
+  if (k < cnt) {
+    const int s = side ? 0 : 1;
+    x = ld_relaxed_sys_f64(a.P.at<double>(src, a.L.pack_x[s]) + k);
+    y = ld_relaxed_sys_f64(a.P.at<double>(src, a.L.pack_y[s]) + k);
+    g = ld_relaxed_sys_s32(a.P.at<int>(src, a.L.pack_g[s]) + k);
+  }
+  a.lx[a.n_own + j] = x; a.ly[a.n_own + j] = y; a.lg[a.n_own + j] = g;
+  if (j == 0) {   // largest incoming strip (calibration of the capacities)
+    const int c0 = a.has_left ? (int)comm_payload(a.P, me - 1, kPhHalo) : 0, c1 = a.has_right ? (int)comm_payload(a.P, me + 1, kPhHalo) : 0;
+    a.status[2] = max(c0, c1);
+  }
+}
+
+// ---- boundary pairs: (global index, local component key) of locally-core points that also live on another rank ---------------
+// walks the SORTED positions of the workspace the local DBSCAN kept (valid for the direct and the banded layout): coordinates, local
+// index, parent and core flag of a point sit together there
+__global__ void __launch_bounds__(kDbBlock) k_slb_pairs_pack(SlabArgs a, DbArgs d) {
+  __shared__ bool s_last;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool want = false;
+  int key = -1, g = -1;
+  if (p < d.ctrl->n_valid && d.core[p] == 1) {
+    const DbRec* r = d.rec + p;
+    const int i = r->sidx;
+    bool cand = i >= a.n_own;                                         // a halo copy: its owner reports it too
+    if (!cand) { const double2 xy = db_xy(d.rec, p); const double u = xy.x + xy.y; cand = (a.has_left && (u - a.H < a.s_lo)) || (a.has_right && (u + a.H >= a.s_hi)); }
+    if (cand) { want = true; key = d.rec[r->parent].cinfo.y; g = a.lg[i]; }
+  }
+  const int me = a.P.rank;
+  const int s = db_append_slot(want, a.counters + 2);
+  if (s >= 0 && s < a.cap_pairs) a.P.at<int2>(me, a.L.pairs)[s] = make_int2(g, key);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence_system();
+  const unsigned long long E = *a.epoch;
+  const int c = ld_relaxed_s32(a.counters + 2);
+  if (c > a.cap_pairs) atomicOr(&a.P.hdr(me)->error, 2);
+  a.counters[2] = 0; a.counters[3] = 0;
+  a.status[3] = c;
+  for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhPairs, E, (unsigned long long)min(c, a.cap_pairs));
+}
+
+// ---- cross-slab merge: pull everybody's pairs, union the keys that name the same point -----------------------------------
+__global__ void __launch_bounds__(kDbBlock) k_slb_merge(SlabArgs a, MergeTables t) {
+  const unsigned long long E = *a.epoch;
+  comm_wait_all_block(a.P, kPhPairs, E);
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (long long)a.P.world * a.cap_pairs) return;
+  const int r = (int)(j / a.cap_pairs), q = (int)(j % a.cap_pairs);
+  if (q >= min((int)comm_payload(a.P, r, kPhPairs), a.cap_pairs)) return;
+  const unsigned long long raw = ld_relaxed_sys_u64(a.P.at<unsigned long long>(r, a.L.pairs) + q);
+  const int G = (int)(unsigned)(raw & 0xffffffffull), K = (int)(unsigned)(raw >> 32);
+  if (G < 0 || K < 0) return;
+  const int sk = mg_insert(t.k_key, t.mask, K);
+  const int sg = mg_insert(t.g_key, t.mask, G);
+  const int first = atomicCAS(t.g_val + sg, -1, sk);
+  if (first != -1 && first != sk) mg_unite(t, sk, first);
+}
+
+__device__ __forceinline__ int slb_home_of(const SlabArgs& a, int g) {   // rank q with gstart[q] <= g < gstart[q+1]
+  int q = 0;
+#pragma unroll 1
+  for (int r = 1; r < a.P.world; ++r) q += (g >= a.gstart[r]) ? 1 : 0;
+  return q;
+}
+
+// ---- cluster heads: owned core points whose global index IS their cluster's key set their bit at the index's home ---------
+// also clears the bitmap of the other parity (nobody touches it during this step) and re-arms the scan of k_slb_heads_rank
+__global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
+  __shared__ bool s_last;
+  const unsigned long long E = *a.epoch;
+  const int me = a.P.rank;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned* other = a.P.at<unsigned>(me, a.L.bits[(E + 1) & 1]);
+  for (int w = i; w < a.nwords; w += gridDim.x * blockDim.x) other[w] = 0u;
+  if (i < a.n_own && a.is_key_l[i]) {
+    const int g = a.lg[i];
+    if (g >= 0 && a.gkey[i] == g) {
+      const int home = slb_home_of(a, g);
+      const int w = g - a.gstart[home];
+      atomicOr_system(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5), 1u << (w & 31));
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence_system();
+  a.counters[3] = 0;
+  for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhHeads, E, 0ull);
+}
+
+// ---- one block: wait for everybody's bits, popc-scan the own bitmap, publish the own head count (and error bits) ----------
+constexpr int kHeadsRankBlock = 1024;
+__global__ void __launch_bounds__(kHeadsRankBlock) k_slb_heads_rank(SlabArgs a) {
+  __shared__ int s_warp[kHeadsRankBlock / kWarp];
+  __shared__ int s_carry;
+  const unsigned long long E = *a.epoch;
+  const int me = a.P.rank;
+  comm_wait_all_block(a.P, kPhHeads, E);
+  const unsigned* bits = a.P.at<unsigned>(me, a.L.bits[E & 1]);
+  int* rank = a.P.at<int>(me, a.L.rank);
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < a.nwords; base += kHeadsRankBlock) {
+    const int w = base + threadIdx.x;
+    const int v = (w < a.nwords) ? __popc(ld_relaxed_sys_u32(bits + w)) : 0;   // remote atomics land in L2: do not trust L1
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int off = s_carry;
+    for (int k = 0; k < warp; ++k) off += s_warp[k];
+    if (w < a.nwords) rank[w] = off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == kHeadsRankBlock - 1) s_carry = off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  const int total = s_carry;
+  a.status[4] = total;
+  __threadfence_system();
+  const unsigned long long err = (unsigned long long)(unsigned)atomicOr(&a.P.hdr(me)->error, 0);
+  for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhGather, E, ((unsigned long long)(unsigned)total) | (err << 40));
+}
+
+// ---- ids in the reference's numbering: clusters ranked by their minimum core index (DBImproved.cs:93-110) -----------------------
+__global__ void __launch_bounds__(kDbBlock) k_slb_ids(SlabArgs a) {
+  __shared__ int s_base[kMaxWorld + 1];
+  __shared__ int s_err;
+  const unsigned long long E = *a.epoch;
+  comm_wait_all_block(a.P, kPhGather, E);
+  if (threadIdx.x == 0) {
+    int acc = 0, err = 0;
+    for (int q = 0; q < a.P.world; ++q) {
+      const unsigned long long w = comm_payload(a.P, q, kPhGather);
+      s_base[q] = acc; acc += (int)(unsigned)(w & 0xffffffffull); err |= (int)(w >> 40);
+    }
+    s_base[a.P.world] = acc; s_err = err | a.P.hdr(a.P.rank)->error;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { a.status[0] = a.first_cluster_id + s_base[a.P.world]; a.status[1] = s_err; a.status[5] = (int)E; }
+  if (i >= a.n_own) return;
+  const int k = a.gkey[i];
+  int id = 0;
+  if (k >= 0) {
+    const int home = slb_home_of(a, k);
+    const int w = k - a.gstart[home];
+    const unsigned word = ld_relaxed_sys_u32(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5));
+    const int r = ld_relaxed_sys_s32(a.P.at<int>(home, a.L.rank) + (w >> 5)) + __popc(word & ((1u << (w & 31)) - 1u));
+    id = a.first_cluster_id + 1 + s_base[home] + r;
+  }
+  a.cid[i] = id;
+  a.is_key[i] = a.is_key_l[i];
+  a.is_classed[i] = id != 0;      // min_pts > 0 in the slab path: a labelled point was taken from a nei list (DBImproved.cs:65)
+}
+
+// the own global indices of the owned points (pre-cut mode: rank r's point i is global point gidx0 + i); once per plan
+__global__ void __launch_bounds__(kDbBlock) k_slb_iota(int* lg, int n, int g0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lg[i] = g0 + i;
+}
+
+}  // namespace vpc
