@@ -41,10 +41,46 @@ def _properties(ctx, dx, dy, grid):
     return cid, key, k
 
 
+def _slab_vs_oracle(dx, dy, cid, key, eps=0.07, min_pts=7, frac=0.10):
+    """a ~10M-point u-slab of the C4 cloud against the grid oracle on all host cores.  DBSCAN of a window equals
+    DBSCAN of the whole cloud away from the window's edges: core flags of points at least eps inside, and the partition (canonicalised
+    by minimum point index) of every cluster that keeps 2 eps clear of the edges, must agree bit for bit."""
+    import os
+    import oracle_py
+    u = dx + dy
+    sample = u[:: max(1, u.numel() // 1_000_000)]
+    lo, hi = float(torch.quantile(sample, 0.5 - frac / 2)), float(torch.quantile(sample, 0.5 + frac / 2))
+    idx = torch.nonzero((u >= lo) & (u < hi)).squeeze(1)
+    wx, wy = dx[idx].cpu().numpy(), dy[idx].cpu().numpy()
+    ocid, okey, _, _ = oracle_py.dbscan(wx, wy, eps, min_pts, 0, variant="grid", n_threads=os.cpu_count() or 8)
+    gcid, gkey = cid[idx].cpu().numpy(), key[idx].cpu().numpy()
+    wu = wx + wy
+    inner = (wu >= lo + 1.01 * eps) & (wu < hi - 1.01 * eps)
+    assert inner.sum() > 0.9 * len(wu) * (1 - 4 * eps / (hi - lo))
+    np.testing.assert_array_equal(gkey[inner], okey[inner])                    # core flags
+    # clusters (of either labelling) that come within 2 eps of the window's edges are excluded, the others must be the same sets
+    near = ~((wu >= lo + 2.02 * eps) & (wu < hi - 2.02 * eps))
+    bad_o = np.unique(ocid[near & (ocid > 0)]); bad_g = np.unique(gcid[near & (gcid > 0)])
+    keep = ~np.isin(ocid, bad_o) & ~np.isin(gcid, bad_g)
+    assert keep.sum() > 0.5 * len(wu)
+    a, b = ocid[keep], gcid[keep]
+    np.testing.assert_array_equal(a > 0, b > 0)                                # noise set
+    nz = a > 0
+    first_a = np.full(int(a.max()) + 1, -1, np.int64); first_b = np.full(int(b.max()) + 1, -1, np.int64)
+    pos = np.flatnonzero(nz)
+    first_a[a[pos][::-1]] = pos[::-1]; first_b[b[pos][::-1]] = pos[::-1]       # minimum member position per cluster
+    np.testing.assert_array_equal(first_a[a[pos]], first_b[b[pos]])           # same partition, canonicalised by the minimum point index
+    # numbering: ids ascend with the minimum core index in both (DBImproved.cs:93-110), so the rank order of the kept clusters agrees
+    ua, ub = np.unique(a[nz]), np.unique(b[nz])
+    assert len(ua) == len(ub)
+    np.testing.assert_array_equal(first_a[ua], first_b[ub])
+
+
 @pytest.mark.parametrize("n", [100_000_000])
 def test_c4_100m_order_independence(ctx, n):
     dx, dy, grid = _cloud(n, 0xC4)
     cid, key, k = _properties(ctx, dx, dy, grid)
+    _slab_vs_oracle(dx, dy, cid, key)
     # a permuted copy of the cloud: same partition, same core flags
     perm = torch.randperm(n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
     px, py = dx[perm].contiguous(), dy[perm].contiguous()
@@ -89,3 +125,26 @@ def test_c5_10m_pipeline_properties(ctx):
         m = np.flatnonzero(cid == c)
         for f, v in enumerate((xyz[0], xyz[1], xyz[2], mx, my)):
             assert res.centres[f, c].item() == np.cumsum(v[m])[-1] / len(m)
+
+
+def test_c3_full_size_vs_oracle(ctx):
+    """Config C3 at full size: 100k source vs 1M target, 50 rounds with the convergence test off, against the
+    grid oracle on all host cores: correspondences of the last round index-exact, R / T / SSE (hence RMSE) within 1e-6 relative
+    (ICP.cs:224-250, :126-180)."""
+    import os
+    import oracle_py
+    model, data, _, _ = synth.icp_clouds(0xC3, 1_000_000, 100_000)
+    res = ctx.icp_rigid(model, data, -1.0, 50)
+    Ro, To, itd, sse, oo = oracle_py.icp_rigid(model, data, -1.0, 50, use_grid=True, n_threads=os.cpu_count() or 8)
+    assert res.iters_done == itd == 50
+    np.testing.assert_array_equal(res.order_last, oo)
+    assert np.abs(res.R - Ro).max() <= 1e-6 * np.abs(Ro).max()
+    assert np.abs(res.T - To).max() <= 1e-6 * np.abs(To).max()
+    assert abs(res.sse_last - sse) <= 1e-6 * sse
+    # and the device-resident entry point the bench times
+    dm, dd = torch.from_numpy(model).to(DEV), torch.from_numpy(data).to(DEV)
+    ctx.icp_set_model_dev(dm)
+    state, order = ctx.icp_rigid_dev(dd, -1.0, 50)
+    st = state.cpu().numpy()
+    np.testing.assert_array_equal(order.cpu().numpy(), oo)
+    assert abs(st[12] - sse) <= 1e-6 * sse and int(st[13]) == 50

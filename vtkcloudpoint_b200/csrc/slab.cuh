@@ -44,7 +44,7 @@ struct SlabArgs {
   int* counters;                            // [0..1] halo strip counts, [2] pairs count, [3] ticket
   unsigned long long* epoch;                // step counter (device resident: graph replays advance it)
   int* cid; unsigned char* is_key; unsigned char* is_classed;   // outputs per owned point
-  int* status;                              // [0] cluster_amount, [1] error bits (1 timeout, 2 overflow), [2] halo-in max, [3] pairs, [4] heads (own), [5] epoch
+  int* status;                              // [0] cluster_amount, [1] error bits (1 timeout, 2 overflow), [2] halo-in max, [3] pairs, [4] heads (own), [5] epoch, [6] halo points pulled
 };
 
 __device__ __forceinline__ bool slb_finite(double x, double y) { return finite_d(x) && finite_d(y) && finite_d(x + y) && finite_d(x - y); }
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pull(SlabArgs a) {
   if (j == 0) {   // largest incoming strip (calibration of the capacities)
     const int c0 = a.has_left ? (int)comm_payload(a.P, me - 1, kPhHalo) : 0, c1 = a.has_right ? (int)comm_payload(a.P, me + 1, kPhHalo) : 0;
     a.status[2] = max(c0, c1);
+    a.status[6] = min(c0, a.cap) + min(c1, a.cap);      // halo points pulled over NVLink this step
   }
 }
 
