@@ -34,6 +34,14 @@ DB_GRID, DB_N = 140, 1_000_000            # config C2
 ICP_M, ICP_N, ICP_ITERS = 1_000_000, 100_000, 50   # config C3
 DB_ALGO_BYTES_PER_PT = 21                  # 16 B read + 4 B cluster_id + 1 B is_key
 WORKLOAD_C2 = "C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7"
+
+
+def workload_string(n_gpus: int) -> str:
+    """The same string in both arms (ours and --impl reference) at every N."""
+    if n_gpus <= 1:
+        return WORKLOAD_C2
+    return (f"C2 recipe scaled to {DB_N * n_gpus} points (1M per GPU, weak scaling), ONE cloud clustered exactly (the result of a single "
+            "DBImproved.dbscan over all points), eps 0.07, minPts 7")
 METRIC = "dbscan_mpts_per_s"
 UNIT = "Mpts/s"
 
@@ -136,9 +144,10 @@ def run_reference(args):
     # same workload as our arm at this N: the C2 cloud, or the N x 1M cloud of the multi-GPU run (fewer passes then)
     n_pts = DB_N * max(args.gpus, 1)
     mx, my = synth.dbscan_cloud(0xC2, int(round(DB_GRID * max(args.gpus, 1) ** 0.5)), n_total=n_pts)
-    for _ in range(min(args.warmup, 1)):
+    warmup = max(args.warmup, 3)                     # the same steps / warm-up as our arm at every N
+    for _ in range(warmup):
         cpu_dbscan_pass(oracle, mx, my, cores)
-    times = [cpu_dbscan_pass(oracle, mx, my, cores) for _ in range(args.steps if args.gpus <= 1 else min(args.steps, 3))]
+    times = [cpu_dbscan_pass(oracle, mx, my, cores) for _ in range(args.steps)]
     total = sum(times)
     value = n_pts * len(times) / total / 1e6
     # ICP: bounded sample = 2 of the 50 iterations on the full C3 clouds
@@ -161,9 +170,9 @@ def run_reference(args):
                            f"({cores} threads) and scaled to one full round"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_C2 if args.gpus <= 1 else f"C2 recipe scaled to {n_pts} points (the cloud our arm clusters across {args.gpus} GPUs)",
+        "config": {"workload": workload_string(args.gpus),
                    "arm": "reference algorithm (C++ port of DBImproved.dbscan) on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -227,7 +236,9 @@ def run_ours(args):
         mx, my = fx[band == rank].copy(), fy[band == rank].copy()
         splitters = torch.from_numpy(np.asarray(qs, dtype=np.float64)).to(dev)
         coord_bound = float(np.abs(fu).max() + np.abs(fx - fy).max())
-        del fx, fy, fu, band
+        slab_order = np.argsort(band, kind="stable")          # the whole cloud in slab order = global index order (parity leg)
+        whole_x, whole_y = fx[slab_order], fy[slab_order]
+        del fx, fy, fu, band, slab_order
     n_loc = len(mx)
     n_all = n_loc
     if world > 1:
@@ -241,7 +252,34 @@ def run_ours(args):
                torch.empty(n_loc, dtype=torch.uint8, device=dev), torch.empty(1, dtype=torch.int32, device=dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     backend, plan, graph = None, None, None
-    if world > 1:
+    peer_comm, peer_plan, peer_graph = None, None, None
+
+    def all_ok(flag: bool) -> bool:
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+    if world > 1 and not args.nccl:
+        # the product path: exchanges over NVLink peer memory inside libvpc's own kernels (csrc/slab.cuh), no NCCL / torch op on the step
+        from vtkcloudpoint_b200.peer import GraphedStep, calibrated_slab_plan
+        try:
+            peer_comm, peer_plan = calibrated_slab_plan(ctx, d_x, d_y, counts.tolist(), qs.tolist(), EPS, MIN_PTS, coord_bound, dev)
+            ok = True
+        except Exception as exc:  # noqa: BLE001
+            print(f"rank {rank}: peer-memory slab plan failed ({type(exc).__name__}: {exc}); falling back to the NCCL path", file=sys.stderr, flush=True)
+            ok = False
+        if not all_ok(ok):
+            peer_comm = peer_plan = None
+        elif not args.no_graph:
+            try:
+                peer_graph = GraphedStep(lambda: peer_plan.step(0), dev)
+                ok = True
+            except Exception as exc:  # noqa: BLE001
+                print(f"rank {rank}: CUDA-graph capture of the peer slab step failed ({type(exc).__name__}: {exc}); issuing eagerly", file=sys.stderr, flush=True)
+                ok = False
+            if not all_ok(ok):
+                peer_graph = None
+    if world > 1 and peer_plan is None:
         from vtkcloudpoint_b200.distributed import GpuBackend, calibrated_lean_plan, dbscan_slabs, dbscan_slabs_lean
         backend = GpuBackend(ctx)
         # pre-cut slabs: the sync-free path (fixed-capacity exchange buffers sized by one probe step at plan creation);
@@ -266,6 +304,11 @@ def run_ours(args):
     def step_dev(eager: bool = False):
         if world == 1:
             ctx.dbscan_dev(d_x, d_y, EPS, MIN_PTS, 0, out=out_dev)
+        elif peer_plan is not None:
+            if peer_graph is not None and not eager:
+                peer_graph.replay()
+            else:
+                peer_plan.step(0)
         else:
             if graph is not None and not eager:
                 graph.replay()
@@ -295,9 +338,16 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     if plan is not None and int(plan.overflow.item()) != 0:
         raise SystemExit("slab exchange buffer overflow: enlarge LeanSlabPlan *_frac")
+    if peer_plan is not None and int(peer_plan.status[1].item()) != 0:
+        raise SystemExit(f"peer slab step reported error bits {int(peer_plan.status[1].item())} (1 = a rank timed out, 2 = exchange buffer overflow)")
     launches = ctx.launch_count - launches0
     if graph is not None:
         launches += graph.launches * args.steps          # replayed launches do not pass through the library's counter
+    if peer_graph is not None:
+        l0 = ctx.launch_count
+        peer_plan.step(0)                                # one eager step: the kernels a replay launches
+        launches += (ctx.launch_count - l0) * args.steps
+        torch.cuda.synchronize()
     dev_ms = max_over_ranks(dev_ms)
     value = n_all * args.steps / (dev_ms * 1e-3) / 1e6
 
@@ -312,6 +362,15 @@ def run_ours(args):
     def step_e2e():
         if world == 1:
             ctx.dbscan(hx_np, hy_np, EPS, MIN_PTS, 0, out=res)
+        elif peer_plan is not None:
+            peer_plan.x.copy_(h_x, non_blocking=True); peer_plan.y.copy_(h_y, non_blocking=True)    # the plan's input buffers
+            if peer_graph is not None:
+                peer_graph.replay()
+            else:
+                peer_plan.step(0)
+            r_cid.copy_(peer_plan.cluster_id, non_blocking=True); r_key.copy_(peer_plan.is_key, non_blocking=True)
+            r_cls.copy_(peer_plan.is_classed, non_blocking=True)
+            torch.cuda.synchronize()
         else:
             if graph is not None:
                 d_x.copy_(h_x, non_blocking=True); d_y.copy_(h_y, non_blocking=True)      # the graph's static input buffers
@@ -367,43 +426,95 @@ def run_ours(args):
     # ---- secondary metric: ICP iters/s.  N = 1: config C3 on one GPU.  N > 1 (weak scaling): the model grows to
     # N x 1M points, one shard per GPU; the 100k data points are replicated; exact cross-rank argmin per round.
     icp = None
+    parity = {}
+    nvlink = None
+    ctx2 = None
+    if world > 1:
+        # ---- parity leg (outside every timed region): each rank clusters the WHOLE cloud on its own GPU through the single-GPU entry
+        # point (itself bit-exact vs the oracle at this size: tests/test_dbscan_gpu.py) and compares its slab, element by element
+        ctx2 = Context(local_rank)           # a second context: the plan's workspace (and the captured graph's pointers) stay untouched
+        step_dev()
+        torch.cuda.synchronize()
+        if peer_plan is not None:
+            got = (peer_plan.cluster_id, peer_plan.is_key, peer_plan.is_classed, int(peer_plan.status[0].item()))
+            stv = peer_plan.status.cpu().numpy()
+            halo_pts = torch.tensor([int(stv[6]), int(stv[3])], dtype=torch.int64, device=dev)
+            dist.all_reduce(halo_pts)
+            # halo strips pulled (x, y, global index = 20 B / point) + every rank pulls every other rank's boundary pairs (8 B each)
+            nvlink = {"bytes_per_step_all_ranks": int(halo_pts[0].item()) * 20 + int(halo_pts[1].item()) * 8 * (world - 1),
+                      "halo_points": int(halo_pts[0].item()), "boundary_pairs": int(halo_pts[1].item()),
+                      "how": "counted from the step's own counters: halo points x 20 B + pairs x 8 B x (world - 1) peer loads, plus 3 x world flag words per rank"}
+        elif plan is not None:
+            c_, k_, l_, a_, _ = dbscan_slabs_lean(plan, d_x, d_y, gidx0, MIN_PTS, 0)
+            got = (c_, k_, l_, int(a_.item()))
+        else:
+            c_, k_, l_, a_ = dbscan_slabs(backend, d_x, d_y, gidx0, EPS, MIN_PTS, 0, splitters=splitters)
+            got = (c_, k_, l_, int(a_))
+        wx, wy = torch.from_numpy(whole_x).to(dev), torch.from_numpy(whole_y).to(dev)
+        scid, skey, scls, samount = ctx2.dbscan_dev(wx, wy, EPS, MIN_PTS, 0)
+        sl = slice(gidx0, gidx0 + n_loc)
+        ok = (int(samount.item()) == got[3] and bool((scid[sl] == got[0]).all()) and bool((skey[sl] == got[1]).all()) and bool((scls[sl] == got[2]).all()))
+        parity["dbscan"] = all_ok(ok)
+        parity["dbscan_how"] = f"every rank's slab vs vpc_dbscan_l1_2d_dev of the whole {n_all}-point cloud on one GPU (cluster ids, core flags, isClassed, cluster count): bit-exact"
+        del wx, wy, scid, skey, scls
     if world > 1 and not args.no_icp:
-        from vtkcloudpoint_b200.distributed import GpuIcpBackend, icp_rigid_sharded
-        m_tot = world * ICP_M
-        model, data, _, _ = synth.icp_clouds(0xC3, m_tot, ICP_N, box=100.0 * world ** (1.0 / 3.0))
-        a_, b_ = m_tot * rank // world, m_tot * (rank + 1) // world
-        dm = torch.from_numpy(np.ascontiguousarray(model[:, a_:b_])).to(dev)
-        dd = torch.from_numpy(data).to(dev)
-        ibe = GpuIcpBackend(ctx)
-        igraph = None
-        if not args.no_graph:
-            from vtkcloudpoint_b200.distributed import IcpShardedGraph
-            ok = torch.ones(1, dtype=torch.int32, device=dev)
-            try:
-                igraph = IcpShardedGraph(ibe, dm, a_, dd, -1.0, ICP_ITERS)
-            except Exception as exc:  # noqa: BLE001
-                print(f"rank {rank}: CUDA-graph capture of the sharded ICP failed ({type(exc).__name__}: {exc}); issuing eagerly", file=sys.stderr, flush=True)
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                igraph = None
-        run_icp = (lambda: igraph.replay()) if igraph is not None else (lambda: icp_rigid_sharded(ibe, dm, a_, dd, -1.0, ICP_ITERS))
-        for _ in range(2):
-            run_icp()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        state, _ = run_icp()
-        e1.record()
-        barrier()
-        icp_ms = max_over_ranks(e0.elapsed_time(e1))
+        from vtkcloudpoint_b200.peer import GraphedStep, IcpDistPlan, PeerComm
+        icp = {"metric": "icp_iters_per_s", "unit": "iters/s"}
+        for mode, m_tot, tag in ((0, world * ICP_M, "target_sharded_weak"), (1, ICP_M, "source_sharded_strong")):
+            model, data, _, _ = synth.icp_clouds(0xC3, m_tot, ICP_N, box=100.0 * (m_tot / ICP_M) ** (1.0 / 3.0))
+            a_, b_ = (m_tot * rank // world, m_tot * (rank + 1) // world) if mode == 0 else (0, m_tot)
+            dm = torch.from_numpy(np.ascontiguousarray(model[:, a_:b_])).to(dev)
+            dd = torch.from_numpy(data).to(dev)
+            icomm = PeerComm.connected(ctx, IcpDistPlan.heap_bytes(ctx._lib, world, ICP_N), dev)
+            ctx.icp_set_model_dev(dm)
+            ip = IcpDistPlan(icomm, mode, dd, a_)
+            run_icp = lambda: ip.run(-1.0, ICP_ITERS)        # noqa: E731
+            igraph = None
+            if not args.no_graph:
+                try:
+                    igraph = GraphedStep(run_icp, dev)
+                    ok = True
+                except Exception as exc:  # noqa: BLE001
+                    print(f"rank {rank}: CUDA-graph capture of the ICP loop failed ({type(exc).__name__}: {exc}); issuing eagerly", file=sys.stderr, flush=True)
+                    ok = False
+                if not all_ok(ok):
+                    igraph = None
+            fn = igraph.replay if igraph is not None else run_icp
+            for _ in range(2):
+                fn()
+            reps = 3
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                state, order = fn()
+            e1.record()
+            barrier()
+            icp_ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+            # parity: the same registration on ONE GPU (whole target), correspondences index-exact, state within 1e-6 relative
+            wm = torch.from_numpy(model).to(dev)
+            ctx2.icp_set_model_dev(wm)
+            sstate, sorder = ctx2.icp_rigid_dev(dd, -1.0, ICP_ITERS)
+            torch.cuda.synchronize()
+            sv, gv = sstate.cpu().numpy(), state.cpu().numpy()
+            ok = (bool((sorder == order).all()) and int(gv[13]) == int(sv[13]) and float(np.abs(gv[:12] - sv[:12]).max()) <= 1e-6 * max(1.0, float(np.abs(sv[:12]).max()))
+                  and abs(gv[12] - sv[12]) <= 1e-6 * sv[12] and icomm.error_bits() == 0)
+            parity["icp_" + tag] = all_ok(ok)
+            icp[tag] = {"value": ICP_ITERS / (icp_ms * 1e-3), "ms_per_iter": icp_ms / ICP_ITERS, "rmse_last": float(np.sqrt(gv[12] / ICP_N)),
+                        "workload": (f"C3 recipe, target of {m_tot} points cut into {world} index shards (1M per GPU), 100k data points on every GPU" if mode == 0 else
+                                     f"C3 itself (100k source vs 1M target), the SOURCE cut into {world} slices, target on every GPU") +
+                                    f", {ICP_ITERS} rounds, fp64, per round: NN + peer-memory exchange + replicated solve, no NCCL call" +
+                                    ("; replayed as one CUDA graph" if igraph is not None else "")}
+            del igraph, fn, run_icp, wm
+            ip.close(); icomm.close()
+        icp["value"] = icp["target_sharded_weak"]["value"]
+        icp["workload"] = icp["target_sharded_weak"]["workload"]
+        parity["icp_how"] = "correspondences of the last round index-exact and R, T, SSE within 1e-6 relative vs vpc_icp_rigid_dev on one GPU with the whole target"
+    if world > 1 and not all(v for k, v in parity.items() if not k.endswith("_how")):     # identical on every rank (all_ok)
         if rank == 0:
-            stv = state.cpu().numpy()
-            icp = {"metric": "icp_iters_per_s", "value": ICP_ITERS / (icp_ms * 1e-3), "unit": "iters/s",
-                   "workload": f"C3 recipe, model sharded over {world} GPUs ({m_tot} points, 1M per GPU), 100k data points replicated, 50 iterations, fp64; "
-                               "includes one model cell-list build per run" + ("; the loop is replayed as one CUDA graph" if igraph is not None else ""),
-                   "ms_per_iter": icp_ms / ICP_ITERS,
-                   "rmse_last": float(np.sqrt(stv[12] / ICP_N))}
+            print(json.dumps({"error": "multi-GPU result differs from the single-GPU result", "parity": parity}), flush=True)
+        sys.stdout.flush()
+        os._exit(3)
     if world == 1 and rank == 0 and not args.no_icp:
         model, data, _, _ = synth.icp_clouds(0xC3, ICP_M, ICP_N)
         hm, hd = torch.from_numpy(model).pin_memory(), torch.from_numpy(data).pin_memory()
@@ -453,10 +564,12 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": (WORKLOAD_C2 if world == 1 else
-                                    f"C2 recipe scaled to {n_all} points (1M per GPU), one cloud clustered exactly across {world} GPUs: u-slabs + 2*eps halo exchange + cross-slab union-find merge (NCCL)"),
-                       "points_total": n_all, "points_per_gpu": DB_N, "parallelism": (f"{world} spatial slabs, one process per GPU, step replayed as one CUDA graph" if graph is not None else
-                                       f"{world} spatial slabs, one process per GPU") if world > 1 else "single GPU",
+            "config": {"workload": workload_string(world),
+                       "points_total": n_all, "points_per_gpu": DB_N,
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"{world} u-slabs (one process per GPU), 2*eps halo strips + boundary component keys + cluster-head counts exchanged " +
+                                       ("over NVLink peer memory by libvpc's own kernels (no NCCL / torch op on the step)" if peer_plan is not None else "with NCCL") +
+                                       ("; step replayed as one CUDA graph" if (peer_graph is not None or graph is not None) else "")),
                        "l2": "flushed between timed steps (256 MiB write)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_all, "d2h_bytes_per_step": 6 * n_all + 4 * (world == 1),
@@ -468,6 +581,9 @@ def run_ours(args):
             "secondary": icp,
             "kernel_ms_per_step": kernels,
         }
+        if world > 1:
+            line["parity"] = parity
+            line["nvlink"] = nvlink
         print(json.dumps(line), flush=True)
     # teardown: release the captured graph (it holds NCCL work) before the communicator goes away, and never let a stuck
     # teardown keep the job alive after the result line is out
@@ -475,9 +591,13 @@ def run_ours(args):
     threading.Timer(30.0, lambda: os._exit(0)).start() if world > 1 else None
     graph = None
     plan = None
-    igraph = run_icp = None       # noqa: F841  (captured graphs hold NCCL work)
+    peer_graph = None             # noqa: F841
     torch.cuda.synchronize()
     barrier()
+    if peer_plan is not None:
+        peer_plan.close(); peer_comm.close()
+    if ctx2 is not None:
+        ctx2.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -494,6 +614,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-literal", action="store_true", help="reference arm: skip the Theta(n^2) literal timings")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: issue the slab step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: the NCCL-based slab path of round 1 instead of the peer-memory path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -18,10 +18,16 @@ LIB = HERE / "libvpc_oracle.so"
 
 def build(force: bool = False) -> Path:
     srcs = [HERE / "vpc_oracle.cpp", HERE / "vpc_oracle_stats.cpp", HERE / "vpc_oracle_aswritten.cpp", HERE / "vpc_oracle_blocked.cpp", HERE / "vpc_oracle.h"]
-    if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
+    import hashlib
+    h = hashlib.sha256()
+    for src in srcs + [HERE / "Makefile"]:
+        h.update(src.read_bytes())
+    stamp = HERE / "libvpc_oracle.so.stamp"           # contents, not file times: those do not survive a snapshot copy
+    if force or not LIB.exists() or not stamp.exists() or stamp.read_text().strip() != h.hexdigest():
         res = subprocess.run(["make", "-C", str(HERE), "-B", "libvpc_oracle.so"], capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+        stamp.write_text(h.hexdigest())
     return LIB
 
 

@@ -27,11 +27,23 @@ def _sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "vpc.h"]
 
 
+def _fingerprint() -> str:
+    """Hash of every source and of the flags.  File times do not survive a snapshot copy (the GPU box would rebuild a fresh
+    library, once per rank and at the same time), contents do."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + os.environ.get("VPC_NVCC_EXTRA", "").split()).encode())
+    for src in _sources() + sorted((CSRC / "host").glob("*.hpp")):
+        h.update(src.name.encode()); h.update(src.read_bytes())
+    return h.hexdigest()
+
+
+STAMP = PKG / "libvpc.so.stamp"
+
+
 def stale() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not STAMP.exists():
         return True
-    t = LIB.stat().st_mtime
-    return any(s.stat().st_mtime > t for s in _sources())
+    return STAMP.read_text().strip() != _fingerprint()
 
 
 def nvcc_path() -> str:
@@ -45,13 +57,15 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
     extra = os.environ.get("VPC_NVCC_EXTRA", "").split()      # developer knob for A/B builds (e.g. -DVPC_ICP_ITER_BLOCK=128)
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(LIB) + ".tmp", str(CSRC / "vpc_api.cu")]
+    tmp = f"{LIB}.{os.getpid()}.tmp"                            # several ranks may build at once: no shared temporary
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", tmp, str(CSRC / "vpc_api.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    os.replace(str(LIB) + ".tmp", LIB)
+    os.replace(tmp, LIB)
+    STAMP.write_text(_fingerprint())
     if verbose:
         print(res.stderr)
     return LIB

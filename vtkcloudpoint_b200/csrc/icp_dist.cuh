@@ -54,7 +54,7 @@ __device__ __forceinline__ bool icpd_block_reduce(const double (&s)[kIcpSums], d
 #pragma unroll
     for (int w = 0; w < kIterBlock / kWarp; ++w) v += sm[threadIdx.x][w];
     partial[(long long)blockIdx.x * kIcpSums + threadIdx.x] = v;
-    __threadfence();
+    __threadfence_system();         // system scope: the block's peer stores (winners into everybody's order[]) precede the ticket too
   }
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -92,7 +92,7 @@ __device__ __forceinline__ void icpd_push_sums(const IcpDistArgs& a, const doubl
     double* dst = a.P.at<double>(q, a.L.sums) + ((E & 1) * a.P.world + a.P.rank) * kIcpSums + k;
     *dst = S[k];
   }
-  __threadfence_system();
+  __threadfence_system();           // every storing thread orders its own peer store before the flags (last block only: cheap)
   __syncthreads();
   if ((int)threadIdx.x < a.P.world) comm_signal(a.P, (int)threadIdx.x, kPhIcpSums, E, 0ull);
 }
@@ -123,13 +123,15 @@ __global__ void __launch_bounds__(kIterBlock) k_icpd_nn_push(IcpModel g, const d
     a.P.at<double>(owner, a.L.cand_y[1])[slot] = b.y;
     a.P.at<double>(owner, a.L.cand_y[2])[slot] = b.z;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();                  // one system fence per block, after the block barrier (see slab.cuh)
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
-  if (threadIdx.x == 0) *a.ticket = 0;
+  if (threadIdx.x == 0) { __threadfence_system(); *a.ticket = 0; }
+  __syncthreads();
   if ((int)threadIdx.x < a.P.world) comm_signal(a.P, (int)threadIdx.x, kPhIcpNn, E, 0ull);
 }
 

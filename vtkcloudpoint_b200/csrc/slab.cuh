@@ -68,9 +68,11 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a) {
   const int me = a.P.rank;
   if (sl >= 0 && sl < a.cap) { a.P.at<double>(me, a.L.pack_x[0])[sl] = xi; a.P.at<double>(me, a.L.pack_y[0])[sl] = yi; a.P.at<int>(me, a.L.pack_g[0])[sl] = a.lg[i]; }
   if (sr >= 0 && sr < a.cap) { a.P.at<double>(me, a.L.pack_x[1])[sr] = xi; a.P.at<double>(me, a.L.pack_y[1])[sr] = yi; a.P.at<int>(me, a.L.pack_g[1])[sr] = a.lg[i]; }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block,
+  if (threadIdx.x == 0) {           // a system-scope fence in every thread costs ~40 us per kernel at 1M points
+    __threadfence_system();
+    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
   __threadfence_system();
@@ -131,9 +133,11 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_pairs_pack(SlabArgs a, DbArgs 
   const int me = a.P.rank;
   const int s = db_append_slot(want, a.counters + 2);
   if (s >= 0 && s < a.cap_pairs) a.P.at<int2>(me, a.L.pairs)[s] = make_int2(g, key);
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block,
+  if (threadIdx.x == 0) {           // a system-scope fence in every thread costs ~40 us per kernel at 1M points
+    __threadfence_system();
+    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
   __threadfence_system();
@@ -186,9 +190,11 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
       atomicOr_system(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5), 1u << (w & 31));
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block,
+  if (threadIdx.x == 0) {           // a system-scope fence in every thread costs ~40 us per kernel at 1M points
+    __threadfence_system();
+    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
   __threadfence_system();
@@ -197,35 +203,32 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
 }
 
 // ---- one block: wait for everybody's bits, popc-scan the own bitmap, publish the own head count (and error bits) ----------
+// thread t owns a contiguous span of words: popc-sum of the span, one block scan of the 1024 sums, then the running ranks
 constexpr int kHeadsRankBlock = 1024;
 __global__ void __launch_bounds__(kHeadsRankBlock) k_slb_heads_rank(SlabArgs a) {
   __shared__ int s_warp[kHeadsRankBlock / kWarp];
-  __shared__ int s_carry;
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
   comm_wait_all_block(a.P, kPhHeads, E);
   const unsigned* bits = a.P.at<unsigned>(me, a.L.bits[E & 1]);
   int* rank = a.P.at<int>(me, a.L.rank);
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
+  const int span = (a.nwords + kHeadsRankBlock - 1) / kHeadsRankBlock;
+  const int w0 = min(threadIdx.x * span, a.nwords), w1 = min(w0 + span, a.nwords);
+  int sum = 0;
+  for (int w = w0; w < w1; ++w) sum += __popc(__ldcg(bits + w));      // L2 loads: remote atomics land there, never trust L1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < a.nwords; base += kHeadsRankBlock) {
-    const int w = base + threadIdx.x;
-    const int v = (w < a.nwords) ? __popc(ld_relaxed_sys_u32(bits + w)) : 0;   // remote atomics land in L2: do not trust L1
-    int incl = v;
+  int incl = sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    int off = s_carry;
-    for (int k = 0; k < warp; ++k) off += s_warp[k];
-    if (w < a.nwords) rank[w] = off + incl - v;
-    __syncthreads();
-    if (threadIdx.x == kHeadsRankBlock - 1) s_carry = off + incl;
-    __syncthreads();
-  }
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < kHeadsRankBlock / kWarp; ++k) { const int v = s_warp[k]; if (k < warp) off += v; total += v; }
+  int run = off + incl - sum;
+  for (int w = w0; w < w1; ++w) { rank[w] = run; run += __popc(__ldcg(bits + w)); }
+  __syncthreads();
   if (threadIdx.x != 0) return;
-  const int total = s_carry;
   a.status[4] = total;
   __threadfence_system();
   const unsigned long long err = (unsigned long long)(unsigned)atomicOr(&a.P.hdr(me)->error, 0);
