@@ -101,7 +101,9 @@ class VpcError(RuntimeError):
 
 @lru_cache(maxsize=None)
 def lib() -> C.CDLL:
-    path = _build.build_lib()          # raises if nvcc is missing or the build fails
+    import os
+    alt = os.environ.get("VPC_LIB")    # developer knob: an A/B build of the same sources (tools/ab_build.py)
+    path = alt if alt else _build.build_lib()          # raises if nvcc is missing or the build fails
     dll = C.CDLL(str(path))            # raises OSError if the library cannot be loaded
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(dll, name)        # AttributeError if a declared symbol is not exported

@@ -104,7 +104,13 @@ struct DbArgs {
   int* cluster_amount;  // nullable
 };
 
-constexpr int kDbBlock = 256;
+#ifndef VPC_DB_BLOCK
+#define VPC_DB_BLOCK 256
+#endif
+#ifndef VPC_COUNT_MINB
+#define VPC_COUNT_MINB 1
+#endif
+constexpr int kDbBlock = VPC_DB_BLOCK;
 constexpr int kNbrCap = 8;   // one 32-byte sector of neighbour positions per non-core point
 constexpr int kNone = 0x7fffffff;
 
@@ -446,7 +452,7 @@ __device__ __forceinline__ int db_block_compact(bool want, int item, int* s_list
 
 // ---- k_db_count: region query -> core flag (isKeyPoint, DBImproved.cs:33-54) ------------------
 // Only points outside dense cells (core[] == 2) still need a count; they are compacted per block.
-__global__ void __launch_bounds__(kDbBlock) k_db_count(DbArgs a) {
+__global__ void __launch_bounds__(kDbBlock, VPC_COUNT_MINB) k_db_count(DbArgs a) {
   __shared__ int s_list[kDbBlock];
   __shared__ int s_cnt[kDbBlock / kWarp];
   const int p0 = blockIdx.x * blockDim.x + threadIdx.x;

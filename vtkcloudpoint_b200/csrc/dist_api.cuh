@@ -212,7 +212,7 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   long long slots = 1024;
   while (slots < 2ll * W * cap_pairs) slots <<= 1;
   p->table_slots = slots; p->table_bytes = 16ull * slots;
-  const size_t bytes = al256(8 * nl) * 2 + al256(4 * nl) * 2 + al256(nl) + al256(4 * no) + al256(no) * 2 + al256(64) * 3 + al256(p->table_bytes) + 4096;
+  const size_t bytes = al256(8 * nl) * 2 + al256(4 * nl) * 2 + al256(nl) + al256(4 * no) + al256(no) * 2 + al256(64) * 3 + al256(4ull * cap_pairs) + al256(p->table_bytes) + 4096;
   void* base = nullptr;
   if (cudaMalloc(&base, bytes) != cudaSuccess) { (void)cudaGetLastError(); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_NOMEM, "cudaMalloc of the slab buffers failed"); }
   cudaMemset(base, 0, bytes);
@@ -221,6 +221,7 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   a.lx = w.take<double>(nl); a.ly = w.take<double>(nl); a.lg = w.take<int>(nl); a.gkey = w.take<int>(nl); a.is_key_l = w.take<unsigned char>(nl);
   a.cid = w.take<int>(no); a.is_key = w.take<unsigned char>(no); a.is_classed = w.take<unsigned char>(no);
   a.counters = w.take<int>(16); a.epoch = w.take<unsigned long long>(8); a.status = w.take<int>(16);
+  a.pair_root = w.take<int>(cap_pairs);
   p->table = w.take<char>(p->table_bytes);
   k_slb_iota<<<blocks_for(a.n_own, kDbBlock), kDbBlock, 0, ctx->own_stream>>>(a.lg, a.n_own, a.gstart[me]);
   if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) { cudaFree(base); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_CUDA, "slab plan initialisation failed"); }
@@ -274,7 +275,7 @@ int vpc_slab_step_phase_dev(vpc_slab_plan* p, int32_t phase, int32_t first_clust
         t.mask = (unsigned)(p->table_slots - 1);
         VPC_CUDA(ctx, cudaMemsetAsync(p->table, 0xff, p->table_bytes, s));
         VPC_LAUNCH(ctx, k_slb_merge, blocks_for((long long)W * a.cap_pairs, kDbBlock), kDbBlock, s, a, t);
-        VPC_LAUNCH(ctx, k_db_remap_roots_table, gl, kDbBlock, s, d, t);
+        VPC_LAUNCH(ctx, k_slb_rekey, blocks_for(a.cap_pairs, kDbBlock), kDbBlock, s, a, d, t);
       }
       VPC_LAUNCH(ctx, k_db_resolve, gl, kDbBlock, s, d);
       ctx->db_slab_valid = false;

@@ -42,6 +42,7 @@ struct SlabArgs {
   double* lx; double* ly; int* lg;          // local cloud: n_own owned points, then halo slots
   unsigned char* is_key_l; int* gkey;       // per local point: core flag, merged cluster key
   int* counters;                            // [0..1] halo strip counts, [2] pairs count, [3] ticket
+  int* pair_root;                           // [cap_pairs] sorted position of the local root behind every pair this rank reported
   unsigned long long* epoch;                // step counter (device resident: graph replays advance it)
   int* cid; unsigned char* is_key; unsigned char* is_classed;   // outputs per owned point
   int* status;                              // [0] cluster_amount, [1] error bits (1 timeout, 2 overflow), [2] halo-in max, [3] pairs, [4] heads (own), [5] epoch, [6] halo points pulled
@@ -68,10 +69,10 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a) {
   const int me = a.P.rank;
   if (sl >= 0 && sl < a.cap) { a.P.at<double>(me, a.L.pack_x[0])[sl] = xi; a.P.at<double>(me, a.L.pack_y[0])[sl] = yi; a.P.at<int>(me, a.L.pack_g[0])[sl] = a.lg[i]; }
   if (sr >= 0 && sr < a.cap) { a.P.at<double>(me, a.L.pack_x[1])[sr] = xi; a.P.at<double>(me, a.L.pack_y[1])[sr] = yi; a.P.at<int>(me, a.L.pack_g[1])[sr] = a.lg[i]; }
-  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block,
-  if (threadIdx.x == 0) {           // a system-scope fence in every thread costs ~40 us per kernel at 1M points
-    __threadfence_system();
-    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block.
+  if (threadIdx.x == 0) {           // The stores are to the OWN heap (peers pull them through this GPU's L2): device scope is enough
+    __threadfence();                // here; the last block's system fence + st.release.sys publish.  (A system fence per thread cost
+    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);   // ~40 us per kernel at 1M points, one per block still ~20 us.)
   }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
@@ -122,21 +123,21 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_pairs_pack(SlabArgs a, DbArgs 
   __shared__ bool s_last;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   bool want = false;
-  int key = -1, g = -1;
+  int key = -1, g = -1, root = -1;
   if (p < d.ctrl->n_valid && d.core[p] == 1) {
     const DbRec* r = d.rec + p;
     const int i = r->sidx;
     bool cand = i >= a.n_own;                                         // a halo copy: its owner reports it too
     if (!cand) { const double2 xy = db_xy(d.rec, p); const double u = xy.x + xy.y; cand = (a.has_left && (u - a.H < a.s_lo)) || (a.has_right && (u + a.H >= a.s_hi)); }
-    if (cand) { want = true; key = d.rec[r->parent].cinfo.y; g = a.lg[i]; }
+    if (cand) { want = true; root = r->parent; key = d.rec[root].cinfo.y; g = a.lg[i]; }
   }
   const int me = a.P.rank;
   const int s = db_append_slot(want, a.counters + 2);
-  if (s >= 0 && s < a.cap_pairs) a.P.at<int2>(me, a.L.pairs)[s] = make_int2(g, key);
-  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block,
-  if (threadIdx.x == 0) {           // a system-scope fence in every thread costs ~40 us per kernel at 1M points
-    __threadfence_system();
-    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
+  if (s >= 0 && s < a.cap_pairs) { a.P.at<int2>(me, a.L.pairs)[s] = make_int2(g, key); a.pair_root[s] = root; }
+  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block.
+  if (threadIdx.x == 0) {           // The stores are to the OWN heap (peers pull them through this GPU's L2): device scope is enough
+    __threadfence();                // here; the last block's system fence + st.release.sys publish.  (A system fence per thread cost
+    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);   // ~40 us per kernel at 1M points, one per block still ~20 us.)
   }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
@@ -166,6 +167,16 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_merge(SlabArgs a, MergeTables 
   if (first != -1 && first != sk) mg_unite(t, sk, first);
 }
 
+// every local root behind a pair this rank reported takes the minimum key of its merged set (the other roots kept theirs: their
+// components touch no slab boundary).  Pairs of one component store the same value: benign.
+__global__ void __launch_bounds__(kDbBlock) k_slb_rekey(SlabArgs a, DbArgs d, MergeTables t) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= min(a.status[3], a.cap_pairs)) return;
+  const int2 gk = a.P.at<int2>(a.P.rank, a.L.pairs)[q];
+  const int s = mg_lookup(t.k_key, t.mask, gk.y);
+  if (s >= 0) d.rec[a.pair_root[q]].cinfo.y = ld_relaxed_s32(t.k_key + mg_find(t.k_par, s));
+}
+
 __device__ __forceinline__ int slb_home_of(const SlabArgs& a, int g) {   // rank q with gstart[q] <= g < gstart[q+1]
   int q = 0;
 #pragma unroll 1
@@ -182,17 +193,19 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned* other = a.P.at<unsigned>(me, a.L.bits[(E + 1) & 1]);
   for (int w = i; w < a.nwords; w += gridDim.x * blockDim.x) other[w] = 0u;
+  int remote = 0;
   if (i < a.n_own && a.is_key_l[i]) {
     const int g = a.lg[i];
     if (g >= 0 && a.gkey[i] == g) {
       const int home = slb_home_of(a, g);
       const int w = g - a.gstart[home];
+      remote = home != me;
       atomicOr_system(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5), 1u << (w & 31));
     }
   }
-  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block,
-  if (threadIdx.x == 0) {           // a system-scope fence in every thread costs ~40 us per kernel at 1M points
-    __threadfence_system();
+  const int any_remote = __syncthreads_or(remote);   // blocks that touched a peer's bitmap order those atomics at system scope
+  if (threadIdx.x == 0) {
+    if (any_remote) __threadfence_system(); else __threadfence();
     s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
