@@ -56,6 +56,16 @@ int64_t vpc_launch_count(const vpc_ctx* ctx);
 int vpc_profile_enable(vpc_ctx* ctx, int on);
 int64_t vpc_profile_report(vpc_ctx* ctx, char* buf, int64_t cap);
 
+/* Host memory.  The host-pointer exports accept ANY host memory.  Pageable arrays -- what the .NET marshaller passes for a
+ * double[] argument: pinned against the GC for the call, but not page-locked -- are moved by worker threads through a page-locked
+ * ring inside the context (csrc/host/staging.hpp; VPC_COPY_THREADS sets the thread count, 0 = plain cudaMemcpy).  Arrays that are
+ * page-locked (allocated with vpc_host_alloc, or registered once with vpc_host_register) are copied directly at the PCIe rate:
+ * a shim that keeps its flattened coordinate arrays between calls should use those. */
+int vpc_host_alloc(void** out, int64_t bytes);
+void vpc_host_free(void* p);
+int vpc_host_register(void* p, int64_t bytes);
+int vpc_host_unregister(void* p);
+
 /* ---- DBSCAN --------------------------------------------------------------------- */
 
 /* Replaces `new DBImproved{cf = first_cluster_id}.dbscan(lst, e, minPts)`

@@ -56,17 +56,21 @@ class IcpResult:
 
 
 class Context:
-    """One vpc_ctx = one GPU.  Raises VpcError when no CUDA device is usable."""
+    """One vpc_ctx.  device = an int: one GPU.  device = a list of ints: ONE context driving several GPUs from this process
+    (vpc_create with n_devices > 1): the host-array calls dbscan() / icp_rigid() are then spread over those devices inside the
+    library (csrc/group_api.cuh); everything else runs on the first one.  Raises VpcError when no CUDA device is usable."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self._lib = capi.lib()
         self._h = C.c_void_p()
-        ids = (C.c_int * 1)(device)
-        rc = self._lib.vpc_create(C.byref(self._h), ids, 1)
+        devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        ids = (C.c_int * len(devs))(*devs)
+        rc = self._lib.vpc_create(C.byref(self._h), ids, len(devs))
         if rc != capi.VPC_OK:
             self._h = C.c_void_p()
             raise capi.VpcError(rc, "vpc_create failed (no CPU fallback exists)")
-        self.device = device
+        self.device = devs[0]
+        self.devices = devs
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

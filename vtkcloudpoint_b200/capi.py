@@ -29,6 +29,10 @@ SIGNATURES = {
     "vpc_launch_count": (_i64, [_p]),
     "vpc_profile_enable": (C.c_int, [_p, C.c_int]),
     "vpc_profile_report": (_i64, [_p, C.c_char_p, _i64]),
+    "vpc_host_alloc": (C.c_int, [C.POINTER(_p), _i64]),
+    "vpc_host_free": (None, [_p]),
+    "vpc_host_register": (C.c_int, [_p, _i64]),
+    "vpc_host_unregister": (C.c_int, [_p]),
     "vpc_dbscan_l1_2d": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p]),
     "vpc_dbscan_l1_2d_dev": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p, _p]),
     "vpc_dbscan_l1_2d_cells": (C.c_int, [_p, _p, _p, _i64, _p, _i32, _f64, _i32, _p, _p, _p, _p]),

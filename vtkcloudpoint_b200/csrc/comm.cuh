@@ -29,6 +29,8 @@ struct HeapHeader {                              // offset 0 of every heap
   unsigned long long word[kPhases][kMaxWorld];   // a small payload that travels with the flag (counts)
   int error;                                     // != 0: a bounded spin gave up (bit 0) / an exchange buffer overflowed (bit 1)
   int pad[15];
+  unsigned long long epoch[8];                   // step counters of the heap's OWNER ([0] slab DBSCAN, [1] ICP): they live with the flags, so
+                                                 // every plan ever created on this heap continues the same monotone sequence
 };
 constexpr size_t kHeapHeaderBytes = (sizeof(HeapHeader) + 255) & ~size_t(255);
 

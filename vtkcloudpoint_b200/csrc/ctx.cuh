@@ -6,12 +6,15 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "dbscan.cuh"
 #include "icp.cuh"
+#include "host/staging.hpp"
 
 using namespace vpc;
 
@@ -62,6 +65,12 @@ struct vpc_ctx {
   bool profile = false;
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
+  // pageable caller memory: worker threads + a page-locked ring (host/staging.hpp); created on first use
+  vpc_host::CopyPool* pool = nullptr;
+  bool pool_tried = false;
+  vpc_host::Stager stager;
+  // single-process multi-GPU mode (vpc_create with n_devices > 1): one sub-context per rank, see group_api.cuh
+  struct vpc_group* group = nullptr;
 };
 
 namespace {
@@ -92,6 +101,18 @@ namespace {
       return VPC_E_CUDA;                                                                     \
     }                                                                                        \
   } while (0)
+
+// worker threads for pageable host memory: VPC_COPY_THREADS (0 = plain cudaMemcpyAsync), default = half the cores, 2..8
+vpc_host::CopyPool* ctx_pool(vpc_ctx* ctx) {
+  if (!ctx->pool_tried) {
+    ctx->pool_tried = true;
+    int t = (int)std::thread::hardware_concurrency() / 2;
+    t = t < 2 ? 2 : (t > 8 ? 8 : t);
+    if (const char* e = std::getenv("VPC_COPY_THREADS")) t = std::atoi(e);
+    if (t > 0) ctx->pool = new (std::nothrow) vpc_host::CopyPool(t);
+  }
+  return ctx->pool;
+}
 
 int fail(vpc_ctx* ctx, int code, const char* msg) {
   if (ctx) ctx->err = msg;

@@ -48,9 +48,59 @@ struct vpc_icp_dist {
   IcpDistArgs a{};
   int mode = 0;                     // 0 target sharded, 1 source sharded
   const double* d_data = nullptr;
-  unsigned long long* epoch = nullptr;
   size_t heap_mark = 0;
 };
+
+namespace {
+
+// The slab step's phases on one rank (slab.cuh).  precut: the rank's slab is already in a.lx / a.ly and the halo strips come from the
+// neighbours (phases 0 and 1); otherwise the local cloud was delivered by k_gen_scatter (gen.cuh) and phase 1 starts at the clustering.
+int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps, int min_pts, void* table, size_t table_bytes, long long table_slots,
+                       int phase, bool precut, cudaStream_t s) {
+  const int W = a.P.world;
+  const int g_own = blocks_for(a.n_own, kDbBlock);
+  switch (phase) {
+    case 0:
+      if (precut) VPC_LAUNCH(ctx, k_slb_halo_pack, g_own, kDbBlock, s, a);
+      break;
+    case 1: {
+      if (precut) VPC_LAUNCH(ctx, k_slb_halo_pull, blocks_for(2ll * a.cap, kDbBlock), kDbBlock, s, a);
+      int rc = dbscan_enqueue(ctx, a.lx, a.ly, n_local, eps, min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg,
+                              nullptr, true);
+      if (rc) return rc;
+      if (W > 1) VPC_LAUNCH(ctx, k_slb_pairs_pack, blocks_for(n_local, kDbBlock), kDbBlock, s, a, ctx->db_slab);
+      break;
+    }
+    case 2: {
+      if (!ctx->db_slab_valid || ctx->db_slab.n != n_local) return fail(ctx, VPC_E_STATE, "phase 1 must be the previous DBSCAN call on this context");
+      DbArgs d = ctx->db_slab;
+      d.compkey = a.gkey;
+      const int gl = blocks_for(n_local, kDbBlock);
+      VPC_CUDA(ctx, cudaMemsetAsync(a.gkey, 0xff, 4ull * n_local, s));      // points outside the grid (NaN padding, non-finite input): noise
+      if (W > 1) {
+        MergeTables t{};
+        t.g_key = static_cast<int*>(table); t.g_val = t.g_key + table_slots; t.k_key = t.g_val + table_slots; t.k_par = t.k_key + table_slots;
+        t.mask = (unsigned)(table_slots - 1);
+        VPC_CUDA(ctx, cudaMemsetAsync(table, 0xff, table_bytes, s));
+        VPC_LAUNCH(ctx, k_slb_merge, blocks_for((long long)W * a.cap_pairs, kDbBlock), kDbBlock, s, a, t);
+        VPC_LAUNCH(ctx, k_slb_rekey, blocks_for(a.cap_pairs, kDbBlock), kDbBlock, s, a, d, t);
+      }
+      VPC_LAUNCH(ctx, k_db_resolve, gl, kDbBlock, s, d);
+      ctx->db_slab_valid = false;
+      VPC_LAUNCH(ctx, k_slb_heads, g_own, kDbBlock, s, a);
+      break;
+    }
+    case 3:
+      VPC_LAUNCH(ctx, k_slb_heads_rank, 1, kHeadsRankBlock, s, a);
+      break;
+    case 4:
+      VPC_LAUNCH(ctx, k_slb_ids, g_own, kDbBlock, s, a);
+      break;
+  }
+  return VPC_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -220,7 +270,8 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   Arena w; w.base = p->local; w.cap = bytes;
   a.lx = w.take<double>(nl); a.ly = w.take<double>(nl); a.lg = w.take<int>(nl); a.gkey = w.take<int>(nl); a.is_key_l = w.take<unsigned char>(nl);
   a.cid = w.take<int>(no); a.is_key = w.take<unsigned char>(no); a.is_classed = w.take<unsigned char>(no);
-  a.counters = w.take<int>(16); a.epoch = w.take<unsigned long long>(8); a.status = w.take<int>(16);
+  a.counters = w.take<int>(16); a.status = w.take<int>(16);
+  a.epoch = &reinterpret_cast<HeapHeader*>(comm->heap)->epoch[0];
   a.pair_root = w.take<int>(cap_pairs);
   p->table = w.take<char>(p->table_bytes);
   k_slb_iota<<<blocks_for(a.n_own, kDbBlock), kDbBlock, 0, ctx->own_stream>>>(a.lg, a.n_own, a.gstart[me]);
@@ -246,50 +297,9 @@ int vpc_slab_step_phase_dev(vpc_slab_plan* p, int32_t phase, int32_t first_clust
   vpc_ctx* ctx = p->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   SlabArgs a = p->a;
   a.first_cluster_id = first_cluster_id;
-  const int W = a.P.world;
-  const int g_own = blocks_for(a.n_own, kDbBlock);
-  switch (phase) {
-    case 0:
-      VPC_LAUNCH(ctx, k_slb_halo_pack, g_own, kDbBlock, s, a);
-      break;
-    case 1: {
-      VPC_LAUNCH(ctx, k_slb_halo_pull, blocks_for(2ll * a.cap, kDbBlock), kDbBlock, s, a);
-      int rc = dbscan_enqueue(ctx, a.lx, a.ly, p->n_local, p->eps, p->min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg,
-                              nullptr, true);
-      if (rc) return rc;
-      if (W > 1) VPC_LAUNCH(ctx, k_slb_pairs_pack, blocks_for(p->n_local, kDbBlock), kDbBlock, s, a, ctx->db_slab);
-      break;
-    }
-    case 2: {
-      if (!ctx->db_slab_valid || ctx->db_slab.n != p->n_local) return fail(ctx, VPC_E_STATE, "phase 1 must be the previous DBSCAN call on this context");
-      DbArgs d = ctx->db_slab;
-      d.compkey = a.gkey;
-      const int gl = blocks_for(p->n_local, kDbBlock);
-      VPC_CUDA(ctx, cudaMemsetAsync(a.gkey, 0xff, 4ull * p->n_local, s));      // points outside the grid (NaN padding, non-finite input): noise
-      if (W > 1) {
-        MergeTables t{};
-        t.g_key = static_cast<int*>(p->table); t.g_val = t.g_key + p->table_slots; t.k_key = t.g_val + p->table_slots; t.k_par = t.k_key + p->table_slots;
-        t.mask = (unsigned)(p->table_slots - 1);
-        VPC_CUDA(ctx, cudaMemsetAsync(p->table, 0xff, p->table_bytes, s));
-        VPC_LAUNCH(ctx, k_slb_merge, blocks_for((long long)W * a.cap_pairs, kDbBlock), kDbBlock, s, a, t);
-        VPC_LAUNCH(ctx, k_slb_rekey, blocks_for(a.cap_pairs, kDbBlock), kDbBlock, s, a, d, t);
-      }
-      VPC_LAUNCH(ctx, k_db_resolve, gl, kDbBlock, s, d);
-      ctx->db_slab_valid = false;
-      VPC_LAUNCH(ctx, k_slb_heads, g_own, kDbBlock, s, a);
-      break;
-    }
-    case 3:
-      VPC_LAUNCH(ctx, k_slb_heads_rank, 1, kHeadsRankBlock, s, a);
-      break;
-    case 4:
-      VPC_LAUNCH(ctx, k_slb_ids, g_own, kDbBlock, s, a);
-      break;
-  }
-  return VPC_OK;
+  return slab_phase_enqueue(ctx, a, p->n_local, p->eps, p->min_pts, p->table, p->table_bytes, p->table_slots, phase, true, static_cast<cudaStream_t>(stream));
 }
 
 int vpc_slab_step_dev(vpc_slab_plan* p, int32_t first_cluster_id, void* stream) {
@@ -331,11 +341,7 @@ int vpc_icp_dist_create(vpc_ctx* ctx, vpc_comm* comm, int32_t mode, const double
             comm->take(8ull * W * sc, &a.L.cand_y[1]) && comm->take(8ull * W * sc, &a.L.cand_y[2]) && comm->take(8ull * 2 * W * kIcpSums, &a.L.sums) &&
             comm->take(4ull * n, &a.L.order);
   if (!ok) { comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_NOMEM, "exchange heap too small (vpc_icp_dist_heap_bytes)"); }
-  void* e = nullptr;
-  if (cudaMalloc(&e, 64) != cudaSuccess) { (void)cudaGetLastError(); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_NOMEM, "cudaMalloc failed"); }
-  cudaMemset(e, 0, 64);
-  p->epoch = static_cast<unsigned long long*>(e);
-  a.epoch = p->epoch;
+  a.epoch = &reinterpret_cast<HeapHeader*>(comm->heap)->epoch[1];
   *out = p;
   return VPC_OK;
 }
@@ -394,7 +400,7 @@ int vpc_icp_dist_rounds_dev(vpc_icp_dist* p, double e, int32_t max_iters, int32_
 
 void vpc_icp_dist_destroy(vpc_icp_dist* p) {
   if (!p) return;
-  { DeviceGuard g(p->ctx->device); cudaDeviceSynchronize(); if (p->epoch) cudaFree(p->epoch); }
+  { DeviceGuard g(p->ctx->device); cudaDeviceSynchronize(); }
   delete p;
 }
 

@@ -258,6 +258,18 @@ struct DeviceGuard {
 
 }  // namespace
 
+struct vpc_group;
+namespace {
+int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, double eps, int32_t min_pts, int32_t first_cluster_id,
+                 int32_t* cluster_id, uint8_t* is_key, uint8_t* is_classed, int32_t* cluster_amount);
+int group_icp(vpc_ctx* top, const double* model_xyz, int64_t m, const double* data_xyz, int64_t n, double e, int32_t max_iters, double R[9], double T[3],
+              int32_t* iters_done, double* sse_last, int32_t* order_last);
+int group_create(vpc_ctx* top, const int* device_ids, int n_devices);
+void group_destroy(vpc_ctx* top);
+int64_t group_launches(const vpc_ctx* top);
+int64_t group_min_points(const vpc_ctx* top);
+}  // namespace
+
 extern "C" {
 
 const char* vpc_version(void) { return "vpc-b200 0.1 (sm_100a)"; }
@@ -265,7 +277,7 @@ const char* vpc_version(void) { return "vpc-b200 0.1 (sm_100a)"; }
 int vpc_create(vpc_ctx** out, const int* device_ids, int n_devices) {
   if (!out) return VPC_E_BADARG;
   *out = nullptr;
-  if (n_devices < 0 || n_devices > 1) return VPC_E_BADARG;  // single-process multi-GPU: reserved
+  if (n_devices < 0 || n_devices > 16) return VPC_E_BADARG;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0) { (void)cudaGetLastError(); return VPC_E_NODEVICE; }
@@ -280,24 +292,31 @@ int vpc_create(vpc_ctx** out, const int* device_ids, int n_devices) {
   ctx->sm_count = prop.multiProcessorCount;
   DeviceGuard g(dev);
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VPC_E_CUDA; }
+  if (n_devices > 1) {                         // one process, several GPUs: a sub-context per rank (group_api.cuh)
+    const int rc = group_create(ctx, device_ids, n_devices);
+    if (rc) { vpc_destroy(ctx); return rc; }
+  }
   *out = ctx;
   return VPC_OK;
 }
 
 void vpc_destroy(vpc_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->group) group_destroy(ctx);
   {
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
     for (Arena* a : {&ctx->db, &ctx->io, &ctx->icp_model, &ctx->icp_work, &ctx->st})
       if (a->base) cudaFree(a->base);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    ctx->stager.release();
   }
+  delete ctx->pool;
   delete ctx;
 }
 
 const char* vpc_last_error(const vpc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-int64_t vpc_launch_count(const vpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t vpc_launch_count(const vpc_ctx* ctx) { return ctx ? ctx->launches + (ctx->group ? group_launches(ctx) : 0) : 0; }
 
 int vpc_profile_enable(vpc_ctx* ctx, int on) {
   if (!ctx) return VPC_E_BADARG;
@@ -349,6 +368,12 @@ int vpc_dbscan_l1_2d(vpc_ctx* ctx, const double* mx, const double* my, int64_t n
     if (cluster_amount) *cluster_amount = first_cluster_id;
     return VPC_OK;
   }
+  // a multi-GPU context spreads the call over its devices (slabs + halo + cross-GPU merge, group_api.cuh); small or degenerate
+  // clouds and min_pts <= 0 (every point, even a NaN one, seeds a cluster) stay on the first device
+  if (ctx->group && min_pts > 0 && eps >= 0.0 && n >= group_min_points(ctx) && (long long)first_cluster_id + n < 0x3fffffffll) {
+    rc = group_dbscan(ctx, mx, my, n, eps, min_pts, first_cluster_id, cluster_id, is_key, is_classed, cluster_amount);
+    if (rc != 1000) return rc;
+  }
   cudaStream_t s = ctx->own_stream;
   rc = arena_reserve(ctx, ctx->io, al256(8ull * n) * 2 + al256(4ull * n) + al256((size_t)n) * 2 + 1024);
   if (rc) return rc;
@@ -358,17 +383,40 @@ int vpc_dbscan_l1_2d(vpc_ctx* ctx, const double* mx, const double* my, int64_t n
   unsigned char* d_key = ctx->io.take<unsigned char>(n);
   unsigned char* d_cls = ctx->io.take<unsigned char>(n);
   int* d_amount = ctx->io.take<int>(1);
-  VPC_CUDA(ctx, cudaMemcpyAsync(d_x, mx, 8ull * n, cudaMemcpyHostToDevice, s));
-  VPC_CUDA(ctx, cudaMemcpyAsync(d_y, my, 8ull * n, cudaMemcpyHostToDevice, s));
+  // pageable arrays (what the P/Invoke marshaller passes) go through worker threads + a page-locked ring; page-locked ones directly
+  vpc_host::CopyPool* pool = ctx_pool(ctx);
+  if (pool) VPC_CUDA(ctx, ctx->stager.reserve(16ull * n));
+  VPC_CUDA(ctx, ctx->stager.h2d(pool, d_x, mx, 8ull * n, s));
+  VPC_CUDA(ctx, ctx->stager.h2d(pool, d_y, my, 8ull * n, s));
   rc = dbscan_enqueue(ctx, d_x, d_y, n, eps, min_pts, first_cluster_id, d_cid, d_key, d_cls, d_amount, s);
   if (rc) return rc;
   int amount = 0;
-  VPC_CUDA(ctx, cudaMemcpyAsync(cluster_id, d_cid, 4ull * n, cudaMemcpyDeviceToHost, s));
-  VPC_CUDA(ctx, cudaMemcpyAsync(is_key, d_key, (size_t)n, cudaMemcpyDeviceToHost, s));
-  VPC_CUDA(ctx, cudaMemcpyAsync(is_classed, d_cls, (size_t)n, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, ctx->stager.d2h(pool, cluster_id, d_cid, 4ull * n, s));
+  VPC_CUDA(ctx, ctx->stager.d2h(pool, is_key, d_key, (size_t)n, s));
+  VPC_CUDA(ctx, ctx->stager.d2h(pool, is_classed, d_cls, (size_t)n, s));
   VPC_CUDA(ctx, cudaMemcpyAsync(&amount, d_amount, 4, cudaMemcpyDeviceToHost, s));
+  VPC_CUDA(ctx, ctx->stager.finish(pool));
   VPC_CUDA(ctx, cudaStreamSynchronize(s));
   if (cluster_amount) *cluster_amount = amount;
+  return VPC_OK;
+}
+
+/* page-locked host memory for callers that can keep their arrays in it (the copies then run at the PCIe rate without staging) */
+int vpc_host_alloc(void** out, int64_t bytes) {
+  if (!out || bytes <= 0) return VPC_E_BADARG;
+  *out = nullptr;
+  if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); *out = nullptr; return VPC_E_NOMEM; }
+  return VPC_OK;
+}
+void vpc_host_free(void* p) { if (p) cudaFreeHost(p); }
+int vpc_host_register(void* p, int64_t bytes) {
+  if (!p || bytes <= 0) return VPC_E_BADARG;
+  if (cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) { (void)cudaGetLastError(); return VPC_E_CUDA; }
+  return VPC_OK;
+}
+int vpc_host_unregister(void* p) {
+  if (!p) return VPC_E_BADARG;
+  if (cudaHostUnregister(p) != cudaSuccess) { (void)cudaGetLastError(); return VPC_E_CUDA; }
   return VPC_OK;
 }
 
@@ -733,6 +781,7 @@ int vpc_icp_rigid(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double
   if (m > 2147483646ll || n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "size exceeds 2^31-2");
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
+  if (ctx->group && n >= 256) return group_icp(ctx, model_xyz, m, data_xyz, n, e, max_iters, R, T, iters_done, sse_last, order_last);
   cudaStream_t s = ctx->own_stream;
   int rc = arena_reserve(ctx, ctx->io, al256(24ull * m) + al256(24ull * n) + al256(4ull * n) + al256(16 * 8) * 2 + 1024);
   if (rc) return rc;
@@ -743,8 +792,10 @@ int vpc_icp_rigid(vpc_ctx* ctx, const double* model_xyz, int64_t m, const double
   double* d_out = ctx->io.take<double>(16);
   double rt[12];
   std::memcpy(rt, R, 72); std::memcpy(rt + 9, T, 24);
-  VPC_CUDA(ctx, cudaMemcpyAsync(d_model, model_xyz, 24ull * m, cudaMemcpyHostToDevice, s));
-  VPC_CUDA(ctx, cudaMemcpyAsync(d_data, data_xyz, 24ull * n, cudaMemcpyHostToDevice, s));
+  vpc_host::CopyPool* pool = ctx_pool(ctx);
+  if (pool) VPC_CUDA(ctx, ctx->stager.reserve(24ull * std::max(m, n)));
+  VPC_CUDA(ctx, ctx->stager.h2d(pool, d_model, model_xyz, 24ull * m, s));
+  VPC_CUDA(ctx, ctx->stager.h2d(pool, d_data, data_xyz, 24ull * n, s));
   VPC_CUDA(ctx, cudaMemcpyAsync(d_rt, rt, 96, cudaMemcpyHostToDevice, s));
   rc = icp_set_model(ctx, d_model, m, s);
   if (rc) return rc;
@@ -1315,4 +1366,4 @@ int vpc_dbscan_blocked_ref(vpc_ctx* ctx, const double* mx, const double* my, int
 
 }  // extern "C"
 
-#include "dist_api.cuh"
+#include "group_api.cuh"
