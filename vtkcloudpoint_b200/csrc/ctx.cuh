@@ -102,12 +102,13 @@ namespace {
     }                                                                                        \
   } while (0)
 
-// worker threads for pageable host memory: VPC_COPY_THREADS (0 = plain cudaMemcpyAsync), default = half the cores, 2..8
+// worker threads for pageable host memory: VPC_COPY_THREADS (0 = plain cudaMemcpyAsync), default 2
 vpc_host::CopyPool* ctx_pool(vpc_ctx* ctx) {
   if (!ctx->pool_tried) {
     ctx->pool_tried = true;
-    int t = (int)std::thread::hardware_concurrency() / 2;
-    t = t < 2 ? 2 : (t > 8 ? 8 : t);
+    // two workers + the caller saturate the host's copy bandwidth (measured on the B200 box, 16 cores: 1 / 2 / 4 / 8 workers give
+    // 0.77 / 1.00 / 0.98 / 0.95 Gpts/s end to end at 1M points, the driver's own pageable path 0.71)
+    int t = std::thread::hardware_concurrency() >= 4 ? 2 : 1;
     if (const char* e = std::getenv("VPC_COPY_THREADS")) t = std::atoi(e);
     if (t > 0) ctx->pool = new (std::nothrow) vpc_host::CopyPool(t);
   }

@@ -1,7 +1,7 @@
 // staging.hpp -- host <-> device copies for PAGEABLE caller memory (what a P/Invoke marshaller hands over: a GC-pinned but not
-// page-locked double[]).  cudaMemcpyAsync from pageable memory is a synchronous bounce through the driver's small staging buffer
-// (~3 GB/s measured on the B200 box, profiles/r01d_time_around.md); here worker threads copy chunks into / out of a page-locked ring
-// while the DMA engine moves the previous chunks, so the copy runs near the PCIe rate.  Page-locked caller memory (vpc_host_alloc,
+// page-locked double[]).  The driver's own pageable path is a single-threaded bounce; here a few worker threads (and the calling
+// thread) copy chunks into / out of a page-locked ring IN PARALLEL and each issues the DMA of its own chunk, so the host-side copy
+// runs at several cores' memcpy rate and overlaps with the PCIe transfers.  Page-locked caller memory (vpc_host_alloc,
 // vpc_host_register) is detected and copied directly.
 //
 // The reference has no counterpart: its points live in List<Point3D> objects (DataModel.cs:102-160); the shim flattens them
@@ -10,66 +10,101 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
-#include <deque>
 #include <functional>
-#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 namespace vpc_host {
 
+// parallel_for over a handful of persistent threads.  Workers spin briefly for the next job (a call makes several in a row), then
+// sleep; one job at a time, the caller takes part.
 class CopyPool {
  public:
   explicit CopyPool(int n_threads) {
     for (int t = 0; t < n_threads; ++t) th_.emplace_back([this] { run(); });
   }
   ~CopyPool() {
-    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_.fetch_add(1); }
     cv_.notify_all();
     for (auto& t : th_) t.join();
   }
-  void submit(std::function<void()> f) {
-    { std::lock_guard<std::mutex> lk(m_); q_.push_back(std::move(f)); }
-    cv_.notify_one();
-  }
   int threads() const { return (int)th_.size(); }
 
+  void parallel_for(size_t n, const std::function<void(size_t)>& body) {
+    if (n == 0) return;
+    if (n == 1 || th_.empty()) { for (size_t i = 0; i < n; ++i) body(i); return; }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      body_ = &body; n_ = n; next_.store(0); done_.store(0); open_ = true;
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    work(body, n);
+    while (done_.load(std::memory_order_acquire) < n) std::this_thread::yield();
+    { std::lock_guard<std::mutex> lk(m_); open_ = false; }
+    while (inside_.load(std::memory_order_acquire) != 0) std::this_thread::yield();   // nobody still holds a pointer to `body`
+  }
+
  private:
+  void work(const std::function<void(size_t)>& body, size_t n) {
+    size_t i, mine = 0;
+    while ((i = next_.fetch_add(1, std::memory_order_relaxed)) < n) { body(i); ++mine; }
+    if (mine) done_.fetch_add(mine, std::memory_order_acq_rel);
+  }
   void run() {
+    unsigned long long seen = 0;
     for (;;) {
-      std::function<void()> f;
-      {
+      // wait for a new generation: spin for a short while (the next copy of the same call is microseconds away), then sleep
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == seen) {
+        if (++spins < 4000) { std::this_thread::yield(); continue; }
         std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
-        if (stop_ && q_.empty()) return;
-        f = std::move(q_.front()); q_.pop_front();
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
       }
-      f();
+      const std::function<void(size_t)>* body = nullptr;
+      size_t n = 0;
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        seen = gen_.load(std::memory_order_acquire);
+        if (stop_) return;
+        if (!open_) continue;
+        body = body_; n = n_;
+        inside_.fetch_add(1, std::memory_order_acq_rel);
+      }
+      work(*body, n);
+      inside_.fetch_sub(1, std::memory_order_acq_rel);
     }
   }
   std::vector<std::thread> th_;
   std::mutex m_;
   std::condition_variable cv_;
-  std::deque<std::function<void()>> q_;
-  bool stop_ = false;
+  std::atomic<unsigned long long> gen_{0};
+  std::atomic<size_t> next_{0}, done_{0};
+  std::atomic<int> inside_{0};
+  const std::function<void(size_t)>* body_ = nullptr;
+  size_t n_ = 0;
+  bool open_ = false, stop_ = false;
 };
 
-// One page-locked ring per device stream.  Not thread safe: the owning context serialises its calls.
+// One page-locked ring per device stream, used in two halves so that filling one half overlaps the DMA out of the other.
+// Not thread safe: the owning context serialises its calls.
 class Stager {
  public:
-  static constexpr size_t kChunk = 1u << 20;   // 1 MiB pieces: 16 of them cover the 1M-point cloud's x or y
+  static constexpr size_t kChunk = 512u << 10;
 
   Stager() = default;
   Stager(const Stager&) = delete;
   ~Stager() { release(); }
 
   void release() {
-    for (auto& s : slots_) if (s.ev) cudaEventDestroy(s.ev);
-    slots_.clear();
+    for (auto& e : half_ev_) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : chunk_ev_) if (e) cudaEventDestroy(e);
+    chunk_ev_.clear();
     if (ring_) cudaFreeHost(ring_);
     ring_ = nullptr; cap_ = 0;
   }
@@ -81,129 +116,110 @@ class Stager {
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
   }
 
-  // grows the ring (call while no transfer is pending: at the start of an API call); 2 chunks of head-room, capped
+  // the ring holds two halves of min(bytes, 64 MiB) each; grows only
   cudaError_t reserve(size_t bytes) {
-    const size_t want = ((std::min<size_t>(bytes, 128u << 20) + kChunk - 1) / kChunk) * kChunk + 2 * kChunk;
-    if (want <= cap_ || !pending_.empty() || outstanding_.load() != 0) return cap_ ? cudaSuccess : cudaErrorNotReady;
+    const size_t half = ((std::min<size_t>(std::max<size_t>(bytes, kChunk), 64u << 20) + kChunk - 1) / kChunk) * kChunk;
+    if (2 * half <= cap_) return cudaSuccess;
     release();
-    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ring_), want, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ring_), 2 * half, cudaHostAllocPortable);
     if (e != cudaSuccess) { ring_ = nullptr; return e; }
-    cap_ = want;
-    slots_.resize(cap_ / kChunk);
-    out_busy_.reset(new std::atomic<int>[slots_.size()]);
-    for (size_t k = 0; k < slots_.size(); ++k) { slots_[k].ev = nullptr; slots_[k].busy = false; out_busy_[k].store(0); }
-    next_ = 0;
+    cap_ = 2 * half;
+    chunk_ev_.assign(cap_ / kChunk, nullptr);
+    half_busy_[0] = half_busy_[1] = false;
+    turn_ = 0;
     return cudaSuccess;
   }
 
-  // host -> device on `stream`; returns after every chunk has been handed to the DMA engine (the host range may be reused at once)
-  cudaError_t h2d(CopyPool* pool, void* dev, const void* host, size_t bytes, cudaStream_t stream) {
+  // host -> device on `stream` of `device`; on return every chunk has been handed to the DMA engine (the host range may be reused)
+  cudaError_t h2d(CopyPool* pool, void* dev, const void* host, size_t bytes, cudaStream_t stream, int device = -1) {
     if (bytes == 0) return cudaSuccess;
     if (!pool || is_pinned(host)) return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream);
     cudaError_t e = cap_ ? cudaSuccess : reserve(bytes);
     if (e != cudaSuccess) return e;
-    drain_pool_ = pool;
-    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
-    std::vector<int> slot_of(n_chunks);
-    std::vector<std::atomic<int>> done(n_chunks);
-    for (auto& d : done) d.store(0);
-    size_t issued = 0, submitted = 0;
-    // keep at most slots_.size() chunks in flight: a slot is reused once its DMA has completed
-    while (issued < n_chunks) {
-      while (submitted < n_chunks && submitted - issued < slots_.size()) {
-        const int sl = acquire_slot();
-        if (sl < 0) return cudaErrorUnknown;
-        slot_of[submitted] = sl;
-        const size_t off = submitted * kChunk, len = std::min(kChunk, bytes - off);
-        char* dst = ring_ + (size_t)sl * kChunk;
-        const char* src = static_cast<const char*>(host) + off;
-        std::atomic<int>* flag = &done[submitted];
-        pool->submit([dst, src, len, flag] { std::memcpy(dst, src, len); flag->store(1, std::memory_order_release); });
-        ++submitted;
-      }
-      while (done[issued].load(std::memory_order_acquire) == 0) std::this_thread::yield();
-      const size_t off = issued * kChunk, len = std::min(kChunk, bytes - off);
-      Slot& s = slots_[slot_of[issued]];
-      e = cudaMemcpyAsync(static_cast<char*>(dev) + off, ring_ + (size_t)slot_of[issued] * kChunk, len, cudaMemcpyHostToDevice, stream);
-      if (e != cudaSuccess) return e;
-      if (!s.ev && (e = cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-      if ((e = cudaEventRecord(s.ev, stream)) != cudaSuccess) return e;
-      s.busy = true;
-      ++issued;
+    if (device < 0) cudaGetDevice(&device);
+    const size_t half = cap_ / 2;
+    std::atomic<int> err{0};
+    for (size_t off = 0; off < bytes; off += half) {
+      const size_t piece = std::min(half, bytes - off), n_chunks = (piece + kChunk - 1) / kChunk;
+      const int h = next_half();
+      if ((e = wait_half(h)) != cudaSuccess) return e;
+      char* base = ring_ + (size_t)h * half;
+      const char* src = static_cast<const char*>(host) + off;
+      char* dst = static_cast<char*>(dev) + off;
+      pool->parallel_for(n_chunks, [&](size_t i) {
+        const size_t o = i * kChunk, len = std::min(kChunk, piece - o);
+        std::memcpy(base + o, src + o, len);
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        if (cudaMemcpyAsync(dst + o, base + o, len, cudaMemcpyHostToDevice, stream) != cudaSuccess) err.store(1);
+      });
+      if (err.load()) return cudaErrorUnknown;
+      if ((e = mark_half(h, stream)) != cudaSuccess) return e;
     }
     return cudaSuccess;
   }
 
-  // device -> host on `stream`; the copies into the caller's memory are finished by finish()
-  cudaError_t d2h(CopyPool* pool, void* host, const void* dev, size_t bytes, cudaStream_t stream) {
+  // device -> host on `stream`; synchronous with respect to the caller's memory: on return `host` holds the data
+  cudaError_t d2h(CopyPool* pool, void* host, const void* dev, size_t bytes, cudaStream_t stream, int device = -1) {
     if (bytes == 0) return cudaSuccess;
     if (!pool || is_pinned(host)) return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cap_ ? cudaSuccess : reserve(bytes);
     if (e != cudaSuccess) return e;
-    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
-    for (size_t c = 0; c < n_chunks; ++c) {
-      const int sl = acquire_slot_for_d2h(pool);
-      if (sl < 0) return cudaErrorUnknown;
-      const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
-      Slot& s = slots_[sl];
-      e = cudaMemcpyAsync(ring_ + (size_t)sl * kChunk, static_cast<const char*>(dev) + off, len, cudaMemcpyDeviceToHost, stream);
-      if (e != cudaSuccess) return e;
-      if (!s.ev && (e = cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-      if ((e = cudaEventRecord(s.ev, stream)) != cudaSuccess) return e;
-      s.busy = true;
-      pending_.push_back(Pending{sl, static_cast<char*>(host) + off, len});
+    if (device < 0) cudaGetDevice(&device);
+    const size_t half = cap_ / 2;
+    std::atomic<int> err{0};
+    for (size_t off = 0; off < bytes; off += half) {
+      const size_t piece = std::min(half, bytes - off), n_chunks = (piece + kChunk - 1) / kChunk;
+      const int h = next_half();
+      if ((e = wait_half(h)) != cudaSuccess) return e;
+      char* base = ring_ + (size_t)h * half;
+      const size_t ev0 = (size_t)h * (half / kChunk);
+      for (size_t i = 0; i < n_chunks; ++i) {            // all DMAs first (they queue behind the kernels), one event per chunk
+        const size_t o = i * kChunk, len = std::min(kChunk, piece - o);
+        if ((e = cudaMemcpyAsync(base + o, static_cast<const char*>(dev) + off + o, len, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+        cudaEvent_t& ev = chunk_ev_[ev0 + i];
+        if (!ev && (e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ev, stream)) != cudaSuccess) return e;
+      }
+      char* dst = static_cast<char*>(host) + off;
+      pool->parallel_for(n_chunks, [&](size_t i) {       // as each chunk lands a thread copies it into the caller's memory
+        const size_t o = i * kChunk, len = std::min(kChunk, piece - o);
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        if (cudaEventSynchronize(chunk_ev_[ev0 + i]) != cudaSuccess) { err.store(1); return; }
+        std::memcpy(dst + o, base + o, len);
+      });
+      if (err.load()) return cudaErrorUnknown;
+      half_busy_[h] = false;                             // drained
     }
     return cudaSuccess;
   }
 
-  // drains the device -> host pipeline: as each chunk's DMA completes a worker copies it into the caller's memory
-  cudaError_t finish(CopyPool* pool) {
-    if (!pool) return cudaSuccess;
-    cudaError_t e = drain(pool, pending_.size());
-    while (outstanding_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
-    return e;
-  }
+  cudaError_t finish(CopyPool*) { return cudaSuccess; }  // d2h is complete on return
 
  private:
-  struct Slot { cudaEvent_t ev; bool busy; };
-  struct Pending { int slot; char* dst; size_t len; };
-
-  int acquire_slot() {                       // next slot of the ring, once its previous DMA and its previous copy-out have completed
-    const int sl = (int)next_;
-    next_ = (next_ + 1) % slots_.size();
-    Slot& s = slots_[sl];
-    // a chunk that still waits to be copied out of this slot: drain the queue up to and including it
-    for (size_t k = 0; k < pending_.size(); ++k)
-      if (pending_[k].slot == sl) { if (drain(drain_pool_, k + 1) != cudaSuccess) return -1; break; }
-    while (out_busy_[sl].load(std::memory_order_acquire) != 0) std::this_thread::yield();
-    if (s.busy) { if (cudaEventSynchronize(s.ev) != cudaSuccess) return -1; s.busy = false; }
-    return sl;
+  int next_half() { const int h = turn_; turn_ ^= 1; return h; }
+  cudaError_t wait_half(int h) {                         // the DMA that last read this half has completed
+    if (!half_busy_[h]) return cudaSuccess;
+    half_busy_[h] = false;
+    return cudaEventSynchronize(half_ev_[h]);
   }
-  int acquire_slot_for_d2h(CopyPool* pool) { drain_pool_ = pool; return acquire_slot(); }
-  cudaError_t drain(CopyPool* pool, size_t count) {
-    for (size_t k = 0; k < count && !pending_.empty(); ++k) {
-      Pending p = pending_.front(); pending_.pop_front();
-      Slot& s = slots_[p.slot];
-      cudaError_t e = cudaEventSynchronize(s.ev);
-      if (e != cudaSuccess) return e;
-      s.busy = false;
-      const char* src = ring_ + (size_t)p.slot * kChunk;
-      outstanding_.fetch_add(1, std::memory_order_acq_rel);
-      out_busy_[p.slot].store(1, std::memory_order_release);
-      std::atomic<int>* out = &outstanding_;
-      std::atomic<int>* mine = &out_busy_[p.slot];
-      pool->submit([p, src, out, mine] { std::memcpy(p.dst, src, p.len); mine->store(0, std::memory_order_release); out->fetch_sub(1, std::memory_order_acq_rel); });
-    }
+  cudaError_t mark_half(int h, cudaStream_t stream) {
+    cudaError_t e;
+    if (!half_ev_[h] && (e = cudaEventCreateWithFlags(&half_ev_[h], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(half_ev_[h], stream)) != cudaSuccess) return e;
+    half_busy_[h] = true;
     return cudaSuccess;
   }
 
   char* ring_ = nullptr;
-  size_t cap_ = 0, next_ = 0;
-  std::vector<Slot> slots_;
-  std::deque<Pending> pending_;
-  std::atomic<int> outstanding_{0};
-  std::unique_ptr<std::atomic<int>[]> out_busy_;
-  CopyPool* drain_pool_ = nullptr;
+  size_t cap_ = 0;
+  int turn_ = 0;
+  cudaEvent_t half_ev_[2] = {nullptr, nullptr};
+  bool half_busy_[2] = {false, false};
+  std::vector<cudaEvent_t> chunk_ev_;
 };
 
 }  // namespace vpc_host
