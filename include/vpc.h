@@ -238,20 +238,43 @@ int vpc_match_within_dev(vpc_ctx* ctx, const double* d_centers_xyz, int64_t n, d
 int vpc_cluster_means_dev(vpc_ctx* ctx, const int32_t* d_cluster_id, int64_t n, int32_t n_clusters, const double* d_vals,
                           int32_t n_fields, double* d_means, int32_t* d_counts, void* stream);
 
-/* ---- the blocked ("分块") multithreaded clustering as one call -----------------------------------
- * Replaces MainForm.getClusterFromMotor (FrmMain.cs:1214-1291) -> DoWork3 / StartCode (:1340-1361, :2782-2794) ->
- * CompleteWork3 (:1432-1520) up to the renumbered labels, reproducing the C#'s behaviour including its quirks: no halo
- * between cells; strict lower / inclusive upper box bounds, so points with mx == xmin or my == ymin outside the first cell
- * and points tied at the first cell's cut fall into no cell (*n_unassigned, labelled 0); cell-local ids renumbered with a
- * running id; clusters whose counted length is <= 3 are zeroed, with the off-by-one of :1460-1499 and without a check of
- * a cell's last cluster; all noise re-clustered globally with cf = clusterSum - delSum - 1 (:1507-1516).  List.Sort's
- * undefined tie order is pinned to the input order.  The sort and both DBSCAN steps run on the GPU (all cells in ONE
- * batched launch); the box assignment and the renumbering are the C#'s host logic.  cluster_id[n] by input order,
- * *cluster_sum = MainForm.clusterSum (:1538); del_sum / rows / cols / n_unassigned are nullable extras.
- * Returns VPC_E_STATE where the C# would throw (clusForMerge[-1], :1487). */
+/* ---- the blocked ("分块") multithreaded clustering as one call ---------------------------------
+ * vpc_dbscan_blocked_ref replaces MainForm.getClusterFromMotor (FrmMain.cs:1214-1291) -> DoWork3 / StartCode (:1340-1361,
+ * :2782-2794) -> CompleteWork3 (:1432-1520) up to the renumbered labels, reproducing the C#'s behaviour including its quirks: no
+ * halo between cells; strict lower / inclusive upper box bounds, so points with mx == xmin or my == ymin outside the first cell and
+ * points tied at the first cell's cut fall into no cell (*n_unassigned, labelled 0); cell-local ids renumbered with a running id;
+ * clusters whose counted length is <= 3 are zeroed, with the off-by-one of :1460-1499 and without a check of a cell's last cluster;
+ * all noise re-clustered globally with cf = clusterSum - delSum - 1 (:1507-1516).  Everything runs on the device (csrc/blocked.cuh):
+ * the sort, the box assignment, every StartCode work item in ONE batched launch, the renumbering as sorted-run arithmetic, the
+ * noise re-cluster; the host reads back a few scalars only.  Pinned where the C# leaves it to chance: List.Sort's tie order = input
+ * order; a point that satisfies TWO cells (the first cell and a box -- x_Min + cell_x can round one ulp below the first cell's own
+ * maximum) is a shared object written by two pool threads in the C#: here every cell slot is a private copy and the point reports
+ * its LATER slot (*n_shared counts such points; oracle/vpc_oracle_blocked.cpp restates both behaviours).
+ * cluster_id[n] by input order, *cluster_sum = MainForm.clusterSum (:1538); del_sum / rows / cols / n_unassigned nullable.
+ * _ex adds: n_shared; merge_order / merge_cid (nullable, capacity 3 n) = clusForMerge in its final order (:1517-1520) as input-point
+ * indices and their ids, *n_merge entries (the order Tools.GetClusList sums centroids in); cluster_sum_cells = clusterSum before
+ * the merge (:1346, :2789).  Returns VPC_E_STATE where the C# would throw (clusForMerge[-1], :1487), VPC_E_BADARG for non-finite
+ * coordinates or a degenerate first cell (division by zero, :1257).
+ *
+ * vpc_merge_ids_by_distance replaces Clustering.MergeBtn_Click's chain (Clustering.cs:141-153): Tools.GetClusList (Tools.cs:162-195)
+ * over the clusForMerge list, Tools.MergeIDByDistance (Tools.cs:580-621: DBImproved.dbscan(centres' (X, Y), thre, 2); every later
+ * member of a centre cluster maps to its first member) and Tools.refreshCensAndClusByDictionary (Tools.cs:521-572: merged clusters
+ * appended to their target, survivors renumbered 1.. in id order, centroids recomputed).  Arrays are per ENTRY of clusForMerge in
+ * list order: merge_cid[k], xyz planar [3][k], mx[k], my[k].  Outputs: new_cid[k], *new_amount; nullable: the dictionary in
+ * insertion order (dict_from -> dict_to, capacity cluster_amount, *n_dict), centers5 planar [5][*n_centers] + center_ids (means
+ * of X, Y, Z, motor_x, motor_y before the merge, bit-identical to LINQ Average), new_centers5 planar [5][*new_amount] after it.
+ * VPC_E_STATE when a cluster id has no points (the C# throws InvalidOperationException, Tools.cs:565). */
 int vpc_dbscan_blocked_ref(vpc_ctx* ctx, const double* mx, const double* my, int64_t n, double eps, int32_t min_pts,
                            int32_t pts_in_cell, int32_t* cluster_id, int32_t* cluster_sum, int32_t* del_sum, int32_t* rows,
                            int32_t* cols, int64_t* n_unassigned);
+int vpc_dbscan_blocked_ref_ex(vpc_ctx* ctx, const double* mx, const double* my, int64_t n, double eps, int32_t min_pts,
+                              int32_t pts_in_cell, int32_t* cluster_id, int32_t* cluster_sum, int32_t* del_sum, int32_t* rows,
+                              int32_t* cols, int64_t* n_unassigned, int64_t* n_shared, int64_t* merge_order, int32_t* merge_cid,
+                              int64_t* n_merge, int32_t* cluster_sum_cells);
+int vpc_merge_ids_by_distance(vpc_ctx* ctx, const int32_t* merge_cid, const double* xyz, const double* mx, const double* my,
+                              int64_t k, int32_t cluster_amount, double thre, int32_t* new_cid, int32_t* new_amount,
+                              int32_t* dict_from, int32_t* dict_to, int32_t* n_dict, double* centers5, int32_t* center_ids,
+                              int32_t* n_centers, double* new_centers5);
 
 /* ---- sorting (the reference's List.Sort / OrderBy steps around the path) -----------------------------------------
  * vpc_sort_pairs_dev: stable LSD radix sort of n (uint64 key, int32 value) pairs on key bits [begin_bit, end_bit), in

@@ -37,29 +37,20 @@ int main() {
   if (dbb.clusterAmount != amount || dbb.cf != amount || dbb.pointsAmount != n) { std::printf("FAIL amount %d vs %d\n", dbb.clusterAmount, amount); return 1; }
   for (int i = 0; i < n; ++i)
     if (pts[i].clusterId != cid[i] || pts[i].isClassed != (cls[i] != 0) || pts[i].isKeyPoint != (key[i] != 0)) { std::printf("FAIL point %d\n", i); return 1; }
-  // ---- blocked clustering (getClusterFromMotor -> DoWork3 -> CompleteWork3): the same host flow driven by libvpc and by the oracle
+  // ---- blocked clustering (getClusterFromMotor -> DoWork3 -> CompleteWork3): the library's device flow vs the oracle's literal,
+  // List-based restatement (oracle/vpc_oracle_blocked.cpp)
   {
-    struct OracleEngine : MainForm::Engine {
-      int dbscan(const double* x, const double* y, int64_t k, double eps, int minPts, int cf, int32_t* id) override {
-        std::vector<uint8_t> a(k), b(k); int32_t amount = cf;
-        vpco_dbscan_l1_2d_literal(x, y, k, eps, minPts, cf, id, a.data(), b.data(), &amount, 0, nullptr);
-        return amount;
-      }
-      void dbscan_cells(const double* x, const double* y, int64_t, const int64_t* off, int n_cells, double eps, int minPts, int32_t* id, int32_t* per_cell) override {
-        for (int c2 = 0; c2 < n_cells; ++c2) {
-          const int64_t a0 = off[c2], k = off[c2 + 1] - a0;
-          std::vector<uint8_t> a(k), b(k); int32_t amount = 0;
-          if (k > 0) vpco_dbscan_l1_2d_literal(x + a0, y + a0, k, eps, minPts, 0, id + a0, a.data(), b.data(), &amount, 0, nullptr);
-          per_cell[c2] = amount;
-        }
-      }
-    } oracle_engine;
-    MainForm::VpcEngine vpc_engine(ctx);
     for (int ptsInCell : {200, 650}) {
-      MainForm::BlockedResult g = MainForm::ClusterBlocked(vpc_engine, mx, my, 0.07, 7, ptsInCell);
-      MainForm::BlockedResult o = MainForm::ClusterBlocked(oracle_engine, mx, my, 0.07, 7, ptsInCell);
-      if (g.clusterSum != o.clusterSum || g.delSum != o.delSum || g.rows != o.rows || g.cols != o.cols || g.clusterId != o.clusterId) {
-        std::printf("FAIL blocked flow (ptsInCell %d): %d vs %d clusters\n", ptsInCell, g.clusterSum, o.clusterSum); return 1;
+      MainForm::BlockedResult g = MainForm::ClusterBlocked(ctx, mx, my, 0.07, 7, ptsInCell);
+      std::vector<int32_t> ocid(n), omc(3 * n);
+      std::vector<int64_t> omo(3 * n);
+      int32_t ocs = 0, ods = 0, orows = 0, ocols = 0, ocsc = 0;
+      int64_t oun = 0, osh = 0, onm = 0;
+      const int rc = vpco_blocked_literal(mx.data(), my.data(), n, 0.07, 7, ptsInCell, 0, 0, 1, ocid.data(), &ocs, &ods, &orows, &ocols, &oun, &osh, omo.data(), omc.data(), &onm, &ocsc);
+      omo.resize(onm); omc.resize(onm);
+      if (rc != 0 || g.clusterSum != ocs || g.delSum != ods || g.rows != orows || g.cols != ocols || g.unassigned != oun || g.shared != osh || g.clusterId != ocid ||
+          g.clusForMerge != omo || g.mergeId != omc) {
+        std::printf("FAIL blocked flow (ptsInCell %d): %d vs %d clusters (rc %d)\n", ptsInCell, g.clusterSum, ocs, rc); return 1;
       }
     }
   }

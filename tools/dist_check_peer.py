@@ -97,6 +97,14 @@ for mode, m_tot in ((0, icp_m * world), (1, icp_m)):
     ctx.icp_set_model_dev(tm)
     ip = IcpDistPlan(icomm, mode, td, a_)
     ms_eager = timed(lambda: ip.run(-1.0, icp_iters), 3)
+    if rank == 0:                        # per-kernel CUDA-event times of one eager run (waiting kernels include the wait)
+        ctx.profile(True); ip.run(-1.0, icp_iters); rep = ctx.profile_report(); ctx.profile(False)
+        agg = {}
+        for kname, ms in rep:
+            agg.setdefault(kname, []).append(ms)
+        say("  per launch [us]: " + "  ".join(f"{k}={1e3 * sum(v) / len(v):.1f}" for k, v in agg.items()))
+    else:
+        ip.run(-1.0, icp_iters)
     ig = GraphedStep(lambda: ip.run(-1.0, icp_iters), dev)
     ms_graph = timed(ig.replay, 5)
     state, order = ig.replay()

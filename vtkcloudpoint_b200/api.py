@@ -290,19 +290,41 @@ class Context:
                 "n_kept": int(n_kept.value), "n_duplicates": int(n_dup.value)}
 
     def dbscan_blocked_ref(self, mx, my, eps: float, min_pts: int, pts_in_cell: int):
-        """The reference's blocked clustering (getClusterFromMotor -> DoWork3 -> CompleteWork3) as one call.
-        Returns dict(cluster_id, cluster_sum, del_sum, rows, cols, n_unassigned)."""
+        """The reference's blocked clustering (getClusterFromMotor -> DoWork3 -> CompleteWork3) as one call, on the device.
+        Returns dict(cluster_id, cluster_sum, del_sum, rows, cols, n_unassigned, n_shared, merge_order, merge_cid, cluster_sum_cells)."""
         mx = np.ascontiguousarray(mx, np.float64)
         my = np.ascontiguousarray(my, np.float64)
         n = len(mx)
         cid = np.zeros(n, np.int32)
-        cs, ds, r, c = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
-        un = C.c_int64(0)
+        mo, mc = np.zeros(3 * n + 1, np.int64), np.zeros(3 * n + 1, np.int32)
+        cs, ds, r, c, csc = (C.c_int32(0) for _ in range(5))
+        un, sh, nm = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         ref = lambda v: C.cast(C.byref(v), C.c_void_p)   # noqa: E731
-        self._check(self._lib.vpc_dbscan_blocked_ref(self._h, _ptr(mx), _ptr(my), n, float(eps), int(min_pts), int(pts_in_cell), _ptr(cid),
-                                                     ref(cs), ref(ds), ref(r), ref(c), ref(un)))
+        self._check(self._lib.vpc_dbscan_blocked_ref_ex(self._h, _ptr(mx), _ptr(my), n, float(eps), int(min_pts), int(pts_in_cell), _ptr(cid),
+                                                        ref(cs), ref(ds), ref(r), ref(c), ref(un), ref(sh), _ptr(mo), _ptr(mc), ref(nm), ref(csc)))
+        k = int(nm.value)
         return {"cluster_id": cid, "cluster_sum": int(cs.value), "del_sum": int(ds.value), "rows": int(r.value), "cols": int(c.value),
-                "n_unassigned": int(un.value)}
+                "n_unassigned": int(un.value), "n_shared": int(sh.value), "merge_order": mo[:k].copy(), "merge_cid": mc[:k].copy(),
+                "cluster_sum_cells": int(csc.value)}
+
+    def merge_ids_by_distance(self, merge_cid, xyz_entries, mx_entries, my_entries, cluster_amount: int, thre: float):
+        """Clustering.MergeBtn_Click's chain (GetClusList -> MergeIDByDistance -> refreshCensAndClusByDictionary) on the clusForMerge
+        list; arrays per ENTRY in list order.  Returns dict(cluster_id, cluster_amount, dict [(from, to)], centers5, center_ids, new_centers5)."""
+        mcid = np.ascontiguousarray(merge_cid, np.int32)
+        k = len(mcid)
+        xyz = _planar(xyz_entries)
+        mx = np.ascontiguousarray(mx_entries, np.float64); my = np.ascontiguousarray(my_entries, np.float64)
+        cap = max(int(cluster_amount), 1)
+        new_cid = np.zeros(k, np.int32)
+        dfrom, dto, cids = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        c5, nc5 = np.zeros(5 * cap), np.zeros(5 * cap)
+        amount, nd, ncen = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        ref = lambda v: C.cast(C.byref(v), C.c_void_p)   # noqa: E731
+        self._check(self._lib.vpc_merge_ids_by_distance(self._h, _ptr(mcid), _ptr(xyz), _ptr(mx), _ptr(my), k, int(cluster_amount), float(thre), _ptr(new_cid),
+                                                        ref(amount), _ptr(dfrom), _ptr(dto), ref(nd), _ptr(c5), _ptr(cids), ref(ncen), _ptr(nc5)))
+        m, a = int(ncen.value), int(amount.value)
+        return {"cluster_id": new_cid, "cluster_amount": a, "dict": list(zip(dfrom[:nd.value].tolist(), dto[:nd.value].tolist())),
+                "centers5": c5[:5 * m].reshape(5, m).copy(), "center_ids": cids[:m].copy(), "new_centers5": nc5[:5 * a].reshape(5, a).copy()}
 
     def argsort_f64(self, vals) -> np.ndarray:
         """Stable ascending permutation of a host array of doubles on the device (vpc_argsort_f64_dev): the sort of

@@ -58,6 +58,8 @@ SIGNATURES = {
     "vpc_match_within_dev": (C.c_int, [_p, _p, _i64, _f64, _p, _p, _p]),
     "vpc_cluster_means_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _p, _p]),
     "vpc_dbscan_blocked_ref": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "vpc_dbscan_blocked_ref_ex": (C.c_int, [_p, _p, _p, _i64, _f64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vpc_merge_ids_by_distance": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _f64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vpc_sort_pairs_dev": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "vpc_argsort_f64_dev": (C.c_int, [_p, _p, _i64, _p, _p]),
     "vpc_cluster_groups_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),

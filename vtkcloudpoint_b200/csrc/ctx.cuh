@@ -49,6 +49,7 @@ struct vpc_ctx {
   Arena icp_model; // model cell list (persists between calls)
   Arena icp_work;  // per-call ICP workspace
   Arena st;        // sort / cluster statistics / ingest workspace
+  Arena blk;       // blocked clustering / centroid merge buffers (blocked_api.cuh)
   // ICP model state
   IcpModel model{};
   bool model_set = false;

@@ -59,16 +59,20 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
                        int phase, bool precut, cudaStream_t s) {
   const int W = a.P.world;
   const int g_own = blocks_for(a.n_own, kDbBlock);
+  const int g_stride = std::min(g_own, ctx->sm_count * 8);          // grid-stride kernels that end in a ticket: few, fat blocks
   switch (phase) {
     case 0:
-      if (precut) VPC_LAUNCH(ctx, k_slb_halo_pack, g_own, kDbBlock, s, a);
+      if (precut) VPC_LAUNCH(ctx, k_slb_halo_pack, g_stride, kDbBlock, s, a);
       break;
     case 1: {
       if (precut) VPC_LAUNCH(ctx, k_slb_halo_pull, blocks_for(2ll * a.cap, kDbBlock), kDbBlock, s, a);
       int rc = dbscan_enqueue(ctx, a.lx, a.ly, n_local, eps, min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg,
                               nullptr, true);
       if (rc) return rc;
-      if (W > 1) VPC_LAUNCH(ctx, k_slb_pairs_pack, blocks_for(n_local, kDbBlock), kDbBlock, s, a, ctx->db_slab);
+      if (W > 1) {
+        if (precut && !ctx->db_slab.banded) VPC_LAUNCH(ctx, k_slb_pairs_small, std::min(blocks_for(4ll * a.cap, kDbBlock), ctx->sm_count * 4), kDbBlock, s, a, ctx->db_slab);
+        else VPC_LAUNCH(ctx, k_slb_pairs_pack, blocks_for(n_local, kDbBlock), kDbBlock, s, a, ctx->db_slab);
+      }
       break;
     }
     case 2: {
@@ -87,7 +91,7 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
       }
       VPC_LAUNCH(ctx, k_db_resolve, gl, kDbBlock, s, d);
       ctx->db_slab_valid = false;
-      VPC_LAUNCH(ctx, k_slb_heads, g_own, kDbBlock, s, a);
+      VPC_LAUNCH(ctx, k_slb_heads, g_stride, kDbBlock, s, a);
       break;
     }
     case 3:
@@ -262,7 +266,7 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   long long slots = 1024;
   while (slots < 2ll * W * cap_pairs) slots <<= 1;
   p->table_slots = slots; p->table_bytes = 16ull * slots;
-  const size_t bytes = al256(8 * nl) * 2 + al256(4 * nl) * 2 + al256(nl) + al256(4 * no) + al256(no) * 2 + al256(64) * 3 + al256(4ull * cap_pairs) + al256(p->table_bytes) + 4096;
+  const size_t bytes = al256(8 * nl) * 2 + al256(4 * nl) * 2 + al256(nl) + al256(4 * no) + al256(no) * 2 + al256(64) * 3 + al256(4ull * cap_pairs) + al256(8ull * cap_halo) + al256(p->table_bytes) + 4096;
   void* base = nullptr;
   if (cudaMalloc(&base, bytes) != cudaSuccess) { (void)cudaGetLastError(); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_NOMEM, "cudaMalloc of the slab buffers failed"); }
   cudaMemset(base, 0, bytes);
@@ -272,7 +276,7 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   a.cid = w.take<int>(no); a.is_key = w.take<unsigned char>(no); a.is_classed = w.take<unsigned char>(no);
   a.counters = w.take<int>(16); a.status = w.take<int>(16);
   a.epoch = &reinterpret_cast<HeapHeader*>(comm->heap)->epoch[0];
-  a.pair_root = w.take<int>(cap_pairs);
+  a.pair_root = w.take<int>(cap_pairs); a.bidx = w.take<int>(2ull * cap_halo);
   p->table = w.take<char>(p->table_bytes);
   k_slb_iota<<<blocks_for(a.n_own, kDbBlock), kDbBlock, 0, ctx->own_stream>>>(a.lg, a.n_own, a.gstart[me]);
   if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) { cudaFree(base); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_CUDA, "slab plan initialisation failed"); }
@@ -317,7 +321,8 @@ void vpc_slab_plan_destroy(vpc_slab_plan* p) {
 int64_t vpc_icp_dist_heap_bytes(int32_t world, int64_t n) {
   if (world < 1 || n < 1) return 0;
   const size_t sc = (size_t)((n + world - 1) / world);
-  return (int64_t)(al256(8ull * world * sc) * 4 + al256(4ull * world * sc) + al256(8ull * 2 * world * kIcpSums) + al256(4ull * n) + 4096);
+  (void)sc;
+  return (int64_t)(al256(8ull * n) * 4 + al256(4ull * n) * 2 + al256(8ull * 2 * kIcpSums) + 4096);
 }
 
 // mode 0: the model set on this context (vpc_icp_set_model_dev) is shard `rank` of the target, whose first point has global index
@@ -337,8 +342,9 @@ int vpc_icp_dist_create(vpc_ctx* ctx, vpc_comm* comm, int32_t mode, const double
   a.P = comm->peers(); a.n = (int)n; a.slice_cap = (int)((n + W - 1) / W); a.idx_offset = mode == 0 ? idx_offset : 0;
   const size_t sc = (size_t)a.slice_cap;
   p->heap_mark = comm->bump;
-  bool ok = comm->take(8ull * W * sc, &a.L.cand_d2) && comm->take(4ull * W * sc, &a.L.cand_idx) && comm->take(8ull * W * sc, &a.L.cand_y[0]) &&
-            comm->take(8ull * W * sc, &a.L.cand_y[1]) && comm->take(8ull * W * sc, &a.L.cand_y[2]) && comm->take(8ull * 2 * W * kIcpSums, &a.L.sums) &&
+  (void)sc;
+  bool ok = comm->take(8ull * n, &a.L.cand_d2) && comm->take(4ull * n, &a.L.cand_idx) && comm->take(8ull * n, &a.L.cand_y[0]) &&
+            comm->take(8ull * n, &a.L.cand_y[1]) && comm->take(8ull * n, &a.L.cand_y[2]) && comm->take(8ull * 2 * kIcpSums, &a.L.sums) &&
             comm->take(4ull * n, &a.L.order);
   if (!ok) { comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_NOMEM, "exchange heap too small (vpc_icp_dist_heap_bytes)"); }
   a.epoch = &reinterpret_cast<HeapHeader*>(comm->heap)->epoch[1];
@@ -371,10 +377,10 @@ int vpc_icp_dist_round_phase_dev(vpc_icp_dist* p, int32_t phase, double e, int32
   IcpDistArgs a = p->a;
   a.e = e; a.max_iters = max_iters; a.st = ctx->icp_state; a.partial = ctx->icp_partial; a.ticket = ctx->icp_ticket;
   if (p->mode == 0) {
-    if (phase == 0) VPC_LAUNCH(ctx, k_icpd_nn_push, blocks_for(a.n, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
-    if (phase == 1) VPC_LAUNCH(ctx, k_icpd_reduce_push, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, p->d_data, a);
+    if (phase == 0) VPC_LAUNCH(ctx, k_icpd_nn_local, blocks_for(a.n, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
+    if (phase == 1) VPC_LAUNCH(ctx, k_icpd_reduce, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, p->d_data, a);
   } else {
-    if (phase == 0) VPC_LAUNCH(ctx, k_icpd_iter_push, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
+    if (phase == 0) VPC_LAUNCH(ctx, k_icpd_iter_local, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
   }
   if (phase == 2) VPC_LAUNCH(ctx, k_icpd_solve, 1, 32, s, a);
   return VPC_OK;
@@ -394,7 +400,7 @@ int vpc_icp_dist_rounds_dev(vpc_icp_dist* p, double e, int32_t max_iters, int32_
   DeviceGuard g(ctx->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d_state_out) VPC_LAUNCH(ctx, k_icp_state_export, 1, 32, s, ctx->icp_state, d_state_out);
-  if (d_order_out) VPC_CUDA(ctx, cudaMemcpyAsync(d_order_out, p->comm->heap + p->a.L.order, 4ull * p->a.n, cudaMemcpyDeviceToDevice, s));
+  if (d_order_out) VPC_LAUNCH(ctx, k_icpd_order_gather, blocks_for(p->a.n, 256), 256, s, p->a, d_order_out);
   return VPC_OK;
 }
 

@@ -11,6 +11,8 @@
 // that order makes every wait find its flag already set.
 #pragma once
 
+#include <chrono>
+
 #include "dist_api.cuh"
 #include "gen.cuh"
 
@@ -66,6 +68,14 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
   vpc_group* G = top->group;
   const int W = G->world;
   vpc_host::CopyPool* pool = ctx_pool(top);
+  static const bool trace = std::getenv("VPC_GROUP_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[vpc group] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   std::vector<int64_t> lo(W + 1);
   for (int c = 0; c <= W; ++c) lo[c] = n * c / W;
   int64_t chunk_max = 0;
@@ -100,15 +110,22 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     ga.x = in[c].x; ga.y = in[c].y; ga.n_chunk = (int)nc; ga.range = in[c].range;
     VPC_LAUNCH(sc, k_gen_bounds, std::min(blocks_for((long long)nc, 256), sc->sm_count * 8), 256, s, ga);
   }
+  mark("reserve + H2D issue");
   // splitters: quantiles of u over a strided host sample (balance only; exactness does not depend on them)
   std::vector<double> spl;
   {
-    const int64_t S = std::min<int64_t>(n, 1 << 16), step = std::max<int64_t>(1, n / S);
+    const int64_t S = std::min<int64_t>(n, 1 << 14), step = std::max<int64_t>(1, n / S);
     std::vector<double> us; us.reserve((size_t)S + 1);
     for (int64_t i = 0; i < n; i += step) { const double u = mx[i] + my[i]; if (std::isfinite(u) && std::isfinite(mx[i] - my[i])) us.push_back(u); }
-    std::sort(us.begin(), us.end());
-    for (int j = 1; j < W; ++j) spl.push_back(us.empty() ? 0.0 : us[std::min(us.size() - 1, us.size() * (size_t)j / (size_t)W)]);
+    for (int j = 1; j < W; ++j) {
+      if (us.empty()) { spl.push_back(0.0); continue; }
+      const size_t k = std::min(us.size() - 1, us.size() * (size_t)j / (size_t)W);
+      std::nth_element(us.begin(), us.begin() + k, us.end());
+      spl.push_back(us[k]);
+    }
+    std::sort(spl.begin(), spl.end());
   }
+  mark("host splitters");
   double umin = INFINITY, umax = -INFINITY, amax = 0.0;
   for (int c = 0; c < W; ++c) {
     DeviceGuard g(G->sub[c]->device);
@@ -117,6 +134,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     VPC_CUDA(top, cudaStreamSynchronize(G->stream[c]));
     if (r[0] <= r[1]) { umin = std::min(umin, ord_decode(r[0])); umax = std::max(umax, ord_decode(r[1])); amax = std::max(amax, ord_decode(r[2])); }
   }
+  mark("sync bounds");
   const double err = amax * 2.220446049250313e-16;
   const double H = 2.0 * (eps * (1.0 + 9.313225746154785e-10) + 8.0 * err) * (1.0 + 9.313225746154785e-10);
   // ---- who goes where
@@ -138,6 +156,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     VPC_CUDA(top, cudaMemcpyAsync(&cnt[(size_t)c * W * 3], in[c].counts, 4ull * W * 3, cudaMemcpyDeviceToHost, G->stream[c]));
     VPC_CUDA(top, cudaStreamSynchronize(G->stream[c]));
   }
+  mark("count + sync");
   std::vector<long long> n_own(W, 0), n_halo(W, 0), n_bo(W, 0);
   for (int c = 0; c < W; ++c)
     for (int d = 0; d < W; ++d) { n_own[d] += cnt[((size_t)c * W + d) * 3]; n_halo[d] += cnt[((size_t)c * W + d) * 3 + 1]; n_bo[d] += cnt[((size_t)c * W + d) * 3 + 2]; }
@@ -189,6 +208,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     VPC_CUDA(top, cudaMemsetAsync(G->comm[d]->heap + sa[d].L.bits[1], 0, 4ull * sa[d].nwords, G->stream[d]));
   }
   for (int d = 0; d < W; ++d) { DeviceGuard g(G->sub[d]->device); VPC_CUDA(top, cudaStreamSynchronize(G->stream[d])); }   // buffers exist and are clear everywhere
+  mark("buffers + clear + sync");
   // ---- deal the points
   for (int c = 0; c < W; ++c) {
     vpc_ctx* sc = G->sub[c];
@@ -223,6 +243,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
         VPC_LAUNCH(sc, k_gen_signal_all, 1, 32, G->stream[d], sa[d].P, (const unsigned long long*)sa[d].epoch, kPhHome);
       }
     }
+  mark("enqueue scatter + slab step");
   // ---- results home, then to the caller's arrays
   for (int c = 0; c < W; ++c) {
     vpc_ctx* sc = G->sub[c];
@@ -246,6 +267,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     VPC_CUDA(top, sc->stager.finish(pool));
     VPC_CUDA(top, cudaStreamSynchronize(G->stream[c]));
   }
+  mark("fetch + D2H + sync");
   if (status[1] != 0) return fail(top, VPC_E_CUDA, (status[1] & 1) ? "a device did not reach an exchange point in time (peer wait timed out)" : "exchange buffer overflow");
   if (cluster_amount) *cluster_amount = status[0];
   return VPC_OK;
@@ -306,8 +328,16 @@ int group_icp(vpc_ctx* top, const double* model_xyz, int64_t m, const double* da
   if (sse_last) *sse_last = out[12];
   if (iters_done) *iters_done = (int32_t)out[13];
   if (order_last) {
-    DeviceGuard g(G->sub[0]->device);
-    cudaError_t ce = cudaMemcpy(order_last, G->comm[0]->heap + plan[0]->a.L.order, 4ull * n, cudaMemcpyDeviceToHost);
+    vpc_ctx* sc = G->sub[0];
+    DeviceGuard g(sc->device);
+    int* d_order = nullptr;                                  // the data copy is no longer needed: reuse nothing, a scratch buffer is simplest
+    cudaError_t ce = cudaMalloc(&d_order, 4ull * n);
+    if (ce == cudaSuccess) {
+      k_icpd_order_gather<<<blocks_for(n, 256), 256, 0, G->stream[0]>>>(plan[0]->a, d_order);
+      ce = cudaMemcpyAsync(order_last, d_order, 4ull * n, cudaMemcpyDeviceToHost, G->stream[0]);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(G->stream[0]);
+      cudaFree(d_order);
+    }
     if (ce != cudaSuccess) { top->err = cudaGetErrorString(ce); cleanup(); return VPC_E_CUDA; }
   }
   int32_t bits = 0;

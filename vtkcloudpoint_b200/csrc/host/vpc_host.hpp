@@ -194,126 +194,28 @@ class MainForm {
   }
 
   // ---- the blocked clustering: getClusterFromMotor (FrmMain.cs:1214-1291) -> DoWork3 / StartCode (:1340-1361, :2782-2794)
-  // -> CompleteWork3 (:1432-1520).  Engine = the two DBSCAN entry points, so that the same host flow can be driven by any
-  // implementation of them (the tests drive it with libvpc and with the oracle and compare).
-  struct Engine {
-    // dbscan(mx, my, n, eps, minPts, cf, cluster_id out) -> clusterAmount
-    virtual int dbscan(const double* mx, const double* my, int64_t n, double eps, int minPts, int cf, int32_t* cid) = 0;
-    // one DBImproved per cell (cf = 0 each): cell-local ids, per-cell clusterAmount
-    virtual void dbscan_cells(const double* mx, const double* my, int64_t n, const int64_t* off, int n_cells, double eps, int minPts, int32_t* cid,
-                              int32_t* per_cell) = 0;
-    virtual ~Engine() {}
-  };
-  struct VpcEngine : Engine {
-    Context& c;
-    explicit VpcEngine(Context& ctx) : c(ctx) {}
-    int dbscan(const double* mx, const double* my, int64_t n, double eps, int minPts, int cf, int32_t* cid) override {
-      std::vector<uint8_t> key(n), cls(n);
-      int32_t amount = cf;
-      c.check(vpc_dbscan_l1_2d(c.get(), mx, my, n, eps, minPts, cf, cid, key.data(), cls.data(), &amount));
-      return amount;
-    }
-    void dbscan_cells(const double* mx, const double* my, int64_t n, const int64_t* off, int n_cells, double eps, int minPts, int32_t* cid,
-                      int32_t* per_cell) override {
-      std::vector<uint8_t> key(n), cls(n);
-      c.check(vpc_dbscan_l1_2d_cells(c.get(), mx, my, n, off, n_cells, eps, minPts, cid, key.data(), cls.data(), per_cell));
-    }
-  };
-
+  // -> CompleteWork3 (:1432-1520): ONE call into the library, which runs the whole flow on the device (csrc/blocked.cuh)
   struct BlockedResult {
     std::vector<int32_t> clusterId;   // per ORIGINAL point; points that fall into no cell keep 0
     int clusterSum = 0;               // MainForm.clusterSum after CompleteWork3
     int delSum = 0, rows = 0, cols = 0;
+    int64_t unassigned = 0, shared = 0;
+    std::vector<int64_t> clusForMerge;   // the list of :1517-1520 as point indices
+    std::vector<int32_t> mergeId;        // their ids
   };
 
-  static BlockedResult ClusterBlocked(Engine& eng, const std::vector<double>& mx, const std::vector<double>& my, double eps, int minPts, int ptsInCell) {
+  static BlockedResult ClusterBlocked(Context& c, const std::vector<double>& mx, const std::vector<double>& my, double eps, int minPts, int ptsInCell) {
     const int64_t n = (int64_t)mx.size();
     if (n == 0) throw MException("empty cloud");
-    // ---- getClusterFromMotor: sort key, first cell, grid of cells (strict lower / inclusive upper bounds, Tools.cs:510-513)
-    const double x_min = *std::min_element(mx.begin(), mx.end()), x_max = *std::max_element(mx.begin(), mx.end());
-    const double y_min = *std::min_element(my.begin(), my.end()), y_max = *std::max_element(my.begin(), my.end());
-    std::vector<int64_t> srt(n);
-    std::iota(srt.begin(), srt.end(), 0);
-    std::stable_sort(srt.begin(), srt.end(), [&](int64_t a, int64_t b) {        // FrmMain.cs:1229-1233, ties pinned to the original order
-      return std::max(mx[a] - x_min, my[a] - y_min) < std::max(mx[b] - x_min, my[b] - y_min);
-    });
-    const int64_t n0 = std::min<int64_t>(ptsInCell, n);
-    double cell_x = -INFINITY, cell_y = -INFINITY;
-    for (int64_t k = 0; k < n0; ++k) { cell_x = std::max(cell_x, mx[srt[k]]); cell_y = std::max(cell_y, my[srt[k]]); }
-    cell_x -= x_min; cell_y -= y_min;                                         // :1255-1256
-    if (!(cell_x > 0 && cell_y > 0)) throw MException("degenerate first cell (the C# divides by zero, FrmMain.cs:1257)");
     BlockedResult out;
-    out.rows = (int)((y_max - y_min) / cell_y) + 1;                           // :1257
-    out.cols = (int)((x_max - x_min) / cell_x) + 1;                           // :1258
-    std::vector<int64_t> order(srt.begin(), srt.begin() + n0), off{0, n0};
-    for (int p = 0; p < out.rows; ++p)
-      for (int q = 0; q < out.cols; ++q) {
-        if (p == 0 && q == 0) continue;
-        const double lo_x = x_min + q * cell_x, lo_y = y_min + p * cell_y;
-        const double hi_x = (q == out.cols - 1) ? x_max : x_min + (q + 1) * cell_x, hi_y = (p == out.rows - 1) ? y_max : y_min + (p + 1) * cell_y;
-        for (int64_t k = 0; k < n; ++k) {                                     // FindAll over the SORTED rawData
-          const int64_t i = srt[k];
-          if (mx[i] > lo_x && my[i] > lo_y && mx[i] <= hi_x && my[i] <= hi_y) order.push_back(i);
-        }
-        off.push_back((int64_t)order.size());
-      }
-    const int n_cells = (int)off.size() - 1;
-    const int64_t nt = (int64_t)order.size();
-    std::vector<double> cx(nt), cy(nt);
-    for (int64_t k = 0; k < nt; ++k) { cx[k] = mx[order[k]]; cy[k] = my[order[k]]; }
-    // ---- DoWork3 / StartCode: every cell in one batched call
-    std::vector<int32_t> cid(nt), per_cell(n_cells);
-    eng.dbscan_cells(cx.data(), cy.data(), nt, off.data(), n_cells, eps, minPts, cid.data(), per_cell.data());
-    int clusterSum = 1;                                                       // :1346
-    for (int v : per_cell) clusterSum += v;                                   // :2789
-    // ---- CompleteWork3: renumber, drop clusters of <= 3 points (with the C#'s off-by-one), re-cluster the noise globally
-    int idNow = 0, delSum = 0;
-    std::vector<int64_t> merge;
-    for (int c = 0; c < n_cells; ++c) {
-      const int64_t a = off[c], b = off[c + 1];
-      if (a == b) continue;                                                   // :1448
-      std::vector<int64_t> pos(b - a);
-      std::iota(pos.begin(), pos.end(), a);
-      std::stable_sort(pos.begin(), pos.end(), [&](int64_t u, int64_t v) { return cid[u] < cid[v]; });   // :1449-1459
-      int idLast = cid[pos[0]], clusLen = 0;                                  // :1460
-      if (idLast != 0) { ++idNow; clusLen = 1; }                              // :1461-1465
-      for (int64_t k : pos) {                                                 // :1470
-        const int id = cid[k];
-        if (id == 0) { merge.push_back(k); continue; }                        // :1475
-        if (id != idLast) {                                                   // :1479
-          if (clusLen <= 3 && idLast != 0) {                                  // :1481
-            ++delSum;
-            for (int t = 0; t < clusLen; ++t) {                               // :1485-1488
-              if ((int64_t)merge.size() - 1 - t < 0) throw MException("Index was out of range (clusForMerge)");
-              cid[merge[merge.size() - 1 - t]] = 0;
-            }
-          } else {
-            ++idNow;                                                          // :1492
-          }
-          clusLen = 1;
-        } else {
-          ++clusLen;                                                          // :1498
-        }
-        cid[k] = idNow;                                                       // :1500
-        merge.push_back(k);
-        idLast = id;
-      }
-    }
-    const int cf = clusterSum - delSum - 1;                                   // :1509
-    std::vector<int64_t> zero;
-    for (int64_t k : merge) if (cid[k] == 0) zero.push_back(k);               // :1510
-    int amount = cf;
-    if (!zero.empty()) {
-      std::vector<double> zx(zero.size()), zy(zero.size());
-      std::vector<int32_t> zc(zero.size());
-      for (size_t t = 0; t < zero.size(); ++t) { zx[t] = cx[zero[t]]; zy[t] = cy[zero[t]]; }
-      amount = eng.dbscan(zx.data(), zy.data(), (int64_t)zero.size(), eps, minPts, cf, zc.data());   // :1516
-      for (size_t t = 0; t < zero.size(); ++t) cid[zero[t]] = zc[t];
-    }
     out.clusterId.assign(n, 0);
-    for (int64_t k = 0; k < nt; ++k) out.clusterId[order[k]] = cid[k];
-    out.clusterSum = amount;                                                  // :1538
-    out.delSum = delSum;
+    out.clusForMerge.assign(3 * n, 0); out.mergeId.assign(3 * n, 0);
+    int32_t cs = 0, ds = 0, r = 0, q = 0, csc = 0;
+    int64_t nm = 0;
+    c.check(vpc_dbscan_blocked_ref_ex(c.get(), mx.data(), my.data(), n, eps, minPts, ptsInCell, out.clusterId.data(), &cs, &ds, &r, &q, &out.unassigned, &out.shared,
+                                      out.clusForMerge.data(), out.mergeId.data(), &nm, &csc));
+    out.clusForMerge.resize(nm); out.mergeId.resize(nm);
+    out.clusterSum = cs; out.delSum = ds; out.rows = r; out.cols = q;
     return out;
   }
 };

@@ -1,18 +1,21 @@
 // icp_dist.cuh -- ICP across the GPUs of a box, exchanging over peer memory (comm.cuh) instead of NCCL all_reduces.
 //
-// One round of ICP.go_hell_ICP (BaseClass/ICP.cs:23-180, intended algorithm, see icp.cuh) in two splits:
+// One round of ICP.go_hell_ICP (BaseClass/ICP.cs:23-180, intended algorithm, see icp.cuh) in two splits.  Data moves
+// by PULL: a producer writes into its OWN heap (device-scope fences only), its last block publishes one flag (one system fence per
+// rank), and consumers read the producer's heap with peer loads -- a system fence per block after peer stores cost 30-50 us per
+// kernel on 2 x B200 (profiles/r02_multi_gpu.md), peer loads hide their ~1 us latency behind the other threads.
 //
 //  TARGET SHARDED (the model is cut into `world` index ranges, the data is replicated) -- for models that do not fit / weak scaling:
-//    k_icpd_nn_push      every rank: local nearest model point of ALL data points; the candidate {d2, global index, y} of point i is
-//                        PUSHED into the heap of the rank that owns i's slice of the reduction (coalesced peer stores); flag
-//    k_icpd_reduce_push  owner of a slice: exact argmin over the `world` candidates (ties -> lowest global index, ICP.cs:240),
-//                        16 sums over its slice, winners pushed into everybody's order[]; the 16 doubles pushed to everybody; flag
-//    k_icpd_solve        every rank: wait, add the `world` partial sums in rank order (identical on all ranks), quaternion solve
+//    k_icpd_nn_local     every rank: nearest point of its shard for ALL data points -> candidate {d2, global index, point} in its heap; flag
+//    k_icpd_reduce       owner of a slice of the data: pulls the `world` candidates of each of its points, exact argmin (ties -> lowest
+//                        global index, ICP.cs:240), 16 sums over the slice -> its heap; flag
+//    k_icpd_solve        every rank: pulls the `world` partial sums, adds them in rank order (identical on all ranks), quaternion solve
 //  SOURCE SHARDED (the data is cut, the model is replicated) -- the right split when the model fits one GPU (last row):
-//    k_icpd_iter_push    every rank: transform + exact NN + sums for ITS data slice, winners into everybody's order[], sums pushed; flag
+//    k_icpd_iter_local   every rank: transform + exact NN + sums for ITS data slice -> its heap; flag
 //    k_icpd_solve        as above
-// Flags carry an epoch (one per executed round); partial-sum slots are double-buffered by epoch parity.  Kernels wait first and
-// signal last, so the ranks can be emulated phase by phase on one GPU.
+//  k_icpd_order_gather   after the rounds: every rank pulls the winners of the other slices (correspondences of the last round)
+// Flags carry an epoch (one per executed round); the sums are double-buffered by epoch parity.  Kernels wait first and signal last, so
+// the ranks can be emulated phase by phase on one GPU.
 #pragma once
 
 #include "comm.cuh"
@@ -21,9 +24,9 @@
 namespace vpc {
 
 struct IcpDistLayout {         // byte offsets in every rank's heap
-  size_t cand_d2, cand_idx, cand_y[3];   // [world][slice_cap] each: candidates pushed by rank r for the points of MY slice
-  size_t sums;                           // double[2][world][kIcpSums]
-  size_t order;                          // int[n] winners (global model indices), identical on every rank after a round
+  size_t cand_d2, cand_idx, cand_y[3];   // [n] each: THIS rank's candidate for every data point (target sharded); peers PULL them
+  size_t sums;                           // double[2][kIcpSums]: this rank's 16 sums, double-buffered by epoch parity; peers pull them
+  size_t order;                          // int[n]: winners (global model indices) of the points THIS rank reduces (its slice)
 };
 
 struct IcpDistArgs {
@@ -54,7 +57,7 @@ __device__ __forceinline__ bool icpd_block_reduce(const double (&s)[kIcpSums], d
 #pragma unroll
     for (int w = 0; w < kIterBlock / kWarp; ++w) v += sm[threadIdx.x][w];
     partial[(long long)blockIdx.x * kIcpSums + threadIdx.x] = v;
-    __threadfence_system();         // system scope: the block's peer stores (winners into everybody's order[]) precede the ticket too
+    __threadfence();
   }
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -85,47 +88,43 @@ __device__ __forceinline__ void icpd_sums_of(double (&s)[kIcpSums], double px, d
   s[15] = ex * ex + ey * ey + ez * ez;                  // ICP.cs:131
 }
 
-// last block of a producing kernel: S[16] -> everybody's slot for this rank and parity, then the flag
-__device__ __forceinline__ void icpd_push_sums(const IcpDistArgs& a, const double* S, unsigned long long E) {
-  const int q = threadIdx.x / kIcpSums, k = threadIdx.x % kIcpSums;
-  if (q < a.P.world) {
-    double* dst = a.P.at<double>(q, a.L.sums) + ((E & 1) * a.P.world + a.P.rank) * kIcpSums + k;
-    *dst = S[k];
-  }
-  __threadfence_system();           // every storing thread orders its own peer store before the flags (last block only: cheap)
+// last block of a producing kernel: S[16] -> this rank's slot for the parity, ONE system fence, then the flags
+__device__ __forceinline__ void icpd_publish_sums(const IcpDistArgs& a, const double* S, unsigned long long E) {
+  if (threadIdx.x < kIcpSums) a.P.at<double>(a.P.rank, a.L.sums)[(E & 1) * kIcpSums + threadIdx.x] = S[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < a.P.world) comm_signal(a.P, (int)threadIdx.x, kPhIcpSums, E, 0ull);
 }
 
-// ---- target sharded, step 1 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIterBlock) k_icpd_nn_push(IcpModel g, const double* __restrict__ data, IcpDistArgs a) {
+// ---- target sharded, step 1: this shard's candidate for every data point, into the own heap ------------------------------------
+__global__ void __launch_bounds__(kIterBlock) k_icpd_nn_local(IcpModel g, const double* __restrict__ data, IcpDistArgs a) {
   if (a.st->done) return;
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch + 1;
+  const int me = a.P.rank;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < a.n) {
     const IcpGridCtrl c = *g.ctrl;
     double px = __ldg(data + i), py = __ldg(data + a.n + i), pz = __ldg(data + 2ll * a.n + i);
     icp_apply_rt(a.st, px, py, pz);
     NnBest b;
-    if (a.P.rank == 0) {
+    if (me == 0) {
       icp_match(g, c, px, py, pz, b);          // shard 0 holds model[0]: the literal scan's start value and its NaN corner cases (ICP.cs:233)
     } else {
       b.d = INFINITY; b.i = 0x7fffffff; b.x = b.y = b.z = 0.0;
       if (c.n_valid > 0 && finite3(px, py, pz)) icp_nearest(g, c, px, py, pz, b);
       if (b.i == 0x7fffffff) b.d = INFINITY;   // nothing to offer: never wins
     }
-    const int owner = i / a.slice_cap, k = i - owner * a.slice_cap;
-    const size_t slot = (size_t)a.P.rank * a.slice_cap + k;
-    a.P.at<double>(owner, a.L.cand_d2)[slot] = b.d;
-    a.P.at<int>(owner, a.L.cand_idx)[slot] = (b.i == 0x7fffffff) ? 0x7fffffff : b.i + a.idx_offset;
-    a.P.at<double>(owner, a.L.cand_y[0])[slot] = b.x;
-    a.P.at<double>(owner, a.L.cand_y[1])[slot] = b.y;
-    a.P.at<double>(owner, a.L.cand_y[2])[slot] = b.z;
+    a.P.at<double>(me, a.L.cand_d2)[i] = b.d;
+    a.P.at<int>(me, a.L.cand_idx)[i] = (b.i == 0x7fffffff) ? 0x7fffffff : b.i + a.idx_offset;
+    a.P.at<double>(me, a.L.cand_y[0])[i] = b.x;
+    a.P.at<double>(me, a.L.cand_y[1])[i] = b.y;
+    a.P.at<double>(me, a.L.cand_y[2])[i] = b.z;
   }
-  __syncthreads();                  // one system fence per block, after the block barrier (see slab.cuh)
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();                           // own heap: device scope; the last block's system fence publishes
     s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
@@ -135,8 +134,8 @@ __global__ void __launch_bounds__(kIterBlock) k_icpd_nn_push(IcpModel g, const d
   if ((int)threadIdx.x < a.P.world) comm_signal(a.P, (int)threadIdx.x, kPhIcpNn, E, 0ull);
 }
 
-// ---- target sharded, step 2: my slice of the data points ----------------------------------------------------------------
-__global__ void __launch_bounds__(kIterBlock) k_icpd_reduce_push(const double* __restrict__ data, IcpDistArgs a) {
+// ---- target sharded, step 2: my slice of the data points, candidates pulled from every shard ---------------------------------------
+__global__ void __launch_bounds__(kIterBlock) k_icpd_reduce(const double* __restrict__ data, IcpDistArgs a) {
   if (a.st->done) return;
   __shared__ double S[kIcpSums];
   const unsigned long long E = *a.epoch + 1;
@@ -150,27 +149,28 @@ __global__ void __launch_bounds__(kIterBlock) k_icpd_reduce_push(const double* _
   if (k < a.slice_cap && i < a.n) {
     // exact argmin over the shards in rank order with the literal scan's rule: strict '<', ties to the lowest index; shard 0's
     // candidate is the start value (a NaN there -- non-finite data point or model[0] -- is never beaten, ICP.cs:233-244)
-    const double* cd = a.P.at<double>(me, a.L.cand_d2);
-    const int* ci = a.P.at<int>(me, a.L.cand_idx);
-    double bd = __ldcg(cd + k); int bi = __ldcg(ci + k), br = 0;          // L2 loads: the candidates arrived as peer stores
-    for (int r = 1; r < a.P.world; ++r) {
-      const double d = __ldcg(cd + (size_t)r * a.slice_cap + k); const int j = __ldcg(ci + (size_t)r * a.slice_cap + k);
-      if (d < bd || (d == bd && j < bi)) { bd = d; bi = j; br = r; }
+    double d[kMaxWorld]; int j[kMaxWorld];
+#pragma unroll 1
+    for (int r = 0; r < a.P.world; ++r) {       // all pulls first: independent peer loads
+      d[r] = ld_relaxed_sys_f64(a.P.at<double>(r, a.L.cand_d2) + i);
+      j[r] = ld_relaxed_sys_s32(a.P.at<int>(r, a.L.cand_idx) + i);
     }
-    const size_t slot = (size_t)br * a.slice_cap + k;
-    const double bx = __ldcg(a.P.at<double>(me, a.L.cand_y[0]) + slot), by = __ldcg(a.P.at<double>(me, a.L.cand_y[1]) + slot),
-                 bz = __ldcg(a.P.at<double>(me, a.L.cand_y[2]) + slot);
+    double bd = d[0]; int bi = j[0], br = 0;
+    for (int r = 1; r < a.P.world; ++r)
+      if (d[r] < bd || (d[r] == bd && j[r] < bi)) { bd = d[r]; bi = j[r]; br = r; }
+    const double bx = ld_relaxed_sys_f64(a.P.at<double>(br, a.L.cand_y[0]) + i), by = ld_relaxed_sys_f64(a.P.at<double>(br, a.L.cand_y[1]) + i),
+                 bz = ld_relaxed_sys_f64(a.P.at<double>(br, a.L.cand_y[2]) + i);
     double px = __ldg(data + i), py = __ldg(data + a.n + i), pz = __ldg(data + 2ll * a.n + i);
     icp_apply_rt(a.st, px, py, pz);
     icpd_sums_of(s, px, py, pz, bx, by, bz);
-    for (int q = 0; q < a.P.world; ++q) a.P.at<int>(q, a.L.order)[i] = bi;
+    a.P.at<int>(me, a.L.order)[i] = bi;
   }
   if (!icpd_block_reduce(s, a.partial, a.ticket, S)) return;
-  icpd_push_sums(a, S, E);
+  icpd_publish_sums(a, S, E);
 }
 
 // ---- source sharded: my slice of the data against the whole (replicated) model ---------------------------------------------
-__global__ void __launch_bounds__(kIterBlock) k_icpd_iter_push(IcpModel g, const double* __restrict__ data, IcpDistArgs a) {
+__global__ void __launch_bounds__(kIterBlock) k_icpd_iter_local(IcpModel g, const double* __restrict__ data, IcpDistArgs a) {
   if (a.st->done) return;
   __shared__ double S[kIcpSums];
   const unsigned long long E = *a.epoch + 1;
@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(kIterBlock) k_icpd_iter_push(IcpModel g, const
     NnBest b;
     icp_match(g, c, px, py, pz, b);
     icpd_sums_of(s, px, py, pz, b.x, b.y, b.z);
-    for (int q = 0; q < a.P.world; ++q) a.P.at<int>(q, a.L.order)[i] = b.i;
+    a.P.at<int>(me, a.L.order)[i] = b.i;
   }
   if (!icpd_block_reduce(s, a.partial, a.ticket, S)) return;
-  icpd_push_sums(a, S, E);
+  icpd_publish_sums(a, S, E);
 }
 
 // ---- every rank: the `world` partial sums in rank order -> the rigid step (replicated, bit-identical on all ranks) -------------
@@ -201,9 +201,11 @@ __global__ void __launch_bounds__(32) k_icpd_solve(IcpDistArgs a) {
   if ((int)threadIdx.x < a.P.world) comm_wait(a.P, (int)threadIdx.x, kPhIcpSums, E);
   __syncwarp();
   if (threadIdx.x < kIcpSums) {
-    const double* src = a.P.at<double>(a.P.rank, a.L.sums) + (E & 1) * a.P.world * kIcpSums + threadIdx.x;
+    double part[kMaxWorld];
+#pragma unroll 1
+    for (int r = 0; r < a.P.world; ++r) part[r] = ld_relaxed_sys_f64(a.P.at<double>(r, a.L.sums) + (E & 1) * kIcpSums + threadIdx.x);   // independent pulls
     double v = 0.0;
-    for (int r = 0; r < a.P.world; ++r) v += ld_relaxed_sys_f64(src + r * kIcpSums);
+    for (int r = 0; r < a.P.world; ++r) v += part[r];      // rank order: the same sum on every rank
     S[threadIdx.x] = v;
   }
   __syncwarp();
@@ -211,6 +213,15 @@ __global__ void __launch_bounds__(32) k_icpd_solve(IcpDistArgs a) {
     icp_solve_round(S, a.n, a.e, a.max_iters, a.st);
     *a.epoch = E;
   }
+}
+
+// correspondences of the last executed round: every slice from the rank that reduced it (the solve of that round has waited for all
+// ranks' sums, which they publish after writing their winners)
+__global__ void __launch_bounds__(256) k_icpd_order_gather(IcpDistArgs a, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int owner = i / a.slice_cap;
+  out[i] = ld_relaxed_sys_s32(a.P.at<int>(owner, a.L.order) + i);
 }
 
 }  // namespace vpc

@@ -43,6 +43,7 @@ struct SlabArgs {
   unsigned char* is_key_l; int* gkey;       // per local point: core flag, merged cluster key
   int* counters;                            // [0..1] halo strip counts, [2] pairs count, [3] ticket
   int* pair_root;                           // [cap_pairs] sorted position of the local root behind every pair this rank reported
+  int* bidx;                                // [2 * cap] pre-cut mode: local indices of the own points inside a halo strip (k_slb_halo_pack)
   unsigned long long* epoch;                // step counter (device resident: graph replays advance it)
   int* cid; unsigned char* is_key; unsigned char* is_classed;   // outputs per owned point
   int* status;                              // [0] cluster_amount, [1] error bits (1 timeout, 2 overflow), [2] halo-in max, [3] pairs, [4] heads (own), [5] epoch, [6] halo points pulled
@@ -53,35 +54,40 @@ __device__ __forceinline__ bool slb_finite(double x, double y) { return finite_d
 // ---- halo strips: pack locally, tell the neighbours -----------------------------------------------------------------
 __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a) {
   __shared__ bool s_last;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool toL = false, toR = false;
-  double xi = 0, yi = 0;
-  if (i < a.n_own) {
-    xi = a.lx[i]; yi = a.ly[i];
-    if (slb_finite(xi, yi)) {
-      const double u = xi + yi;
-      toL = a.has_left && (u - a.H < a.s_lo);
-      toR = a.has_right && (u + a.H >= a.s_hi);
-    }
-  }
-  const int sl = db_append_slot(toL, a.counters + 0);
-  const int sr = db_append_slot(toR, a.counters + 1);
   const int me = a.P.rank;
-  if (sl >= 0 && sl < a.cap) { a.P.at<double>(me, a.L.pack_x[0])[sl] = xi; a.P.at<double>(me, a.L.pack_y[0])[sl] = yi; a.P.at<int>(me, a.L.pack_g[0])[sl] = a.lg[i]; }
-  if (sr >= 0 && sr < a.cap) { a.P.at<double>(me, a.L.pack_x[1])[sr] = xi; a.P.at<double>(me, a.L.pack_y[1])[sr] = yi; a.P.at<int>(me, a.L.pack_g[1])[sr] = a.lg[i]; }
+  for (int base = blockIdx.x * blockDim.x; base < a.n_own; base += gridDim.x * blockDim.x) {   // block-uniform trip count (warp ballots inside)
+    const int i = base + threadIdx.x;
+    bool toL = false, toR = false;
+    double xi = 0, yi = 0;
+    if (i < a.n_own) {
+      xi = a.lx[i]; yi = a.ly[i];
+      if (slb_finite(xi, yi)) {
+        const double u = xi + yi;
+        toL = a.has_left && (u - a.H < a.s_lo);
+        toR = a.has_right && (u + a.H >= a.s_hi);
+      }
+    }
+    const int sl = db_append_slot(toL, a.counters + 0);
+    const int sr = db_append_slot(toR, a.counters + 1);
+    const int sb = db_append_slot(toL || toR, a.counters + 4);      // the same points are this rank's own pair candidates later
+    if (sl >= 0 && sl < a.cap) { a.P.at<double>(me, a.L.pack_x[0])[sl] = xi; a.P.at<double>(me, a.L.pack_y[0])[sl] = yi; a.P.at<int>(me, a.L.pack_g[0])[sl] = a.lg[i]; }
+    if (sr >= 0 && sr < a.cap) { a.P.at<double>(me, a.L.pack_x[1])[sr] = xi; a.P.at<double>(me, a.L.pack_y[1])[sr] = yi; a.P.at<int>(me, a.L.pack_g[1])[sr] = a.lg[i]; }
+    if (sb >= 0 && sb < 2 * a.cap) a.bidx[sb] = i;
+  }
   __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block.
   if (threadIdx.x == 0) {           // The stores are to the OWN heap (peers pull them through this GPU's L2): device scope is enough
-    __threadfence();                // here; the last block's system fence + st.release.sys publish.  (A system fence per thread cost
-    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);   // ~40 us per kernel at 1M points, one per block still ~20 us.)
+    __threadfence();                // here; the last block's system fence + st.release.sys publish.
+    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
   __threadfence_system();
   const unsigned long long E = *a.epoch + 1;
   *a.epoch = E;                                           // the later kernels of this step read it
-  const int cl = ld_relaxed_s32(a.counters + 0), cr = ld_relaxed_s32(a.counters + 1);
+  const int cl = ld_relaxed_s32(a.counters + 0), cr = ld_relaxed_s32(a.counters + 1), cb = ld_relaxed_s32(a.counters + 4);
   if (cl > a.cap || cr > a.cap) atomicOr(&a.P.hdr(me)->error, 2);
-  a.counters[0] = 0; a.counters[1] = 0; a.counters[3] = 0;
+  a.counters[0] = 0; a.counters[1] = 0; a.counters[3] = 0; a.counters[4] = 0;
+  a.status[7] = min(cb, 2 * a.cap);                       // number of own boundary points listed in bidx
   if (a.has_left) comm_signal(a.P, me - 1, kPhHalo, E, (unsigned long long)min(cl, a.cap));
   if (a.has_right) comm_signal(a.P, me + 1, kPhHalo, E, (unsigned long long)min(cr, a.cap));
 }
@@ -150,6 +156,40 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_pairs_pack(SlabArgs a, DbArgs 
   for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhPairs, E, (unsigned long long)min(c, a.cap_pairs));
 }
 
+// the same for the direct (non-banded) layout in pre-cut mode, without a pass over the whole cloud: the candidates are the halo slots
+// and the own boundary points k_slb_halo_pack listed; core flag and key come from the workspace through keyslot (by local index)
+__global__ void __launch_bounds__(kDbBlock) k_slb_pairs_small(SlabArgs a, DbArgs d) {
+  __shared__ bool s_last;
+  const int me = a.P.rank;
+  const int n_cand = 2 * a.cap + a.status[7];
+  for (int base = blockIdx.x * blockDim.x; base < n_cand; base += gridDim.x * blockDim.x) {
+    const int j = base + threadIdx.x;
+    bool want = false;
+    int key = -1, g = -1, root = -1;
+    if (j < n_cand) {
+      const int i = (j < 2 * a.cap) ? a.n_own + j : a.bidx[j - 2 * a.cap];
+      const int2 ks = d.keyslot[i];
+      if (ks.x >= 0) {
+        const int pos = __ldg(d.cell_start + ks.x) + ks.y;
+        if (d.core[pos] == 1) { want = true; root = d.rec[pos].parent; key = d.rec[root].cinfo.y; g = a.lg[i]; }
+      }
+    }
+    const int s = db_append_slot(want, a.counters + 2);
+    if (s >= 0 && s < a.cap_pairs) { a.P.at<int2>(me, a.L.pairs)[s] = make_int2(g, key); a.pair_root[s] = root; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1); }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence_system();
+  const unsigned long long E = *a.epoch;
+  const int c = ld_relaxed_s32(a.counters + 2);
+  if (c > a.cap_pairs) atomicOr(&a.P.hdr(me)->error, 2);
+  a.counters[2] = 0; a.counters[3] = 0;
+  a.status[3] = c;
+  for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhPairs, E, (unsigned long long)min(c, a.cap_pairs));
+}
+
 // ---- cross-slab merge: pull everybody's pairs, union the keys that name the same point -----------------------------------
 __global__ void __launch_bounds__(kDbBlock) k_slb_merge(SlabArgs a, MergeTables t) {
   const unsigned long long E = *a.epoch;
@@ -190,16 +230,16 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned* other = a.P.at<unsigned>(me, a.L.bits[(E + 1) & 1]);
-  for (int w = i; w < a.nwords; w += gridDim.x * blockDim.x) other[w] = 0u;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < a.nwords; w += gridDim.x * blockDim.x) other[w] = 0u;
   int remote = 0;
-  if (i < a.n_own && a.is_key_l[i]) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_own; i += gridDim.x * blockDim.x) {
+    if (!a.is_key_l[i]) continue;
     const int g = a.lg[i];
     if (g >= 0 && a.gkey[i] == g) {
       const int home = slb_home_of(a, g);
       const int w = g - a.gstart[home];
-      remote = home != me;
+      remote |= home != me;
       atomicOr_system(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5), 1u << (w & 31));
     }
   }

@@ -306,7 +306,7 @@ void vpc_destroy(vpc_ctx* ctx) {
   {
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
-    for (Arena* a : {&ctx->db, &ctx->io, &ctx->icp_model, &ctx->icp_work, &ctx->st})
+    for (Arena* a : {&ctx->db, &ctx->io, &ctx->icp_model, &ctx->icp_work, &ctx->st, &ctx->blk})
       if (a->base) cudaFree(a->base);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     ctx->stager.release();
@@ -1204,166 +1204,7 @@ int vpc_dbscan_slab_finish_merge_dev(vpc_ctx* ctx, const int32_t* d_pairs_all, i
   return VPC_OK;
 }
 
-// ---- the blocked ("分块") clustering as ONE call: MainForm.getClusterFromMotor (FrmMain.cs:1214-1291) -> DoWork3 / StartCode
-// (:1340-1361, :2782-2794) -> CompleteWork3 (:1432-1520), quirks included.  The host part is the C#'s own
-// host logic (sort, cell boxes, renumbering); both clustering steps run on the GPU (all cells in one batched launch).
-int vpc_dbscan_blocked_ref(vpc_ctx* ctx, const double* mx, const double* my, int64_t n, double eps, int32_t min_pts, int32_t pts_in_cell,
-                           int32_t* cluster_id, int32_t* cluster_sum, int32_t* del_sum, int32_t* rows_out, int32_t* cols_out, int64_t* n_unassigned) {
-  if (!ctx) return VPC_E_BADARG;
-  if (n <= 0 || !mx || !my || !cluster_id || !cluster_sum || pts_in_cell <= 0) return fail(ctx, VPC_E_BADARG, "bad arguments (the C# returns early on an empty cloud, FrmMain.cs:1228)");
-  if (n > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "n exceeds 2^31-2");
-  // ---- getClusterFromMotor: sort key max(mx - xmin, my - ymin) (stable: List.Sort's tie order is undefined, pinned to the input
-  // order), first cell = the first pts_in_cell points, then a rows x cols grid of boxes (lo, hi] (Tools.getListByScale2, Tools.cs:510-513)
-  double x_min = mx[0], x_max = mx[0], y_min = my[0], y_max = my[0];
-  for (int64_t i = 0; i < n; ++i) {
-    // the C#'s Min/Max/Sort on NaN keys give an order-dependent partition; non-finite coordinates are rejected here
-    if (!std::isfinite(mx[i]) || !std::isfinite(my[i])) return fail(ctx, VPC_E_BADARG, "the blocked partition needs finite coordinates");
-    x_min = std::min(x_min, mx[i]); x_max = std::max(x_max, mx[i]);
-    y_min = std::min(y_min, my[i]); y_max = std::max(y_max, my[i]);
-  }
-  std::vector<double> key(n);
-  for (int64_t i = 0; i < n; ++i) key[i] = std::max(mx[i] - x_min, my[i] - y_min);
-  std::vector<int32_t> srt(n);
-  {
-    double* d_key = nullptr; int32_t* d_ord = nullptr;
-    {
-      std::lock_guard<std::mutex> lk(ctx->mu);
-      DeviceGuard g(ctx->device);
-      VPC_CUDA(ctx, cudaMalloc(&d_key, 8ull * n));
-      if (cudaMalloc(&d_ord, 4ull * n) != cudaSuccess) { cudaFree(d_key); return fail(ctx, VPC_E_NOMEM, "cudaMalloc failed"); }
-      cudaMemcpyAsync(d_key, key.data(), 8ull * n, cudaMemcpyHostToDevice, ctx->own_stream);
-    }
-    int rc = vpc_argsort_f64_dev(ctx, d_key, n, d_ord, ctx->own_stream);      // the device radix sort (sort.cuh)
-    {
-      std::lock_guard<std::mutex> lk(ctx->mu);
-      DeviceGuard g(ctx->device);
-      if (rc == VPC_OK && cudaMemcpyAsync(srt.data(), d_ord, 4ull * n, cudaMemcpyDeviceToHost, ctx->own_stream) != cudaSuccess) rc = VPC_E_CUDA;
-      if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess && rc == VPC_OK) rc = VPC_E_CUDA;
-      cudaFree(d_key); cudaFree(d_ord);
-      if (rc == VPC_E_CUDA) ctx->err = "argsort for the blocked partition failed";
-    }
-    if (rc) return rc;
-  }
-  const int64_t n0 = std::min<int64_t>(pts_in_cell, n);
-  double cell_x = -INFINITY, cell_y = -INFINITY;
-  for (int64_t k = 0; k < n0; ++k) { cell_x = std::max(cell_x, mx[srt[k]]); cell_y = std::max(cell_y, my[srt[k]]); }
-  cell_x -= x_min; cell_y -= y_min;                                                         // FrmMain.cs:1255-1256
-  if (!(cell_x > 0 && cell_y > 0)) return fail(ctx, VPC_E_BADARG, "degenerate first cell: the C# divides by zero here (FrmMain.cs:1257-1258)");
-  const double fr = (y_max - y_min) / cell_y, fc = (x_max - x_min) / cell_x;
-  if (!(fr < 2e9 && fc < 2e9) || (fr + 1) * (fc + 1) > 2e9) return fail(ctx, VPC_E_TOOBIG, "too many cells");
-  const int rows = (int)fr + 1, cols = (int)fc + 1;                                         // :1257-1258
-  if (rows_out) *rows_out = rows;
-  if (cols_out) *cols_out = cols;
-  // box edges exactly as the C# computes them; edge j of an axis = lower bound of box j and upper bound of box j-1
-  std::vector<double> ex((size_t)cols + 1), ey((size_t)rows + 1);
-  for (int q = 0; q < cols; ++q) ex[q] = x_min + q * cell_x;
-  ex[cols] = x_max;
-  for (int p = 0; p < rows; ++p) ey[p] = y_min + p * cell_y;
-  ey[rows] = y_max;
-  auto in_x = [&](double v, int q) { return q >= 0 && q < cols && v > ex[q] && v <= ((q == cols - 1) ? x_max : x_min + (q + 1) * cell_x); };
-  auto in_y = [&](double v, int p) { return p >= 0 && p < rows && v > ey[p] && v <= ((p == rows - 1) ? y_max : y_min + (p + 1) * cell_y); };
-  // cell of every sorted point beyond the first cell: the C# runs FindAll per box over the sorted list, so a box receives its
-  // points in sorted order; the predicate is evaluated literally on the boxes around the arithmetic guess
-  const int64_t n_cells = (int64_t)rows * cols;            // slot 0 = the first cell, box (p, q) -> p * cols + q (box (0,0) is skipped)
-  std::vector<int64_t> cnt((size_t)n_cells + 1, 0);
-  std::vector<int32_t> cell_a(n, -1), cell_b(n, -1);       // up to two boxes per point would already be a rounding anomaly
-  cnt[1] = n0;
-  int64_t unassigned = 0;
-  for (int64_t k = 0; k < n; ++k) {
-    const int64_t i = srt[k];
-    const int q0 = (int)std::min<double>(std::max<double>(std::floor((mx[i] - x_min) / cell_x), 0.0), (double)cols - 1);
-    const int p0 = (int)std::min<double>(std::max<double>(std::floor((my[i] - y_min) / cell_y), 0.0), (double)rows - 1);
-    int found = 0;
-    for (int p = p0 - 1; p <= p0 + 1; ++p)
-      for (int q = q0 - 1; q <= q0 + 1; ++q) {
-        if ((p == 0 && q == 0) || !in_y(my[i], p) || !in_x(mx[i], q)) continue;
-        const int32_t c = (int32_t)((int64_t)p * cols + q);
-        if (found == 0) cell_a[k] = c; else if (found == 1) cell_b[k] = c;
-        ++found; ++cnt[(size_t)c + 1];
-      }
-    if (found > 2) return fail(ctx, VPC_E_BADARG, "a point satisfies more than two cell boxes (degenerate cell size)");
-    if (found == 0 && k >= n0) ++unassigned;
-  }
-  if (n_unassigned) *n_unassigned = unassigned;
-  // CSR: group 0 = first cell (sorted points 0..n0-1), then boxes in (p, q) order; empty groups stay as empty cells
-  std::vector<int64_t> off((size_t)n_cells + 1, 0);
-  for (int64_t c = 0; c < n_cells; ++c) off[(size_t)c + 1] = off[(size_t)c] + cnt[(size_t)c + 1];
-  const int64_t nt = off[(size_t)n_cells];
-  std::vector<int64_t> fill(off.begin(), off.end() - 1);
-  std::vector<int64_t> order(nt);
-  for (int64_t k = 0; k < n0; ++k) order[fill[0]++] = srt[k];
-  for (int64_t k = 0; k < n; ++k) {
-    if (cell_a[k] >= 0) order[fill[cell_a[k]]++] = srt[k];
-    if (cell_b[k] >= 0) order[fill[cell_b[k]]++] = srt[k];
-  }
-  // note: group 0 doubles as box (0,0)'s slot (which the C# never fills), so the cell list has rows * cols entries
-  std::vector<double> cx(nt), cy(nt);
-  for (int64_t k = 0; k < nt; ++k) { cx[k] = mx[order[k]]; cy[k] = my[order[k]]; }
-  // ---- DoWork3 / StartCode: one DBImproved per cell, all cells in one batched call
-  std::vector<int32_t> cid(nt), per_cell((size_t)n_cells);
-  std::vector<uint8_t> fk(std::max<int64_t>(nt, 1)), fc2(std::max<int64_t>(nt, 1));
-  if (n_cells > 2147483646ll) return fail(ctx, VPC_E_TOOBIG, "too many cells");
-  int rc = vpc_dbscan_l1_2d_cells(ctx, cx.data(), cy.data(), nt, off.data(), (int32_t)n_cells, eps, min_pts, cid.data(), fk.data(), fc2.data(), per_cell.data());
-  if (rc) return rc;
-  long long csum = 1;                                                                       // :1346
-  for (int32_t v : per_cell) csum += v;                                                     // :2789
-  // ---- CompleteWork3 (:1443-1520): per cell sort by id, running renumbering, clusters of <= 3 counted points are zeroed (with
-  // the C#'s off-by-one and without a check of a cell's last cluster), all noise is re-clustered globally with cf seeded
-  int id_now = 0, dels = 0;
-  std::vector<int64_t> merge;
-  merge.reserve(nt);
-  std::vector<int64_t> pos;
-  for (int64_t c = 0; c < n_cells; ++c) {
-    const int64_t a = off[(size_t)c], b = off[(size_t)c + 1];
-    if (a == b) continue;                                                                   // :1448
-    pos.resize(b - a);
-    std::iota(pos.begin(), pos.end(), a);
-    std::stable_sort(pos.begin(), pos.end(), [&](int64_t u, int64_t v) { return cid[u] < cid[v]; });   // :1449-1459
-    int id_last = cid[pos[0]], clus_len = 0;                                                // :1460
-    if (id_last != 0) { ++id_now; clus_len = 1; }                                           // :1461-1465
-    for (int64_t k : pos) {                                                                 // :1470
-      const int id = cid[k];
-      if (id == 0) { merge.push_back(k); continue; }                                        // :1475
-      if (id != id_last) {                                                                  // :1479
-        if (clus_len <= 3 && id_last != 0) {                                                // :1481
-          ++dels;
-          for (int t = 0; t < clus_len; ++t) {                                              // :1485-1488
-            if ((int64_t)merge.size() - 1 - t < 0) return fail(ctx, VPC_E_STATE, "the C# indexes clusForMerge[-1] here (ArgumentOutOfRangeException, FrmMain.cs:1487)");
-            cid[merge[merge.size() - 1 - t]] = 0;
-          }
-        } else {
-          ++id_now;                                                                         // :1492
-        }
-        clus_len = 1;
-      } else {
-        ++clus_len;                                                                         // :1498
-      }
-      cid[k] = id_now;                                                                      // :1500
-      merge.push_back(k);
-      id_last = id;
-    }
-  }
-  const int cf = (int)(csum - dels - 1);                                                    // :1509
-  std::vector<int64_t> zero;
-  for (int64_t k : merge) if (cid[k] == 0) zero.push_back(k);                               // :1510
-  int32_t amount = cf;
-  if (!zero.empty()) {
-    const int64_t nz = (int64_t)zero.size();
-    std::vector<double> zx(nz), zy(nz);
-    std::vector<int32_t> zc(nz);
-    std::vector<uint8_t> zk(nz), zl(nz);
-    for (int64_t t = 0; t < nz; ++t) { zx[t] = cx[zero[t]]; zy[t] = cy[zero[t]]; }
-    rc = vpc_dbscan_l1_2d(ctx, zx.data(), zy.data(), nz, eps, min_pts, cf, zc.data(), zk.data(), zl.data(), &amount);   // :1516
-    if (rc) return rc;
-    for (int64_t t = 0; t < nz; ++t) cid[zero[t]] = zc[t];
-  }
-  for (int64_t i = 0; i < n; ++i) cluster_id[i] = 0;
-  for (int64_t k = 0; k < nt; ++k) cluster_id[order[k]] = cid[k];
-  *cluster_sum = amount;                                                                    // :1538
-  if (del_sum) *del_sum = dels;
-  return VPC_OK;
-}
-
 }  // extern "C"
 
+#include "blocked_api.cuh"
 #include "group_api.cuh"
