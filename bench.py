@@ -32,6 +32,7 @@ sys.path.insert(0, str(ROOT))
 EPS, MIN_PTS = 0.07, 7
 DB_GRID, DB_N = 140, 1_000_000            # config C2
 ICP_M, ICP_N, ICP_ITERS = 1_000_000, 100_000, 50   # config C3
+C4_N, C4_GRID = 100_000_000, 1400                  # config C4
 DB_ALGO_BYTES_PER_PT = 21                  # 16 B read + 4 B cluster_id + 1 B is_key
 WORKLOAD_C2 = "C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7"
 
@@ -536,6 +537,56 @@ def run_ours(args):
         icp["value"] = icp["target_sharded_weak"]["value"]
         icp["workload"] = icp["target_sharded_weak"]["workload"]
         parity["icp_how"] = "correspondences of the last round index-exact and R, T, SSE within 1e-6 relative vs vpc_icp_rigid_dev on one GPU with the whole target"
+    # ---- config C4: 100M points, ONE cloud cut into `world` slabs (strong scaling), generated on the device
+    c4 = None
+    if world > 1 and not args.no_c4:
+        from vtkcloudpoint_b200.peer import GraphedStep, calibrated_slab_plan
+        n4, grid4 = C4_N, C4_GRID
+        fx4, fy4 = ctx.synth_dbscan_cloud_dev(0xC4, grid4, n4)
+        u4 = fx4 + fy4
+        qs4 = torch.quantile(u4[::101].contiguous(), torch.tensor([j / world for j in range(1, world)], dtype=torch.float64, device=dev))
+        band4 = torch.bucketize(u4, qs4, right=True)
+        counts4 = torch.bincount(band4, minlength=world).cpu().numpy()
+        bound4 = float(u4.abs().max().item() + (fx4 - fy4).abs().max().item())
+        del u4
+        sx4, sy4 = fx4[band4 == rank].contiguous(), fy4[band4 == rank].contiguous()
+        g0 = int(counts4[:rank].sum())
+        comm4, plan4 = calibrated_slab_plan(ctx, sx4, sy4, counts4.tolist(), qs4.cpu().tolist(), EPS, MIN_PTS, bound4, dev)
+        g4 = None if args.no_graph else GraphedStep(lambda: plan4.step(0), dev)
+        fn4 = g4.replay if g4 is not None else (lambda: plan4.step(0))
+        for _ in range(2):
+            fn4()
+        barrier()
+        reps = 5
+        ev4 = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn4(); e1.record()
+            ev4.append((e0, e1))
+        barrier()
+        ms4 = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev4)) / reps
+        st4 = plan4.status.cpu().numpy()
+        # parity: the whole slab-ordered cloud on ONE GPU (each rank does it on its own), slab compared element by element
+        wx4 = torch.cat([fx4[band4 == r] for r in range(world)]); wy4 = torch.cat([fy4[band4 == r] for r in range(world)])
+        del fx4, fy4, band4
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scid, skey, scls, samount = ctx2.dbscan_dev(wx4, wy4, EPS, MIN_PTS, 0)
+        torch.cuda.synchronize()
+        e0.record(); scid, skey, scls, samount = ctx2.dbscan_dev(wx4, wy4, EPS, MIN_PTS, 0); e1.record(); torch.cuda.synchronize()
+        ms4_single = e0.elapsed_time(e1)
+        sl4 = slice(g0, g0 + int(counts4[rank]))
+        ok = (int(st4[1]) == 0 and int(samount.item()) == int(st4[0]) and bool((scid[sl4] == plan4.cluster_id).all()) and bool((skey[sl4] == plan4.is_key).all())
+              and bool((scls[sl4] == plan4.is_classed).all()))
+        parity["c4_100m"] = all_ok(ok)
+        c4 = {"metric": METRIC, "value": n4 / (ms4 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms4, "points": n4, "clusters": int(st4[0]),
+              "single_gpu_ms_per_step": ms4_single, "speedup_vs_one_gpu": ms4_single / ms4,
+              "roofline_frac": DB_ALGO_BYTES_PER_PT * n4 / (ms4 * 1e-3) / 1e9 / (peak_gbs * world),
+              "workload": f"C4: blocked DBSCAN on 100M points (1400 x 1400 clusters x 40 + 21.6M noise, generated on the device), {world} u-slabs with 2*eps halo "
+                          "exchange + cross-GPU union-find merge over NVLink peer memory; strong scaling; bit-equal to one GPU on the whole cloud"}
+        del g4, fn4, wx4, wy4, scid, skey, scls, sx4, sy4
+        plan4.close(); comm4.close()
+        torch.cuda.empty_cache()
     if world > 1 and not all(v for k, v in parity.items() if not k.endswith("_how")):     # identical on every rank (all_ok)
         if rank == 0:
             print(json.dumps({"error": "multi-GPU result differs from the single-GPU result", "parity": parity}), flush=True)
@@ -611,6 +662,7 @@ def run_ours(args):
         if world > 1:
             line["parity"] = parity
             line["nvlink"] = nvlink
+            line["secondary_c4"] = c4
         print(json.dumps(line), flush=True)
     # teardown: release the captured graph (it holds NCCL work) before the communicator goes away, and never let a stuck
     # teardown keep the job alive after the result line is out
@@ -641,6 +693,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-literal", action="store_true", help="reference arm: skip the Theta(n^2) literal timings")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: issue the slab step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 100M-point strong-scaling leg (config C4)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: the NCCL-based slab path of round 1 instead of the peer-memory path")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -356,6 +356,12 @@ int vpc_ingest_text(vpc_ctx* ctx, const char* text, int64_t len, double x_angle,
                     int32_t remove_duplicates, int64_t row_cap, double* mx, double* my, double* dist, double* xyz,
                     uint8_t* keep, uint8_t* row_status, int64_t* n_rows, int64_t* n_kept, int64_t* n_duplicates);
 
+/* Bench / test utility (no counterpart in the reference): the synthetic clustered cloud of the benchmark configs (the
+ * recipe and its defaults are vtkcloudpoint_b200/synth.py:dbscan_cloud, reproduced bit for bit) generated on the device -- config C4's
+ * 100M points are "generated on-device per slab".  Writes output positions [start, start + count) of the shuffled cloud. */
+int vpc_synth_dbscan_cloud_dev(vpc_ctx* ctx, uint64_t seed, int32_t grid, int32_t pts_per_cluster, int64_t n_total, double pitch, double sigma,
+                               double x0, double y0, int64_t start, int64_t count, double* d_mx, double* d_my, void* stream);
+
 /* ---- ICP across GPUs: the model is sharded (one shard per GPU, vpc_icp_set_model_dev on each), the
  * data is replicated.  One round of ICP.go_hell_ICP (ICP.cs:23-180) becomes
  *   vpc_icp_shard_nn_dev          local nearest model point: d2[i], idx[i] = local index + idx_offset

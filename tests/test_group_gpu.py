@@ -111,3 +111,26 @@ def test_pageable_and_page_locked_host_arrays_agree(ctx, oracle):
         if n <= 131_073:
             cid, key, cls, amount = oracle.dbscan(mx, my, 0.07, 7, 0)
             np.testing.assert_array_equal(a.cluster_id, cid)
+
+
+def test_group_blocked_cells_over_devices(gctx, oracle):
+    """The StartCode work items (one per cell, FrmMain.cs:1356-1359) spread over the group's devices: same result as the oracle."""
+    mx, my = synth.dbscan_cloud(0xC1, 14, n_total=10_000, decimals=3)
+    for ppc in (200, 650):
+        exp = oracle.blocked(mx, my, 0.07, 7, ppc)
+        before = gctx.launch_count
+        got = gctx.dbscan_blocked_ref(mx, my, 0.07, 7, ppc)
+        assert gctx.launch_count - before > 20
+        for k in ("rows", "cols", "n_unassigned", "cluster_sum", "del_sum"):
+            assert got[k] == exp[k], k
+        np.testing.assert_array_equal(got["cluster_id"], exp["cluster_id"])
+        np.testing.assert_array_equal(got["merge_cid"], exp["merge_cid"])
+
+
+def test_device_generator_matches_numpy_recipe(ctx):
+    """vpc_synth_dbscan_cloud_dev (config C4 is generated on the device) reproduces synth.dbscan_cloud bit for bit."""
+    for seed, grid, n, start, count in ((0xC2, 44, 100_000, 0, 100_000), (0xC4, 1400, 100_000_000, 73_000_123, 50_000), (0xC1, 14, 10_000, 17, 1000)):
+        mx, my = synth.dbscan_cloud(seed, grid, n_total=n, start=start, count=count)
+        dx, dy = ctx.synth_dbscan_cloud_dev(seed, grid, n, start, count)
+        np.testing.assert_array_equal(dx.cpu().numpy().view(np.int64), mx.view(np.int64))
+        np.testing.assert_array_equal(dy.cpu().numpy().view(np.int64), my.view(np.int64))

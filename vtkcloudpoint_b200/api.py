@@ -326,6 +326,17 @@ class Context:
         return {"cluster_id": new_cid, "cluster_amount": a, "dict": list(zip(dfrom[:nd.value].tolist(), dto[:nd.value].tolist())),
                 "centers5": c5[:5 * m].reshape(5, m).copy(), "center_ids": cids[:m].copy(), "new_centers5": nc5[:5 * a].reshape(5, a).copy()}
 
+    def synth_dbscan_cloud_dev(self, seed: int, grid: int, n_total: int, start: int = 0, count: int | None = None, pts_per_cluster: int = 40, pitch: float = 0.5,
+                               sigma: float = 0.012, x0: float = 149.0, y0: float = 307.0, device=None):
+        """synth.dbscan_cloud generated on the device (bit for bit the same doubles).  Returns (mx, my) float64 CUDA tensors."""
+        import torch
+        count = n_total - start if count is None else count
+        dev = torch.device("cuda", self.device) if device is None else device
+        mx = torch.empty(count, dtype=torch.float64, device=dev); my = torch.empty(count, dtype=torch.float64, device=dev)
+        self._check(self._lib.vpc_synth_dbscan_cloud_dev(self._h, int(seed), int(grid), int(pts_per_cluster), int(n_total), float(pitch), float(sigma), float(x0), float(y0),
+                                                         int(start), int(count), mx.data_ptr(), my.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        return mx, my
+
     def argsort_f64(self, vals) -> np.ndarray:
         """Stable ascending permutation of a host array of doubles on the device (vpc_argsort_f64_dev): the sort of
         MainForm.getClusterFromMotor (FrmMain.cs:1229-1233)."""

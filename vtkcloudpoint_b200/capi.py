@@ -72,6 +72,7 @@ SIGNATURES = {
     "vpc_polar_to_xyz_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _f64, _i32, _i32, _p, _p, _p]),
     "vpc_dedupe_xyz_dev": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p]),
     "vpc_ingest_text": (C.c_int, [_p, _p, _i64, _f64, _f64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vpc_synth_dbscan_cloud_dev": (C.c_int, [_p, C.c_uint64, _i32, _i32, _i64, _f64, _f64, _f64, _f64, _i64, _i64, _p, _p, _p]),
     "vpc_icp_shard_begin_dev": (C.c_int, [_p, _i64, _p]),
     "vpc_icp_shard_nn_dev": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
     "vpc_icp_shard_select_dev": (C.c_int, [_p, _i64, _p, _p, _p, _p]),

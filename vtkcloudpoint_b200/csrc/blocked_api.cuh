@@ -97,7 +97,7 @@ int vpc_dbscan_blocked_ref_ex(vpc_ctx* ctx, const double* mx, const double* my, 
   const double cell_x = ord_decode(hb.c0x) - x_min, cell_y = ord_decode(hb.c0y) - y_min;          // FrmMain.cs:1255-1256
   if (!(cell_x > 0 && cell_y > 0)) return fail(ctx, VPC_E_BADARG, "degenerate first cell: the C# divides by zero here (FrmMain.cs:1257-1258)");
   const double fr = (y_max - y_min) / cell_y, fc = (x_max - x_min) / cell_x;
-  if (!(fr < 2e9 && fc < 2e9) || (fr + 1) * (fc + 1) > 2e9) return fail(ctx, VPC_E_TOOBIG, "too many cells");
+  if (!(fr < 2e9 && fc < 2e9) || (fr + 1) * (fc + 1) > 6.4e7) return fail(ctx, VPC_E_TOOBIG, "too many cells (more than 64M)");
   const int rows = (int)fr + 1, cols = (int)fc + 1;                                                // :1257-1258
   if (rows_out) *rows_out = rows;
   if (cols_out) *cols_out = cols;
@@ -131,9 +131,14 @@ int vpc_dbscan_blocked_ref_ex(vpc_ctx* ctx, const double* mx, const double* my, 
   VPC_LAUNCH(ctx, k_blk_gather, gt, kBlkBlock, s, d_entry, d_srt, d_x, d_y, nt, d_cx, d_cy, d_slot_orig);
   // ---- DoWork3 / StartCode: one DBImproved per cell, every cell in ONE batched launch
   VPC_CUDA(ctx, cudaMemsetAsync(d_per_cell, 0, 4ull * n_cells, s));
-  ctx->db_ws_n = -1;
-  rc = dbscan_enqueue(ctx, d_cx, d_cy, nt, eps, min_pts, 0, d_lid, d_k8, d_c8, nullptr, s, d_off, (int32_t)n_cells, d_per_cell);
-  ctx->db_ws_n = -1;
+  if (ctx->group && (int64_t)nt >= group_min_points(ctx)) {
+    // a multi-GPU context: contiguous ranges of cells go to the devices (the reference's thread pool over cells, FrmMain.cs:1356-1359)
+    rc = group_cells(ctx, d_cx, d_cy, nt, d_off, (int)n_cells, eps, min_pts, d_lid, d_per_cell, s);
+  } else {
+    ctx->db_ws_n = -1;
+    rc = dbscan_enqueue(ctx, d_cx, d_cy, nt, eps, min_pts, 0, d_lid, d_k8, d_c8, nullptr, s, d_off, (int32_t)n_cells, d_per_cell);
+    ctx->db_ws_n = -1;
+  }
   if (rc) return rc;
   VPC_LAUNCH(ctx, k_blk_amounts, std::min(blocks_for(n_cells, kBlkBlock), ctx->sm_count * 4), kBlkBlock, s, d_per_cell, (int)n_cells, d_b);
   VPC_CUDA(ctx, cudaMemcpyAsync(&hb, d_b, sizeof hb, cudaMemcpyDeviceToHost, s));

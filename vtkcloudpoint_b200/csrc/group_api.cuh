@@ -349,6 +349,71 @@ int group_icp(vpc_ctx* top, const double* model_xyz, int64_t m, const double* da
 }
 
 
+// ---- the StartCode work items of the blocked clustering over the devices of the group (second row) ----------------------
+// The reference's only parallelism is one thread-pool work item per cell (FrmMain.cs:1356-1359, 2782-2794); cells never interact (no
+// halo), so contiguous ranges of cells, balanced by point count, go to the devices with no exchange at all: coordinates out, cell-local
+// ids and per-cell cluster counts back.  d_cx / d_cy / d_off / d_lid / d_per_cell live on the top context's device, whose stream `s`
+// has produced the inputs and will consume the outputs.
+int group_cells(vpc_ctx* top, const double* d_cx, const double* d_cy, int nt, const int* d_off, int n_cells, double eps, int min_pts, int* d_lid, int* d_per_cell,
+                cudaStream_t s) {
+  vpc_group* G = top->group;
+  const int W = G->world;
+  int rc = group_ensure_comms(top, kHeapHeaderBytes + 4096);          // peer access between the devices
+  if (rc) return rc;
+  std::vector<int> off((size_t)n_cells + 1);
+  VPC_CUDA(top, cudaMemcpyAsync(off.data(), d_off, 4ull * (n_cells + 1), cudaMemcpyDeviceToHost, s));
+  cudaEvent_t ready = nullptr;
+  VPC_CUDA(top, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  VPC_CUDA(top, cudaEventRecord(ready, s));
+  VPC_CUDA(top, cudaStreamSynchronize(s));
+  std::vector<int> cut(W + 1, n_cells);
+  cut[0] = 0;
+  for (int r = 1; r < W; ++r) {                                       // first cell whose start reaches r / W of the slots
+    const long long want = (long long)nt * r / W;
+    cut[r] = (int)(std::lower_bound(off.begin(), off.end(), (int)want) - off.begin());
+    cut[r] = std::min(std::max(cut[r], cut[r - 1]), n_cells);
+  }
+  std::vector<cudaEvent_t> done(W, nullptr);
+  for (int r = 0; r < W; ++r) {
+    const int c0 = cut[r], c1 = cut[r + 1], a = off[c0], cnt = off[c1] - a, nc = c1 - c0;
+    if (nc <= 0 || cnt <= 0) {
+      if (nc > 0) { DeviceGuard g0(top->device); VPC_CUDA(top, cudaMemsetAsync(d_per_cell + c0, 0, 4ull * nc, s)); }
+      continue;
+    }
+    vpc_ctx* sc = G->sub[r];
+    DeviceGuard g(sc->device);
+    cudaStream_t sr = G->stream[r];
+    VPC_SUB(top, sc, arena_reserve(sc, G->loc[r], al256(8ull * cnt) * 2 + al256(4ull * cnt) + al256((size_t)cnt) * 2 + al256(4ull * (nc + 1)) * 2 + 4096));
+    Arena& w = G->loc[r];
+    double* x = w.take<double>(cnt); double* y = w.take<double>(cnt); int* lid = w.take<int>(cnt);
+    unsigned char* k8 = w.take<unsigned char>(cnt); unsigned char* c8 = w.take<unsigned char>(cnt);
+    int* loff = w.take<int>(nc + 1); int* per = w.take<int>(nc + 1);
+    std::vector<int> rel((size_t)nc + 1);
+    for (int c = 0; c <= nc; ++c) rel[c] = off[c0 + c] - a;
+    VPC_CUDA(top, cudaStreamWaitEvent(sr, ready, 0));
+    VPC_CUDA(top, cudaMemcpyPeerAsync(x, sc->device, d_cx + a, top->device, 8ull * cnt, sr));
+    VPC_CUDA(top, cudaMemcpyPeerAsync(y, sc->device, d_cy + a, top->device, 8ull * cnt, sr));
+    VPC_CUDA(top, cudaMemcpyAsync(loff, rel.data(), 4ull * (nc + 1), cudaMemcpyHostToDevice, sr));
+    VPC_CUDA(top, cudaStreamSynchronize(sr));                         // `rel` is a stack-lifetime host buffer
+    sc->db_ws_n = -1;
+    rc = dbscan_enqueue(sc, x, y, cnt, eps, min_pts, 0, lid, k8, c8, nullptr, sr, loff, nc, per);
+    sc->db_ws_n = -1;
+    if (rc) { top->err = sc->err; return rc; }
+    VPC_CUDA(top, cudaMemcpyPeerAsync(d_lid + a, top->device, lid, sc->device, 4ull * cnt, sr));
+    VPC_CUDA(top, cudaMemcpyPeerAsync(d_per_cell + c0, top->device, per, sc->device, 4ull * nc, sr));
+    VPC_CUDA(top, cudaEventCreateWithFlags(&done[r], cudaEventDisableTiming));
+    VPC_CUDA(top, cudaEventRecord(done[r], sr));
+  }
+  {
+    DeviceGuard g0(top->device);
+    for (int r = 0; r < W; ++r) if (done[r]) VPC_CUDA(top, cudaStreamWaitEvent(s, done[r], 0));
+    VPC_CUDA(top, cudaStreamSynchronize(s));
+  }
+  for (int r = 0; r < W; ++r) if (done[r]) { DeviceGuard g(G->sub[r]->device); cudaEventDestroy(done[r]); }
+  cudaEventDestroy(ready);
+  return VPC_OK;
+}
+
 int group_create(vpc_ctx* top, const int* device_ids, int n_devices) {
   vpc_group* G = new (std::nothrow) vpc_group();
   if (!G) return VPC_E_NOMEM;

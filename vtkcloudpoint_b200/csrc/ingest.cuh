@@ -221,4 +221,44 @@ k_in_parse_rows(const unsigned char* __restrict__ text, long long len, const lon
   status[r - 1] = (unsigned char)st;
 }
 
+// ---- the synthetic clustered cloud of the benchmark configs, generated on the device ("C4 ... generated on-device per
+// slab") -- bit for bit the recipe of vtkcloudpoint_b200/synth.py:dbscan_cloud (counter-based splitmix64, IEEE adds / muls only):
+// grid x grid cluster centres at `pitch`, pts_per_cluster points each ~ centre + sigma * (Irwin-Hall of four uniforms), uniform noise
+// up to n_total points, shuffled by an affine permutation of the index.  Writes output positions [start, start + count).
+__device__ __forceinline__ unsigned long long syn_splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double syn_uniform(unsigned long long base, unsigned long long idx) {
+  return (double)(syn_splitmix64(idx + base) >> 11) * (1.0 / 9007199254740992.0);
+}
+struct SynBases { unsigned long long n1[4], n2[4], u20, u21; };   // stream bases: approx_normal streams 1 and 2 (4 uniforms each), uniforms 20 and 21
+__global__ void __launch_bounds__(256)
+k_syn_dbscan_cloud(SynBases b, int grid, int pts_per_cluster, unsigned long long n_total, unsigned long long perm_a, unsigned long long perm_b, double pitch,
+                   double sigma, double x0, double y0, long long start, long long count, double* __restrict__ mx, double* __restrict__ my) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const unsigned long long i = (unsigned long long)(start + t);
+  const unsigned long long j = (i * perm_a + perm_b) % n_total;
+  const unsigned long long n_clustered = (unsigned long long)grid * grid * pts_per_cluster;
+  double x, y;
+  if (j < n_clustered) {
+    const long long c = (long long)(j / (unsigned long long)pts_per_cluster);
+    const double cx = (double)(c % grid), cy = (double)(c / grid);
+    double sx = syn_uniform(b.n1[0], j); sx = sx + syn_uniform(b.n1[1], j); sx = sx + syn_uniform(b.n1[2], j); sx = sx + syn_uniform(b.n1[3], j);
+    double sy = syn_uniform(b.n2[0], j); sy = sy + syn_uniform(b.n2[1], j); sy = sy + syn_uniform(b.n2[2], j); sy = sy + syn_uniform(b.n2[3], j);
+    const double gx = (sx - 2.0) * 1.7320508075688772, gy = (sy - 2.0) * 1.7320508075688772;
+    x = (x0 + cx * pitch) + gx * sigma;
+    y = (y0 + cy * pitch) + gy * sigma;
+  } else {
+    const double span = (double)(grid - 1) * pitch + 1.0;
+    x = (x0 - 0.5) + syn_uniform(b.u20, j) * span;
+    y = (y0 - 0.5) + syn_uniform(b.u21, j) * span;
+  }
+  mx[t] = x; my[t] = y;
+}
+
 }  // namespace vpc

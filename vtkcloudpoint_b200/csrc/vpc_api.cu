@@ -268,6 +268,8 @@ int group_create(vpc_ctx* top, const int* device_ids, int n_devices);
 void group_destroy(vpc_ctx* top);
 int64_t group_launches(const vpc_ctx* top);
 int64_t group_min_points(const vpc_ctx* top);
+int group_cells(vpc_ctx* top, const double* d_cx, const double* d_cy, int nt, const int* d_off, int n_cells, double eps, int min_pts, int* d_lid, int* d_per_cell,
+                cudaStream_t s);
 }  // namespace
 
 extern "C" {
@@ -1152,6 +1154,30 @@ int vpc_ingest_text(vpc_ctx* ctx, const char* text, int64_t len, double x_angle,
   VPC_CUDA(ctx, cudaStreamSynchronize(s));
   if (n_duplicates) *n_duplicates = ndup;
   if (n_kept) { long long k = 0; for (long long i = 0; i < rows; ++i) k += keep[i]; *n_kept = k; }
+  return VPC_OK;
+}
+
+// bench / test utility: the synthetic clustered cloud of synth.py:dbscan_cloud, generated on the device (see include/vpc.h)
+int vpc_synth_dbscan_cloud_dev(vpc_ctx* ctx, uint64_t seed, int32_t grid, int32_t pts_per_cluster, int64_t n_total, double pitch, double sigma, double x0, double y0,
+                               int64_t start, int64_t count, double* d_mx, double* d_my, void* stream) {
+  if (!ctx) return VPC_E_BADARG;
+  if (grid <= 0 || pts_per_cluster <= 0 || n_total <= 0 || start < 0 || count < 0 || start + count > n_total || (count > 0 && (!d_mx || !d_my)) ||
+      (long long)grid * grid * pts_per_cluster > n_total) return fail(ctx, VPC_E_BADARG, "bad generator arguments");
+  if (count == 0) return VPC_OK;
+  auto splitmix = [](unsigned long long x) { x += 0x9E3779B97F4A7C15ull; unsigned long long z = x; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+  auto base = [&](unsigned long long stream_id) { return splitmix(seed ^ (stream_id * 0xD1342543DE82EF95ull)); };
+  SynBases b{};
+  for (int k = 0; k < 4; ++k) { b.n1[k] = base(4ull * 1 + k); b.n2[k] = base(4ull * 2 + k); }
+  b.u20 = base(20); b.u21 = base(21);
+  auto gcd = [](unsigned long long a, unsigned long long c) { while (c) { const unsigned long long t = a % c; a = c; c = t; } return a; };
+  unsigned long long pa = n_total > 1 ? 2654435761ull % (unsigned long long)n_total : 1ull;
+  if (pa == 0) pa = 1;
+  while (gcd(pa, (unsigned long long)n_total) != 1) ++pa;
+  const unsigned long long pb = 12345ull % (unsigned long long)n_total;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard g(ctx->device);
+  VPC_LAUNCH(ctx, k_syn_dbscan_cloud, blocks_for(count, 256), 256, static_cast<cudaStream_t>(stream), b, grid, pts_per_cluster, (unsigned long long)n_total, pa, pb, pitch,
+             sigma, x0, y0, (long long)start, (long long)count, d_mx, d_my);
   return VPC_OK;
 }
 
