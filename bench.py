@@ -33,6 +33,7 @@ EPS, MIN_PTS = 0.07, 7
 DB_GRID, DB_N = 140, 1_000_000            # config C2
 ICP_M, ICP_N, ICP_ITERS = 1_000_000, 100_000, 50   # config C3
 C4_N, C4_GRID = 100_000_000, 1400                  # config C4
+C5_N = 10_000_000                                  # config C5
 DB_ALGO_BYTES_PER_PT = 21                  # 16 B read + 4 B cluster_id + 1 B is_key
 WORKLOAD_C2 = "C2: DBSCAN on a 1M-point synthetic clustered cloud with noise (140x140 clusters x 40 pts + 216k noise), eps 0.07, minPts 7"
 
@@ -201,8 +202,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # CPU-side barrier: ranks that only wait must not park an NCCL kernel on their GPU
 
     def barrier():
         if world > 1:
@@ -403,6 +406,9 @@ def run_ours(args):
     # idle at the barrier) with the whole cloud in the recipe's shuffled order: chunk H2D on every PCIe link, NVLink re-deal into
     # slabs, slab step, results pulled home, D2H -- all inside the one call (csrc/group_api.cuh).
     e2e_pageable = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)                   # every GPU is idle from here: rank 0's one-process context drives them all
     if rank == 0:
         if world == 1:
             gx, gy, gctx = mx.copy(), my.copy(), ctx
@@ -420,6 +426,8 @@ def run_ours(args):
                         "cluster_amount": int(gres.cluster_amount)}
         if world > 1:
             gctx.close()
+    if world > 1:
+        dist.barrier(group=host_group)
     barrier()
     clocks = sampler.stop()
 
@@ -587,6 +595,53 @@ def run_ours(args):
         del g4, fn4, wx4, wy4, scid, skey, scls, sx4, sy4
         plan4.close(); comm4.close()
         torch.cuda.empty_cache()
+    # ---- config C5: the full pipeline (DBSCAN -> bounding-circle radius filter -> centroids -> ICP to the checkerboard truth -> match)
+    # on 10M points across the GPUs (BASELINE.json config 5 names 8 GPUs; --c5 runs it at any N > 1)
+    c5 = None
+    if world > 1 and (world == 8 or args.c5) and not args.no_c5:
+        from vtkcloudpoint_b200.pipeline import GpuPipelineBackend, run_pipeline
+        n5 = C5_N
+        grid5 = int(round((n5 * 0.784 / 40) ** 0.5))
+        a5, b5 = n5 * rank // world, n5 * (rank + 1) // world
+        px, py = ctx.synth_dbscan_cloud_dev(0xC5, grid5, n5, a5, b5 - a5)
+        # every 17th cluster is stretched along x so that its bounding circle exceeds the 0.088 threshold (MCC.Designer.cs:71)
+        cxi, cyi = torch.round((px - 149.0) / 0.5), torch.round((py - 307.0) / 0.5)
+        near = ((px - (149.0 + 0.5 * cxi)).abs() < 0.06) & ((py - (307.0 + 0.5 * cyi)).abs() < 0.06)
+        fat = near & (((cxi + grid5 * cyi).to(torch.int64) % 17) == 0)
+        px = torch.where(fat, 149.0 + 0.5 * cxi + (px - (149.0 + 0.5 * cxi)) * 2.6, px).contiguous()
+        idx = torch.arange(a5, b5, device=dev, dtype=torch.float64)
+        pd = 41.91 + 0.004 * (torch.frac(idx * 0.6180339887498949) - 0.5)
+        pxyz, _ = ctx.polar_to_xyz_dev(px, py, pd.contiguous(), 149.0, 307.0)
+        gx5, gy5 = torch.meshgrid(torch.arange(grid5, device=dev, dtype=torch.float64), torch.arange(grid5, device=dev, dtype=torch.float64), indexing="ij")
+        cxyz, _ = ctx.polar_to_xyz_dev((149.0 + 0.5 * gx5.reshape(-1)).contiguous(), (307.0 + 0.5 * gy5.reshape(-1)).contiguous(),
+                                       torch.full((grid5 * grid5,), 41.91, dtype=torch.float64, device=dev), 149.0, 307.0)
+        th5 = np.deg2rad(0.4)
+        gen5 = torch.Generator(device="cpu").manual_seed(5)
+        cen5 = cxyz[:2].cpu()
+        R5 = torch.tensor([[np.cos(th5), -np.sin(th5)], [np.sin(th5), np.cos(th5)]], dtype=torch.float64)
+        truth5 = R5 @ cen5 + torch.tensor([[0.011], [-0.007]], dtype=torch.float64) + 2e-3 * torch.randn(cen5.shape, generator=gen5, dtype=torch.float64)
+        truth5 = truth5[:, torch.randperm(truth5.shape[1], generator=gen5)].contiguous().to(dev)
+        be5 = GpuPipelineBackend(ctx)
+        kw5 = dict(eps=EPS, min_pts=MIN_PTS, radius_threshold=0.088, icp_e=1e-9, icp_max_iters=10, match_distance=0.05)
+        res5 = run_pipeline(be5, px, py, pxyz, a5, truth5, **kw5)         # warm-up (workspaces, NCCL channels)
+        times5 = []
+        for _ in range(3):
+            barrier(); t0 = time.perf_counter()
+            res5 = run_pipeline(be5, px, py, pxyz, a5, truth5, **kw5)
+            torch.cuda.synchronize(); times5.append(max_over_ranks(time.perf_counter() - t0))
+        st5 = res5.icp_state.cpu().numpy()
+        ok = (res5.cluster_amount >= grid5 * grid5 and abs(st5[0] - np.cos(th5)) < 1e-4 and abs(st5[3] - np.sin(th5)) < 1e-4 and abs(st5[9] - 0.011) < 5e-3
+              and abs(st5[10] + 0.007) < 5e-3 and float((res5.matched >= 0).float().mean().item()) > 0.98)
+        parity["c5_pipeline_properties"] = all_ok(ok)
+        t5 = min(times5)
+        c5 = {"metric": "pipeline_mpts_per_s", "value": n5 / t5 / 1e6, "unit": UNIT, "ms_per_pass": 1e3 * t5, "points": n5, "clusters": res5.cluster_amount,
+              "kept_centres": int(res5.kept_ids.numel()), "filtered_by_radius": int(res5.filtered.sum().item()), "icp_iters": int(st5[13]),
+              "rmse": float(np.sqrt(st5[12] / max(int(res5.kept_ids.numel()), 1))), "matched_fraction": float((res5.matched >= 0).float().mean().item()),
+              "workload": f"C5: DBSCAN -> bounding-circle radius filter (0.088) -> centroids -> ICP to the checkerboard truth -> thresholded match, {n5} points "
+                          f"in arbitrary order across {world} GPUs (vtkcloudpoint_b200/pipeline.py; exchanges over NCCL), wall clock incl. host glue, best of 3",
+              "check": "planted rigid motion (0.4 deg, (0.011, -0.007)) recovered, > 98 % of the centres matched; bit-exact vs the oracle pipeline at 1M points in "
+                       "tools/dist_check_pipeline.py and tests/test_pipeline_cpu.py"}
+        del res5, px, py, pxyz
     if world > 1 and not all(v for k, v in parity.items() if not k.endswith("_how")):     # identical on every rank (all_ok)
         if rank == 0:
             print(json.dumps({"error": "multi-GPU result differs from the single-GPU result", "parity": parity}), flush=True)
@@ -663,6 +718,7 @@ def run_ours(args):
             line["parity"] = parity
             line["nvlink"] = nvlink
             line["secondary_c4"] = c4
+            line["secondary_c5"] = c5
         print(json.dumps(line), flush=True)
     # teardown: release the captured graph (it holds NCCL work) before the communicator goes away, and never let a stuck
     # teardown keep the job alive after the result line is out
@@ -693,6 +749,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-literal", action="store_true", help="reference arm: skip the Theta(n^2) literal timings")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: issue the slab step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--c5", action="store_true", help="N > 1: run the 10M-point pipeline leg (config C5) at this N (default: only at N = 8)")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 100M-point strong-scaling leg (config C4)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: the NCCL-based slab path of round 1 instead of the peer-memory path")
     args = ap.parse_args()
