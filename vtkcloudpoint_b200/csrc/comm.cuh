@@ -3,8 +3,9 @@
 // Every rank (= one GPU) owns a "heap": one device allocation of the same size and layout on every rank.  A kernel on rank r
 // reaches rank q's heap through a peer pointer (cudaIpcOpenMemHandle across processes, cudaDeviceEnablePeerAccess inside one
 // process), so an exchange is ordinary loads / stores to mapped peer addresses over NVLink plus a flag:
-//   producer:  data stores ... __threadfence_system() ... (last block)  st.release.sys flag[q][phase][me] = epoch
-//   consumer:  spin ld.acquire.sys flag[me][phase][src] >= epoch, then read (local data, or the producer's heap by peer loads)
+//   producer:  data stores ... (last block) ONE __threadfence_system(), then st.relaxed.sys flag[q][phase][me] = epoch << 32 | count
+//   consumer:  spin ld.relaxed.sys on flag[me][phase][src] until its epoch arrives, one __threadfence_system(), then read (local data,
+//              or the producer's heap by peer loads)
 // Flags carry a monotonically increasing epoch, so they are never reset and a CUDA-graph replay needs no host work.  Every spin is
 // bounded (kSpinLimit cycles): a rank that never shows up raises the heap's error word instead of hanging the GPU.
 // Peer loads use ld.relaxed.sys (peer lines are cached in L1 only, SURVEY/B300_MICROARCH: L2 is bypassed), so a value written by
@@ -26,7 +27,7 @@ constexpr int kPhHalo = 0, kPhPairs = 1, kPhHeads = 2, kPhIcpNn = 3, kPhIcpSums 
 
 struct HeapHeader {                              // offset 0 of every heap
   unsigned long long flag[kPhases][kMaxWorld];   // flag[phase][src]: written by rank src, read by the heap's owner
-  unsigned long long word[kPhases][kMaxWorld];   // a small payload that travels with the flag (counts)
+  unsigned long long reserved[kPhases][kMaxWorld];
   int error;                                     // != 0: a bounded spin gave up (bit 0) / an exchange buffer overflowed (bit 1)
   int pad[15];
   unsigned long long epoch[8];                   // step counters of the heap's OWNER ([0] slab DBSCAN, [1] ICP): they live with the flags, so
@@ -74,26 +75,31 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   return v;
 }
 
-// Tell rank `dst` that this rank finished `phase` of step `epoch`; `payload` rides along (written first).
+// A flag word = (epoch << 32) | payload: ONE relaxed system-scope store per destination publishes both, so a count travels with the
+// flag without a second ordered store.  The CALLER orders its data before the flags with ONE __threadfence_system() (fence + relaxed
+// store = a release pattern); a st.release.sys per destination would repeat that fence `world` times -- on 4 x B200 that alone was
+// ~60 us per ICP round (profiles/r02_multi_gpu.md).
 __device__ __forceinline__ void comm_signal(const Peers& P, int dst, int phase, unsigned long long epoch, unsigned long long payload) {
-  HeapHeader* h = P.hdr(dst);
-  st_relaxed_sys_u64(&h->word[phase][P.rank], payload);
-  st_release_sys_u64(&h->flag[phase][P.rank], epoch);
+  st_relaxed_sys_u64(&P.hdr(dst)->flag[phase][P.rank], (epoch << 32) | (payload & 0xffffffffull));
 }
-// Wait until rank `src` has signalled `phase` of step `epoch` (bounded).  Returns false on timeout (and raises the error word).
+// Wait until rank `src` has signalled `phase` of step `epoch` (bounded): relaxed polling, one acquiring fence at the end.
+// Returns false on timeout (and raises the error word).
 __device__ __forceinline__ bool comm_wait(const Peers& P, int src, int phase, unsigned long long epoch) {
   HeapHeader* h = P.hdr(P.rank);
   const unsigned long long* f = &h->flag[phase][src];
-  if (ld_acquire_sys_u64(f) >= epoch) return true;
-  const long long t0 = clock64();
-  while (ld_acquire_sys_u64(f) < epoch) {
-    if (clock64() - t0 > kSpinLimit) { atomicOr(&h->error, 1); return false; }
-    __nanosleep(64);
+  bool ok = true;
+  if ((ld_relaxed_sys_u64(f) >> 32) < epoch) {
+    const long long t0 = clock64();
+    while ((ld_relaxed_sys_u64(f) >> 32) < epoch) {
+      if (clock64() - t0 > kSpinLimit) { atomicOr(&h->error, 1); ok = false; break; }
+      __nanosleep(32);
+    }
   }
-  return true;
+  __threadfence_system();
+  return ok;
 }
 __device__ __forceinline__ unsigned long long comm_payload(const Peers& P, int src, int phase) {
-  return ld_relaxed_sys_u64(&P.hdr(P.rank)->word[phase][src]);
+  return ld_relaxed_sys_u64(&P.hdr(P.rank)->flag[phase][src]) & 0xffffffffull;
 }
 
 // One thread per source rank waits, then the block is released.  Call from ALL threads of a block.

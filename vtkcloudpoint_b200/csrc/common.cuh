@@ -91,9 +91,8 @@ constexpr unsigned long long kTilePrefix = 2ull << 32;
 
 // kPopc: the scanned value of item i is popc(in[i]) instead of in[i] (ranks inside a bitmap).
 template <bool kPopc>
-__global__ void __launch_bounds__(kScanBlock)
-k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr,
-                 int n_static, unsigned long long* tile_state, int* tile_counter, int* total_out) {
+__device__ __forceinline__ void scan_exclusive_body(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr,
+                                                    int n_static, unsigned long long* tile_state, int* tile_counter, int* total_out) {
   __shared__ int s_tile;
   __shared__ int s_warp[kScanBlock / kWarp];
   __shared__ int s_excl;
@@ -193,6 +192,13 @@ k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* _
       run += v[k];
     }
   }
+}
+
+template <bool kPopc>
+__global__ void __launch_bounds__(kScanBlock)
+k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr,
+                 int n_static, unsigned long long* tile_state, int* tile_counter, int* total_out) {
+  scan_exclusive_body<kPopc>(in, out, n_ptr, n_static, tile_state, tile_counter, total_out);
 }
 
 inline int scan_tiles(long long n) { return (int)((n + kScanTile - 1) / kScanTile); }

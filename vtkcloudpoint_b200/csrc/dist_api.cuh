@@ -95,10 +95,11 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
       break;
     }
     case 3:
-      VPC_LAUNCH(ctx, k_slb_heads_rank, 1, kHeadsRankBlock, s, a);
+      VPC_LAUNCH(ctx, k_slb_heads_scan, scan_tiles(a.nwords), kScanBlock, s, a);
+      VPC_LAUNCH(ctx, k_slb_heads_publish, 1, 32, s, a);
       break;
     case 4:
-      VPC_LAUNCH(ctx, k_slb_ids, g_own, kDbBlock, s, a);
+      VPC_LAUNCH(ctx, k_slb_ids, g_stride, kDbBlock, s, a);
       break;
   }
   return VPC_OK;
@@ -266,7 +267,7 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   long long slots = 1024;
   while (slots < 2ll * W * cap_pairs) slots <<= 1;
   p->table_slots = slots; p->table_bytes = 16ull * slots;
-  const size_t bytes = al256(8 * nl) * 2 + al256(4 * nl) * 2 + al256(nl) + al256(4 * no) + al256(no) * 2 + al256(64) * 3 + al256(4ull * cap_pairs) + al256(8ull * cap_halo) + al256(p->table_bytes) + 4096;
+  const size_t bytes = al256(8 * nl) * 2 + al256(4 * nl) * 2 + al256(nl) + al256(4 * no) + al256(no) * 2 + al256(64) * 3 + al256(4ull * cap_pairs) + al256(8ull * cap_halo) + al256(8ull * (scan_tiles(a.nwords) + 1)) + 256 + al256(p->table_bytes) + 4096;
   void* base = nullptr;
   if (cudaMalloc(&base, bytes) != cudaSuccess) { (void)cudaGetLastError(); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_NOMEM, "cudaMalloc of the slab buffers failed"); }
   cudaMemset(base, 0, bytes);
@@ -277,6 +278,7 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   a.counters = w.take<int>(16); a.status = w.take<int>(16);
   a.epoch = &reinterpret_cast<HeapHeader*>(comm->heap)->epoch[0];
   a.pair_root = w.take<int>(cap_pairs); a.bidx = w.take<int>(2ull * cap_halo);
+  a.scan_state = w.take<unsigned long long>(scan_tiles(a.nwords) + 1); a.scan_counter = w.take<int>(4);
   p->table = w.take<char>(p->table_bytes);
   k_slb_iota<<<blocks_for(a.n_own, kDbBlock), kDbBlock, 0, ctx->own_stream>>>(a.lg, a.n_own, a.gstart[me]);
   if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) { cudaFree(base); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_CUDA, "slab plan initialisation failed"); }

@@ -139,15 +139,15 @@ __global__ void __launch_bounds__(256) k_gen_pack(const int* __restrict__ cid, c
 // home: wait until every destination has packed, then pull each point's word from where it went
 __global__ void __launch_bounds__(256) k_gen_fetch(GenArgs a) {
   comm_wait_all_block(a.P, kPhHome, *a.epoch);
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_chunk) return;
-  const int2 w = a.where[i];
-  unsigned v = 0u;
-  if (w.x >= 0) v = ld_relaxed_sys_u32(a.packed_of[w.x] + w.y);
-  const int c = (int)(v & 0x3fffffffu);
-  a.cid[i] = c > 0 ? c + a.first_cluster_id : 0;
-  a.is_key[i] = (v >> 30) & 1u;
-  a.is_classed[i] = (v >> 31) & 1u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_chunk; i += (long long)gridDim.x * blockDim.x) {   // few, fat blocks (one acquiring fence each)
+    const int2 w = a.where[i];
+    unsigned v = 0u;
+    if (w.x >= 0) v = ld_relaxed_sys_u32(a.packed_of[w.x] + w.y);
+    const int c = (int)(v & 0x3fffffffu);
+    a.cid[i] = c > 0 ? c + a.first_cluster_id : 0;
+    a.is_key[i] = (v >> 30) & 1u;
+    a.is_classed[i] = (v >> 31) & 1u;
+  }
 }
 
 __global__ void k_gen_signal_all(Peers P, const unsigned long long* epoch, int phase) {

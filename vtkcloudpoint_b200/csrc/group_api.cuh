@@ -180,7 +180,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     const size_t nl = (size_t)(n_own[d] + n_halo[d]), no = (size_t)n_own[d];
     n_local[d] = (int)nl;
     VPC_SUB(top, sc, arena_reserve(sc, G->loc[d], al256(8 * nl) * 2 + al256(4 * nl) * 2 + al256(nl) + al256(4 * no) * 2 + al256(no) * 2 + al256(64) * 2 +
-                                                    al256(4ull * cap_pairs) + al256(table_bytes) + 4096));
+                                                    al256(4ull * cap_pairs) + al256(8ull * (scan_tiles((chunk_max >> 5) + 2) + 1)) + 256 + al256(table_bytes) + 4096));
     Arena& w = G->loc[d];
     SlabArgs& a = sa[d];
     a = SlabArgs{};
@@ -194,6 +194,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     a.lx = w.take<double>(nl); a.ly = w.take<double>(nl); a.lg = w.take<int>(nl); a.gkey = w.take<int>(nl); a.is_key_l = w.take<unsigned char>(nl);
     a.cid = w.take<int>(no); packed[d] = w.take<unsigned>(no); a.is_key = w.take<unsigned char>(no); a.is_classed = w.take<unsigned char>(no);
     a.counters = w.take<int>(16); a.status = w.take<int>(16); a.pair_root = w.take<int>((size_t)cap_pairs);
+    a.scan_state = w.take<unsigned long long>(scan_tiles((chunk_max >> 5) + 2) + 1); a.scan_counter = w.take<int>(4);
     table[d] = w.take<char>(table_bytes);
     a.epoch = &reinterpret_cast<HeapHeader*>(G->comm[d]->heap)->epoch[0];
     vpc_comm* cm = G->comm[d];
@@ -248,7 +249,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
   for (int c = 0; c < W; ++c) {
     vpc_ctx* sc = G->sub[c];
     DeviceGuard g(sc->device);
-    VPC_LAUNCH(sc, k_gen_fetch, blocks_for(ga[c].n_chunk, 256), 256, G->stream[c], ga[c]);
+    VPC_LAUNCH(sc, k_gen_fetch, std::min(blocks_for(ga[c].n_chunk, 256), sc->sm_count * 8), 256, G->stream[c], ga[c]);
   }
   int status[16] = {0};
   for (int c = 0; c < W; ++c) {

@@ -11,7 +11,7 @@
 //   [remap + resolve]  dbscan.cuh: local roots take the merged key, border rule with global keys (DBImproved.cs:87)
 //   k_slb_heads        owned core points that head their cluster set their bit in the bitmap of the rank that is HOME to that
 //                      global index (peer atomicOr when remote); flag to everybody
-//   k_slb_heads_rank   wait for everybody, popc-scan of the own bitmap, publish the head count
+//   k_slb_heads_scan   wait for everybody, popc-scan of the own bitmap; k_slb_heads_publish: the head count to everybody
 //   k_slb_ids          wait for everybody; id = first + 1 + (heads on lower homes) + rank inside the home's bitmap (DBImproved.cs:93-110)
 // A kernel waits only as its FIRST action and signals as its LAST, so the ranks can also be emulated one after the other on a single
 // GPU (phase by phase, vpc_api: lockstep mode) -- that is how the single-GPU test-suite exercises this file.
@@ -43,6 +43,7 @@ struct SlabArgs {
   unsigned char* is_key_l; int* gkey;       // per local point: core flag, merged cluster key
   int* counters;                            // [0..1] halo strip counts, [2] pairs count, [3] ticket
   int* pair_root;                           // [cap_pairs] sorted position of the local root behind every pair this rank reported
+  unsigned long long* scan_state; int* scan_counter;   // look-back scan of the head bitmap (re-armed by k_slb_heads)
   int* bidx;                                // [2 * cap] pre-cut mode: local indices of the own points inside a halo strip (k_slb_halo_pack)
   unsigned long long* epoch;                // step counter (device resident: graph replays advance it)
   int* cid; unsigned char* is_key; unsigned char* is_classed;   // outputs per owned point
@@ -225,13 +226,15 @@ __device__ __forceinline__ int slb_home_of(const SlabArgs& a, int g) {   // rank
 }
 
 // ---- cluster heads: owned core points whose global index IS their cluster's key set their bit at the index's home ---------
-// also clears the bitmap of the other parity (nobody touches it during this step) and re-arms the scan of k_slb_heads_rank
+// also clears the bitmap of the other parity (nobody touches it during this step) and re-arms the scan of k_slb_heads_scan
 __global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
   unsigned* other = a.P.at<unsigned>(me, a.L.bits[(E + 1) & 1]);
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < a.nwords; w += gridDim.x * blockDim.x) other[w] = 0u;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < (a.nwords + kScanTile - 1) / kScanTile; w += gridDim.x * blockDim.x) a.scan_state[w] = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.scan_counter = 0;
   int remote = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_own; i += gridDim.x * blockDim.x) {
     if (!a.is_key_l[i]) continue;
@@ -255,37 +258,23 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
   for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhHeads, E, 0ull);
 }
 
-// ---- one block: wait for everybody's bits, popc-scan the own bitmap, publish the own head count (and error bits) ----------
-// thread t owns a contiguous span of words: popc-sum of the span, one block scan of the 1024 sums, then the running ranks
-constexpr int kHeadsRankBlock = 1024;
-__global__ void __launch_bounds__(kHeadsRankBlock) k_slb_heads_rank(SlabArgs a) {
-  __shared__ int s_warp[kHeadsRankBlock / kWarp];
+// ---- wait for everybody's bits, popc-scan the own bitmap (multi-tile look-back scan: a single block took 58 us for 31k words), then
+// publish the own head count (and error bits)
+__global__ void __launch_bounds__(kScanBlock) k_slb_heads_scan(SlabArgs a) {
+  const unsigned long long E = *a.epoch;
+  comm_wait_all_block(a.P, kPhHeads, E);
+  const int me = a.P.rank;
+  scan_exclusive_body<true>(reinterpret_cast<const int*>(a.P.at<unsigned>(me, a.L.bits[E & 1])), a.P.at<int>(me, a.L.rank), nullptr, a.nwords, a.scan_state,
+                            a.scan_counter, a.status + 4);
+}
+__global__ void __launch_bounds__(32) k_slb_heads_publish(SlabArgs a) {
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
-  comm_wait_all_block(a.P, kPhHeads, E);
-  const unsigned* bits = a.P.at<unsigned>(me, a.L.bits[E & 1]);
-  int* rank = a.P.at<int>(me, a.L.rank);
-  const int span = (a.nwords + kHeadsRankBlock - 1) / kHeadsRankBlock;
-  const int w0 = min(threadIdx.x * span, a.nwords), w1 = min(w0 + span, a.nwords);
-  int sum = 0;
-  for (int w = w0; w < w1; ++w) sum += __popc(__ldcg(bits + w));      // L2 loads: remote atomics land there, never trust L1
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  int off = 0, total = 0;
-#pragma unroll
-  for (int k = 0; k < kHeadsRankBlock / kWarp; ++k) { const int v = s_warp[k]; if (k < warp) off += v; total += v; }
-  int run = off + incl - sum;
-  for (int w = w0; w < w1; ++w) { rank[w] = run; run += __popc(__ldcg(bits + w)); }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  a.status[4] = total;
-  __threadfence_system();
+  if (threadIdx.x == 0) __threadfence_system();
+  __syncwarp();
+  const int total = a.status[4];
   const unsigned long long err = (unsigned long long)(unsigned)atomicOr(&a.P.hdr(me)->error, 0);
-  for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhGather, E, ((unsigned long long)(unsigned)total) | (err << 40));
+  if ((int)threadIdx.x < a.P.world) comm_signal(a.P, (int)threadIdx.x, kPhGather, E, ((unsigned long long)(unsigned)total & 0x0fffffffull) | ((err & 0xfull) << 28));
 }
 
 // ---- ids in the reference's numbering: clusters ranked by their minimum core index (DBImproved.cs:93-110) -----------------------
@@ -298,26 +287,31 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_ids(SlabArgs a) {
     int acc = 0, err = 0;
     for (int q = 0; q < a.P.world; ++q) {
       const unsigned long long w = comm_payload(a.P, q, kPhGather);
-      s_base[q] = acc; acc += (int)(unsigned)(w & 0xffffffffull); err |= (int)(w >> 40);
+      s_base[q] = acc; acc += (int)(unsigned)(w & 0x0fffffffull); err |= (int)((w >> 28) & 0xfull);
     }
     s_base[a.P.world] = acc; s_err = err | a.P.hdr(a.P.rank)->error;
   }
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { a.status[0] = a.first_cluster_id + s_base[a.P.world]; a.status[1] = s_err; a.status[5] = (int)E; }
-  if (i >= a.n_own) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[0] = a.first_cluster_id + s_base[a.P.world]; a.status[1] = s_err; a.status[5] = (int)E; }
+  // few, fat blocks: the wait above ends in a system-scope fence per block (3906 of them cost ~20 us at 1M points)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_own; i += gridDim.x * blockDim.x) {
   const int k = a.gkey[i];
   int id = 0;
   if (k >= 0) {
     const int home = slb_home_of(a, k);
     const int w = k - a.gstart[home];
-    const unsigned word = ld_relaxed_sys_u32(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5));
-    const int r = ld_relaxed_sys_s32(a.P.at<int>(home, a.L.rank) + (w >> 5)) + __popc(word & ((1u << (w & 31)) - 1u));
+    // the own bitmap / ranks were completed by earlier kernels of this stream (peer atomics land in L2, L1 starts clean): cached
+    // loads; a peer's are pulled past L1
+    const unsigned* bp = a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5);
+    const int* rp = a.P.at<int>(home, a.L.rank) + (w >> 5);
+    const unsigned word = (home == a.P.rank) ? __ldg(bp) : ld_relaxed_sys_u32(bp);
+    const int r = ((home == a.P.rank) ? __ldg(rp) : ld_relaxed_sys_s32(rp)) + __popc(word & ((1u << (w & 31)) - 1u));
     id = a.first_cluster_id + 1 + s_base[home] + r;
   }
   a.cid[i] = id;
   a.is_key[i] = a.is_key_l[i];
   a.is_classed[i] = id != 0;      // min_pts > 0 in the slab path: a labelled point was taken from a nei list (DBImproved.cs:65)
+  }
 }
 
 // the own global indices of the owned points (pre-cut mode: rank r's point i is global point gidx0 + i); once per plan
