@@ -334,6 +334,8 @@ def run_ours(args):
     evs = []
     for _ in range(args.steps):
         flush.zero_()                      # L2 flush, outside the timed interval
+        if peer_comm is not None:
+            peer_comm.barrier_dev(dev)     # ... and so is the skew the flush leaves between the ranks: a device-side barrier aligns the start of the step
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step_dev()
@@ -571,6 +573,7 @@ def run_ours(args):
         ev4 = []
         for _ in range(reps):
             flush.zero_()
+            comm4.barrier_dev(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn4(); e1.record()
             ev4.append((e0, e1))
@@ -704,7 +707,7 @@ def run_ours(args):
                                        f"{world} u-slabs (one process per GPU), 2*eps halo strips + boundary component keys + cluster-head counts exchanged " +
                                        ("over NVLink peer memory by libvpc's own kernels (no NCCL / torch op on the step)" if peer_plan is not None else "with NCCL") +
                                        ("; step replayed as one CUDA graph" if (peer_graph is not None or graph is not None) else "")),
-                       "l2": "flushed between timed steps (256 MiB write)",
+                       "l2": "flushed between timed steps (256 MiB write)" + ("; a device-side barrier kernel after the flush aligns the ranks before each timed step" if peer_plan is not None else ""),
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
             "e2e": {"value": e2e_pageable["value"], "unit": UNIT, "h2d_bytes_per_step": 16 * n_all, "d2h_bytes_per_step": 6 * n_all + 4,
                     "ms_per_step": e2e_pageable["ms_per_step"], "host_memory": e2e_pageable["host_memory"], "api": e2e_pageable["api"],

@@ -403,6 +403,8 @@ int vpc_comm_handle(vpc_comm* comm, void* handle_out);
 int vpc_comm_connect(vpc_comm* comm, const void* handles);
 int vpc_comm_connect_local(vpc_comm* comm, vpc_comm* const* all);
 int vpc_comm_error(vpc_comm* comm, int32_t* error_bits);
+/* a barrier over the ranks as one tiny kernel on `stream` (no host synchronisation); real concurrent ranks only, not the emulation mode */
+int vpc_comm_barrier_dev(vpc_comm* comm, void* stream);
 /* closes the imported heaps; with one process per GPU: disconnect on every rank, synchronise the ranks, then destroy */
 int vpc_comm_disconnect(vpc_comm* comm);
 void vpc_comm_destroy(vpc_comm* comm);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "vpc_comm_connect": (C.c_int, [_p, _p]),
     "vpc_comm_connect_local": (C.c_int, [_p, C.POINTER(_p)]),
     "vpc_comm_error": (C.c_int, [_p, _p]),
+    "vpc_comm_barrier_dev": (C.c_int, [_p, _p]),
     "vpc_comm_disconnect": (C.c_int, [_p]),
     "vpc_comm_destroy": (None, [_p]),
     "vpc_slab_plan_heap_bytes": (_i64, [_i32, _i64, _i32, _i32]),

@@ -23,7 +23,7 @@ constexpr int kPhases = 8;                       // flag rows per heap
 constexpr long long kSpinLimit = 6000000000ll;   // ~3 s at 1.9 GHz
 
 // phases (rows of the flag table)
-constexpr int kPhHalo = 0, kPhPairs = 1, kPhHeads = 2, kPhIcpNn = 3, kPhIcpSums = 4, kPhGather = 5, kPhHome = 6;
+constexpr int kPhHalo = 0, kPhPairs = 1, kPhHeads = 2, kPhIcpNn = 3, kPhIcpSums = 4, kPhGather = 5, kPhHome = 6, kPhBarrier = 7;
 
 struct HeapHeader {                              // offset 0 of every heap
   unsigned long long flag[kPhases][kMaxWorld];   // flag[phase][src]: written by rank src, read by the heap's owner
@@ -106,6 +106,23 @@ __device__ __forceinline__ unsigned long long comm_payload(const Peers& P, int s
 __device__ __forceinline__ void comm_wait_all_block(const Peers& P, int phase, unsigned long long epoch) {
   if ((int)threadIdx.x < P.world) comm_wait(P, (int)threadIdx.x, phase, epoch);
   __syncthreads();
+}
+
+// A barrier over the ranks as one tiny kernel: signal everybody, then wait for everybody (its own epoch counter, epoch[2]).  Only for
+// ranks that really run at the same time (one process per GPU / one stream per device): it signals before it waits, so it must not be
+// used in the phase-by-phase emulation of several ranks on one GPU.
+__global__ void k_comm_barrier(Peers P) {
+  __shared__ unsigned long long s_e;
+  if (threadIdx.x == 0) {
+    unsigned long long* e = &P.hdr(P.rank)->epoch[2];
+    s_e = *e + 1; *e = s_e;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < P.world) {
+    comm_signal(P, (int)threadIdx.x, kPhBarrier, s_e, 0ull);
+    comm_wait(P, (int)threadIdx.x, kPhBarrier, s_e);
+  }
 }
 
 }  // namespace vpc

@@ -191,6 +191,16 @@ int vpc_comm_error(vpc_comm* c, int32_t* error_bits) {
   return VPC_OK;
 }
 
+// device-side barrier over the ranks of the comm, enqueued on `stream` (one tiny kernel, no host synchronisation)
+int vpc_comm_barrier_dev(vpc_comm* c, void* stream) {
+  if (!c) return VPC_E_BADARG;
+  std::lock_guard<std::mutex> lk(c->ctx->mu);
+  if (!c->connected) return fail(c->ctx, VPC_E_STATE, "vpc_comm_connect has not been called");
+  DeviceGuard g(c->ctx->device);
+  VPC_LAUNCH(c->ctx, k_comm_barrier, 1, 32, static_cast<cudaStream_t>(stream), c->peers());
+  return VPC_OK;
+}
+
 // close the imported heaps (one process per GPU: call on every rank, synchronise the ranks, THEN destroy -- an exporter must not
 // free its heap while somebody still maps it)
 int vpc_comm_disconnect(vpc_comm* c) {

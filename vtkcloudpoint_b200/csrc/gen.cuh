@@ -89,25 +89,28 @@ __global__ void __launch_bounds__(256) k_gen_count(GenArgs a) {
 
 __global__ void __launch_bounds__(256) k_gen_scatter(GenArgs a) {
   __shared__ bool s_last;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  double x = 0, y = 0; int o = -1, lo = 0, hi = -1;
-  const bool ok = (i < a.n_chunk) && gen_classify(a, i, x, y, o, lo, hi);
-  // owned copy: one warp-aggregated slot request per destination present in the warp
-  const int key = ok ? o : -1;
-  const unsigned grp = __match_any_sync(kFull, key);
-  const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
-  int slot = 0;
-  if (ok) {
-    if (lane == leader) slot = atomicAdd(a.cursor + o * 2, __popc(grp));
-    slot = __shfl_sync(grp, slot, leader) + __popc(grp & ((1u << lane) - 1u)) + a.base[o][0];
-    a.dst_x[o][slot] = x; a.dst_y[o][slot] = y; a.dst_g[o][slot] = a.g0 + (int)i;
-    for (int d = lo; d <= hi; ++d)
-      if (d != o) {                         // halo copies: a small minority, plain atomics
-        const int hs = atomicAdd(a.cursor + d * 2 + 1, 1) + a.base[d][1];
-        a.dst_x[d][hs] = x; a.dst_y[d][hs] = y; a.dst_g[d][hs] = a.g0 + (int)i;
-      }
+  // few, fat blocks (block-uniform trip count: warp votes inside): every block ends in ONE system-scope fence for its peer stores
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_chunk; base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    double x = 0, y = 0; int o = -1, lo = 0, hi = -1;
+    const bool ok = (i < a.n_chunk) && gen_classify(a, i, x, y, o, lo, hi);
+    // owned copy: one warp-aggregated slot request per destination present in the warp
+    const int key = ok ? o : -1;
+    const unsigned grp = __match_any_sync(kFull, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+    int slot = 0;
+    if (ok) {
+      if (lane == leader) slot = atomicAdd(a.cursor + o * 2, __popc(grp));
+      slot = __shfl_sync(grp, slot, leader) + __popc(grp & ((1u << lane) - 1u)) + a.base[o][0];
+      a.dst_x[o][slot] = x; a.dst_y[o][slot] = y; a.dst_g[o][slot] = a.g0 + (int)i;
+      for (int d = lo; d <= hi; ++d)
+        if (d != o) {                         // halo copies: a small minority, plain atomics
+          const int hs = atomicAdd(a.cursor + d * 2 + 1, 1) + a.base[d][1];
+          a.dst_x[d][hs] = x; a.dst_y[d][hs] = y; a.dst_g[d][hs] = a.g0 + (int)i;
+        }
+    }
+    if (i < a.n_chunk) a.where[i] = ok ? make_int2(o, slot) : make_int2(-1, 0);
   }
-  if (i < a.n_chunk) a.where[i] = ok ? make_int2(o, slot) : make_int2(-1, 0);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();                 // the block's peer stores precede the ticket (and so the flags)

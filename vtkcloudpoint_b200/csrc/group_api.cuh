@@ -224,7 +224,7 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
       a.base[d][0] = (int)b0; a.base[d][1] = (int)b1;
     }
     a.first_cluster_id = first_cluster_id; a.cid = in[c].cid; a.is_key = in[c].key; a.is_classed = in[c].cls;
-    VPC_LAUNCH(sc, k_gen_scatter, blocks_for(a.n_chunk, 256), 256, G->stream[c], a);
+    VPC_LAUNCH(sc, k_gen_scatter, std::min(blocks_for(a.n_chunk, 256), sc->sm_count * 8), 256, G->stream[c], a);
   }
   // ---- the slab step, phase by phase
   for (int d = 0; d < W; ++d) {

@@ -75,6 +75,10 @@ class PeerComm:
             c.ctx._check(c._lib.vpc_comm_connect_local(c._h, arr))
         return comms
 
+    def barrier_dev(self, device):
+        """A barrier over the ranks as one tiny kernel on torch's current stream (no host synchronisation)."""
+        self.ctx._check(self._lib.vpc_comm_barrier_dev(self._h, torch.cuda.current_stream(device).cuda_stream))
+
     def error_bits(self) -> int:
         v = C.c_int32(0)
         self.ctx._check(self._lib.vpc_comm_error(self._h, C.cast(C.byref(v), C.c_void_p)))
