@@ -2,7 +2,7 @@
 
 The product is the C-ABI CUDA library libvpc.so (include/vpc.h); this package holds its
 sources (csrc/), the build recipe, the ctypes binding and the host-side mirror of the
-reference's BaseClass interface (reference_api.py).  Nothing here imports oracle/.
+reference's BaseClass interface (api.py; C++ mirror csrc/host/vpc_host.hpp; C# shim csharp/).  Nothing here imports oracle/.
 """
 from .api import Context, DbscanResult, IcpResult  # noqa: F401
 from .capi import VpcError  # noqa: F401

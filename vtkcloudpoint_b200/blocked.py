@@ -8,7 +8,7 @@ that implement it on the device (csrc/blocked.cuh, csrc/blocked_api.cuh):
                     = Context.merge_ids_by_distance  (vpc_merge_ids_by_distance)
 
 There is ONE implementation of this flow in the product (the library); the literal List-based restatement it is checked against lives
-in oracle/vpc_oracle_blocked.cpp.  Nothing here computes: the functions only arrange arrays for the calls.
+in the literal restatement in oracle/ (part 4, blocked clustering).  Nothing here computes: the functions only arrange arrays for the calls.
 """
 from __future__ import annotations
 

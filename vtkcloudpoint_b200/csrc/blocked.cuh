@@ -11,7 +11,7 @@
 //                     scan of the "this run advances idNow" flags, and one back-reaching store per affected cell
 //   zeroList        = stable compaction
 // Slot semantics (the C#'s data race on shared Point3D objects): every cell slot is a private copy of its point and a point with two
-// slots reports its LATER slot -- see oracle/vpc_oracle_blocked.cpp, which restates both that and the literal shared-object schedule.
+// slots reports its LATER slot -- see the literal restatement in oracle/ (part 4, blocked clustering), which restates both that and the literal shared-object schedule.
 #pragma once
 
 #include "common.cuh"
