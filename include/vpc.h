@@ -16,7 +16,10 @@
  *
  * Thread safety: a vpc_ctx serialises its calls with an internal mutex, so the
  * reference's ThreadPool workers (FrmMain.cs:1356-1359) may share one context or use
- * one context each.  No global mutable state.
+ * one context each.  No global mutable state.  The mutex serialises ENQUEUEING: the
+ * *_dev exports take a caller stream but work in the context's own workspaces, so keep
+ * ONE stream in flight per context (use a context per stream for concurrency), and do
+ * not capture a call that has to grow a workspace into a CUDA graph (run it once first).
  */
 #ifndef VPC_H_
 #define VPC_H_
@@ -39,9 +42,15 @@ typedef struct vpc_ctx vpc_ctx;
 
 /* ---- context ------------------------------------------------------------------- */
 
-/* One context drives one GPU (device_ids[0]; device_ids == NULL means device 0).
- * n_devices > 1 is reserved for the single-process multi-GPU mode; the multi-GPU path
- * shipped today is one process per GPU (vtkcloudpoint_b200/distributed.py). */
+/* n_devices <= 1: one context drives one GPU (device_ids[0]; device_ids == NULL means device 0).
+ * n_devices > 1 (<= 16): ONE context drives several GPUs of an NVLink box from this process.  The host-pointer calls
+ * vpc_dbscan_l1_2d, vpc_icp_rigid and vpc_dbscan_blocked_ref[_ex] then spread large inputs over those devices inside the
+ * library (csrc/group_api.cuh): DBSCAN exactly -- chunk c of the arrays goes to device c, the points are re-dealt over NVLink
+ * into slabs of x + y with 2 eps halos, clustered, merged across devices and the results pulled home (clouds below
+ * VPC_GROUP_MIN_POINTS [262144] points per device, or min_pts <= 0, stay on the first device); ICP with the source cut into
+ * slices; the blocked clustering with its cells spread over the devices.  Every other export runs on device_ids[0].
+ * A device id may appear more than once (test / emulation mode on a box with fewer GPUs: the ranks then share a GPU and their
+ * kernels are enqueued phase by phase on one stream). */
 int vpc_create(vpc_ctx** out, const int* device_ids, int n_devices);
 void vpc_destroy(vpc_ctx* ctx);
 const char* vpc_last_error(const vpc_ctx* ctx);

@@ -14,7 +14,25 @@ namespace vtkPointCloud
         public int cf = 0;              // DBImproved.cs:13 -- may be pre-seeded by the caller (FrmMain.cs:1509)
         private IntPtr ctx;
 
-        public DBImprovedGpu() { NativeMethods.Check(IntPtr.Zero, NativeMethods.vpc_create(out ctx, null, 0)); }
+        // ONE native context for the whole application: StartCode creates a DBImproved per work item (FrmMain.cs:2785), and a context
+        // owns a CUDA stream and device workspaces that should not be re-created per cell.  The context serialises its calls with an
+        // internal mutex, so the pool threads may share it.  Devices = null: GPU 0.  Devices = {0, 1, .., 7}: one context drives all
+        // those GPUs -- dbscan() / go_hell_ICP() on large clouds are then spread over them inside libvpc (include/vpc.h, vpc_create).
+        private static readonly object gate = new object();
+        private static IntPtr shared = IntPtr.Zero;
+        public static int[] Devices = null;
+
+        public DBImprovedGpu()
+        {
+            lock (gate)
+            {
+                if (shared == IntPtr.Zero)
+                    NativeMethods.Check(IntPtr.Zero, NativeMethods.vpc_create(out shared, Devices, Devices == null ? 0 : Devices.Length));
+                ctx = shared;
+            }
+        }
+        internal static IntPtr SharedContext() { return new DBImprovedGpu().ctx; }     // ICPGpu and ToolsGpu use the same native context
+        public static void Shutdown() { lock (gate) { if (shared != IntPtr.Zero) { NativeMethods.vpc_destroy(shared); shared = IntPtr.Zero; } } }
 
         public void dbscan(List<Point3D> lst, double e, int minPts)
         {
@@ -74,6 +92,44 @@ namespace vtkPointCloud
             return clusterSum;
         }
 
-        public void Dispose() { if (ctx != IntPtr.Zero) { NativeMethods.vpc_destroy(ctx); ctx = IntPtr.Zero; } }
+        // dbscanBlocked plus the list the merge needs: clusForMerge (FrmMain.cs:1517-1520) as indices into rawData with their ids
+        public int dbscanBlocked(List<Point3D> rawData, double e, int minPts, int ptsInCell, out int delSum, out long[] mergeOrder, out int[] mergeCid, out long nShared)
+        {
+            int n = rawData.Count;
+            double[] mx = new double[n], my = new double[n];
+            for (int i = 0; i < n; i++) { mx[i] = rawData[i].motor_x; my[i] = rawData[i].motor_y; }
+            int[] cid = new int[n]; long[] mo = new long[3 * n]; int[] mc = new int[3 * n];
+            int clusterSum, rows, cols, sumCells; long unassigned, nMerge;
+            NativeMethods.Check(ctx, NativeMethods.vpc_dbscan_blocked_ref_ex(ctx, mx, my, n, e, minPts, ptsInCell, cid, out clusterSum, out delSum, out rows, out cols,
+                                                                             out unassigned, out nShared, mo, mc, out nMerge, out sumCells));
+            for (int i = 0; i < n; i++) { rawData[i].clusterId = cid[i]; rawData[i].isClassed = cid[i] != 0; }
+            mergeOrder = new long[nMerge]; mergeCid = new int[nMerge];
+            Array.Copy(mo, mergeOrder, nMerge); Array.Copy(mc, mergeCid, nMerge);
+            pointsAmount += n;
+            clusterAmount = clusterSum;
+            return clusterSum;
+        }
+
+        // The centroid merge of Clustering.MergeBtn_Click (Clustering.cs:141-153) on the result of dbscanBlocked: clusForMerge comes back from
+        // vpc_dbscan_blocked_ref_ex as point indices; the per-entry arrays are gathered in list order (the order the C# sums centroids in).
+        public int mergeByDistance(List<Point3D> rawData, long[] mergeOrder, int[] mergeCid, int clusterSum, double thre)
+        {
+            int k = mergeOrder.Length;
+            double[] xyz = new double[3 * k], mx = new double[k], my = new double[k];
+            for (int t = 0; t < k; t++)
+            {
+                Point3D p = rawData[(int)mergeOrder[t]];
+                xyz[t] = p.X; xyz[k + t] = p.Y; xyz[2 * k + t] = p.Z; mx[t] = p.motor_x; my[t] = p.motor_y;
+            }
+            int[] newCid = new int[k], dfrom = new int[clusterSum], dto = new int[clusterSum], cids = new int[clusterSum];
+            double[] c5 = new double[5 * clusterSum], nc5 = new double[5 * clusterSum];
+            int newAmount, nDict, nCenters;
+            NativeMethods.Check(ctx, NativeMethods.vpc_merge_ids_by_distance(ctx, mergeCid, xyz, mx, my, k, clusterSum, thre, newCid, out newAmount,
+                                                                             dfrom, dto, out nDict, c5, cids, out nCenters, nc5));
+            for (int t = 0; t < k; t++) rawData[(int)mergeOrder[t]].clusterId = newCid[t];      // Tools.cs:557-560
+            return newAmount;
+        }
+
+        public void Dispose() { ctx = IntPtr.Zero; }   // the native context is shared: DBImprovedGpu.Shutdown() releases it at application exit
     }
 }

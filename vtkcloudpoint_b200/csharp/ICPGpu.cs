@@ -12,7 +12,7 @@ namespace vtkPointCloud
         public int itersDone; public double sseLast; public int[] orderLast;   // extras the C# discards
         public int maxIters = 0;   // 0 = unbounded like the reference (ICP.cs:180 has no cap); the VTK path uses 100 (FrmMain.cs:855)
 
-        public ICPGpu() { NativeMethods.Check(IntPtr.Zero, NativeMethods.vpc_create(out ctx, null, 0)); }
+        public ICPGpu() { ctx = DBImprovedGpu.SharedContext(); }   // one native context per application (DBImprovedGpu.Devices selects the GPUs)
 
         private static double[] Planar(List<Point3D> pts)
         {
@@ -38,6 +38,6 @@ namespace vtkPointCloud
             return Y;
         }
 
-        public void Dispose() { if (ctx != IntPtr.Zero) { NativeMethods.vpc_destroy(ctx); ctx = IntPtr.Zero; } }
+        public void Dispose() { ctx = IntPtr.Zero; }   // shared context: DBImprovedGpu.Shutdown() releases it
     }
 }

@@ -65,6 +65,32 @@ namespace vtkPointCloud
             long rowCap, [Out] double[] mx, [Out] double[] my, [Out] double[] dist, [Out] double[] xyz, [Out] byte[] keep, [Out] byte[] rowStatus,
             out long nRows, out long nKept, out long nDuplicates);
 
+        // the same call with the merge bookkeeping: shared-point count, clusForMerge (FrmMain.cs:1517-1520) as point indices + ids
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_dbscan_blocked_ref_ex(IntPtr ctx, double[] mx, double[] my, long n, double eps, int minPts, int ptsInCell,
+            [Out] int[] clusterId, out int clusterSum, out int delSum, out int rows, out int cols, out long nUnassigned, out long nShared,
+            [Out] long[] mergeOrder, [Out] int[] mergeCid, out long nMerge, out int clusterSumCells);
+
+        // Clustering.MergeBtn_Click's chain: Tools.GetClusList -> MergeIDByDistance -> refreshCensAndClusByDictionary (Tools.cs:162-195, 580-621, 521-572)
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_merge_ids_by_distance(IntPtr ctx, int[] mergeCid, double[] xyz, double[] mx, double[] my, long k, int clusterAmount,
+            double thre, [Out] int[] newCid, out int newAmount, [Out] int[] dictFrom, [Out] int[] dictTo, out int nDict, [Out] double[] centers5,
+            [Out] int[] centerIds, out int nCenters, [Out] double[] newCenters5);
+
+        // page-locked host memory: arrays allocated / registered here are copied at the PCIe rate without staging (include/vpc.h, "Host memory")
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_host_alloc(out IntPtr p, long bytes);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern void vpc_host_free(IntPtr p);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_host_register(IntPtr p, long bytes);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)]
+        internal static extern int vpc_host_unregister(IntPtr p);
+        // IntPtr overload of the clustering call for page-locked buffers
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl, EntryPoint = "vpc_dbscan_l1_2d")]
+        internal static extern int vpc_dbscan_l1_2d_ptr(IntPtr ctx, IntPtr mx, IntPtr my, long n, double eps, int minPts,
+            int firstClusterId, IntPtr clusterId, IntPtr isKey, IntPtr isClassed, out int clusterAmount);
+
         internal static void Check(IntPtr ctx, int rc)
         {
             if (rc != 0)   // the reference signals errors with MException (Matrix.cs:710-715)

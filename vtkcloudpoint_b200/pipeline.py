@@ -148,6 +148,10 @@ def run_pipeline(backend, mx, my, xyz, gidx0: int, truth_xy, *, eps: float, min_
     m = truth_xy.shape[1]
     a, b = (m * rank) // world, (m * (rank + 1)) // world
     truth_planar = torch.stack([truth_xy[0], truth_xy[1], torch.zeros_like(truth_xy[0])]).contiguous()
+    if 0 < m < world:
+        # every rank must own at least one truth point (an empty shard would leave its rank out of the collectives); all ranks see
+        # the same m, so all raise together
+        raise ValueError(f"the truth set ({m} points) is smaller than the number of ranks ({world})")
     if centres_planar.shape[1] == 0 or m == 0:
         state = torch.zeros(16, dtype=torch.float64, device=dev)
         order = torch.empty(0, dtype=torch.int32, device=dev)
