@@ -686,6 +686,24 @@ def run_ours(args):
                "ms_per_iter": 1e3 / it_s, "model_grid_build_ms": build_ms, "e2e_iters_per_s": ICP_ITERS / icp_e2e_s,
                "roofline_frac": algo_bytes * it_s / 1e9 / peak_gbs, "rmse_last": r.rmse, "kernel_ms_per_launch": icp_kernels}
 
+    # ---- the blocked ("分块") multithreaded clustering (getClusterFromMotor -> DoWork3 / StartCode -> CompleteWork3) as ONE device-resident
+    # call, N = 1 only: the C2 cloud and a 10M-point cloud, ptsInCell 200 (Clustering.Designer.cs:158), host arrays in, labels out
+    blocked = None
+    if rank == 0 and world == 1 and not args.no_blocked:
+        blocked = {"metric": "blocked_dbscan_mpts_per_s", "unit": UNIT, "pts_in_cell": 200,
+                   "api": "vpc_dbscan_blocked_ref_ex(host pointers, pageable): sort, box assignment, all StartCode work items in one batched launch, renumbering, noise re-cluster on the device"}
+        for tag, bx, by in (("c2_1m", mx, my), ("10m", *synth.dbscan_cloud(0xC5, 443, n_total=10_000_000))):
+            ctx.dbscan_blocked_ref(bx, by, EPS, MIN_PTS, 200)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                br = ctx.dbscan_blocked_ref(bx, by, EPS, MIN_PTS, 200)
+            dt = (time.perf_counter() - t0) / reps
+            blocked[tag] = {"value": len(bx) / dt / 1e6, "ms_per_call": 1e3 * dt, "points": len(bx), "cells": br["rows"] * br["cols"], "cluster_sum": br["cluster_sum"],
+                            "n_unassigned": br["n_unassigned"], "n_shared": br["n_shared"]}
+            if tag == "10m":
+                blk10 = (bx, by, br)
+
     # ---- CPU baseline (oracle port) on this box's host cores, N = 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -695,6 +713,17 @@ def run_ours(args):
         t = min(cpu_dbscan_pass(oracle, mx, my, cores) for _ in range(2))
         cpu = {"value": DB_N / t / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"one pass over the full C2 cloud ({DB_N} pts), grid-accelerated C++ port of DBImproved.dbscan, best of 2"}
+        if blocked is not None:
+            # the reference's own parallel path -- cell partition, one thread-pool task per cell (StartCode), CompleteWork3 -- as
+            # the oracle's List-based restatement on all host cores, and the GPU result checked against it
+            t0 = time.perf_counter(); ob = oracle.blocked(mx, my, EPS, MIN_PTS, 200, fast=True, n_threads=cores); t1 = time.perf_counter() - t0
+            bx, by, br = blk10
+            t0 = time.perf_counter(); ob10 = oracle.blocked(bx, by, EPS, MIN_PTS, 200, fast=True, n_threads=cores); t10 = time.perf_counter() - t0
+            g1 = ctx.dbscan_blocked_ref(mx, my, EPS, MIN_PTS, 200)
+            cpu["blocked_b2"] = {"c2_1m_mpts_per_s": DB_N / t1 / 1e6, "10m_mpts_per_s": len(bx) / t10 / 1e6, "cores": cores, "kind": "port",
+                                 "sample": "one pass each: cell partition + one thread-pool task per cell (StartCode analogue) + CompleteWork3, C++ restatement of the C# (oracle, fast variant)",
+                                 "gpu_equals_cpu": bool(np.array_equal(g1["cluster_id"], ob["cluster_id"]) and g1["cluster_sum"] == ob["cluster_sum"]
+                                                        and np.array_equal(br["cluster_id"], ob10["cluster_id"]) and br["cluster_sum"] == ob10["cluster_sum"])}
 
     if rank == 0:
         line = {
@@ -717,6 +746,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "secondary": icp,
+            "secondary_blocked": blocked,
             "kernel_ms_per_step": kernels,
         }
         if world > 1:
@@ -752,6 +782,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-blocked", action="store_true", help="N = 1: skip the blocked-clustering leg")
     ap.add_argument("--no-literal", action="store_true", help="reference arm: skip the Theta(n^2) literal timings")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: issue the slab step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--c5", action="store_true", help="N > 1: run the 10M-point pipeline leg (config C5) at this N (default: only at N = 8)")
