@@ -60,6 +60,8 @@ struct vpc_ctx {
   int sm_count = 148;
   DbArgs db_slab{};       // arguments of the last vpc_dbscan_slab_local_dev, for ..._finish_dev
   bool db_slab_valid = false;
+  DbArgs db_pre{};        // workspace laid out by the slab step's phase 0 (pre-cut mode), consumed by its phase 1
+  bool db_pre_valid = false;
   int64_t db_ws_n = -1;  // n the DBSCAN workspace is currently laid out and initialised for
   bool db_ws_banded = false;
   // optional per-kernel CUDA-event timing (bench.py's roofline leg)

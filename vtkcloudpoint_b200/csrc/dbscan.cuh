@@ -134,66 +134,45 @@ __device__ __forceinline__ bool db_valid(double x, double y, bool eps_ok) {
   return eps_ok && finite_d(x) && finite_d(y) && finite_d(x + y) && finite_d(x - y);
 }
 
-// ---- k_db_bounds: (u, v) bounding box; the last block derives the grid ------------------------
-__global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
-  const bool eps_ok = (a.eps >= 0.0);
-  double umn = INFINITY, umx = -INFINITY, vmn = INFINITY, vmx = -INFINITY;
-  const long long nth = (long long)gridDim.x * blockDim.x;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// ---- bounding box of the cloud in (u, v), shared by k_db_bounds and the slab step's halo kernels (slab.cuh), which fold the pass
+// over the points into kernels that read them anyway
+struct DbBox { double umn = INFINITY, umx = -INFINITY, vmn = INFINITY, vmx = -INFINITY; };
+__device__ __forceinline__ void db_box_take(DbBox& b, double x, double y, bool eps_ok) {
+  if (db_valid(x, y, eps_ok)) {
+    const double u = x + y, v = x - y;
+    b.umn = fmin(b.umn, u); b.umx = fmax(b.umx, u);
+    b.vmn = fmin(b.vmn, v); b.vmx = fmax(b.vmx, v);
+  }
+}
+// re-arms the scan states and the head bitmap of this invocation (any kernel before k_db_hist)
+__device__ __forceinline__ void db_bounds_rearm(const DbArgs& a, long long tid, long long nth) {
   for (long long i = tid; i < a.tiles0; i += nth) a.tile_state0[i] = 0;
   for (long long i = tid; i < a.tiles1; i += nth) a.tile_state1[i] = 0;
   if (a.banded) for (long long i = tid; i < a.tiles2; i += nth) a.tile_state2[i] = 0;
   for (long long i = tid; i <= (a.n >> 5); i += nth) a.headbits[i] = 0u;
-  auto take = [&](double x, double y) {
-    if (db_valid(x, y, eps_ok)) {
-      const double u = x + y, v = x - y;
-      umn = fmin(umn, u); umx = fmax(umx, u);
-      vmn = fmin(vmn, v); vmx = fmax(vmx, v);
-    }
-  };
-  if ((((unsigned long long)a.x | (unsigned long long)a.y) & 15ull) == 0) {   // 128-bit loads, two points each
-    const double2* x2 = reinterpret_cast<const double2*>(a.x);
-    const double2* y2 = reinterpret_cast<const double2*>(a.y);
-    const long long n2 = a.n >> 1;
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    for (long long i = tid; i < n2; i += 4 * nth) {      // eight 128-bit loads in flight per thread (NaN = not there)
-      double2 xv[4], yv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool in = i + k * nth < n2;
-        xv[k] = in ? __ldg(x2 + i + k * nth) : make_double2(nan, nan);
-        yv[k] = in ? __ldg(y2 + i + k * nth) : make_double2(nan, nan);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { take(xv[k].x, yv[k].x); take(xv[k].y, yv[k].y); }
-    }
-    if (tid == 0 && (a.n & 1)) take(__ldg(a.x + a.n - 1), __ldg(a.y + a.n - 1));
-  } else {
-    for (long long i = tid; i < a.n; i += nth) take(__ldg(a.x + i), __ldg(a.y + i));
-  }
-  umn = warp_min_d(umn); umx = warp_max_d(umx); vmn = warp_min_d(vmn); vmx = warp_max_d(vmx);
+}
+// block reduction of the boxes; thread 0 merges the block's box into the control block.  Ends in __syncthreads().
+__device__ __forceinline__ void db_box_publish(DbCtrl* c, DbBox b) {
   __shared__ double s[4][kDbBlock / kWarp];
-  __shared__ bool s_last;
+  b.umn = warp_min_d(b.umn); b.umx = warp_max_d(b.umx); b.vmn = warp_min_d(b.vmn); b.vmx = warp_max_d(b.vmx);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s[0][warp] = umn; s[1][warp] = umx; s[2][warp] = vmn; s[3][warp] = vmx; }
+  if (lane == 0) { s[0][warp] = b.umn; s[1][warp] = b.umx; s[2][warp] = b.vmn; s[3][warp] = b.vmx; }
   __syncthreads();
-  DbCtrl* c = a.ctrl;
   if (threadIdx.x == 0) {
     for (int w = 1; w < kDbBlock / kWarp; ++w) {
-      umn = fmin(umn, s[0][w]); umx = fmax(umx, s[1][w]);
-      vmn = fmin(vmn, s[2][w]); vmx = fmax(vmx, s[3][w]);
+      b.umn = fmin(b.umn, s[0][w]); b.umx = fmax(b.umx, s[1][w]);
+      b.vmn = fmin(b.vmn, s[2][w]); b.vmx = fmax(b.vmx, s[3][w]);
     }
-    if (umn <= umx) {
-      atomicMin(&c->umin_k, ord_encode(umn)); atomicMax(&c->umax_k, ord_encode(umx));
-      atomicMin(&c->vmin_k, ord_encode(vmn)); atomicMax(&c->vmax_k, ord_encode(vmx));
+    if (b.umn <= b.umx) {
+      atomicMin(&c->umin_k, ord_encode(b.umn)); atomicMax(&c->umax_k, ord_encode(b.umx));
+      atomicMin(&c->vmin_k, ord_encode(b.vmn)); atomicMax(&c->vmax_k, ord_encode(b.vmx));
     }
-    __threadfence();
-    s_last = (atomicAdd(&c->blocks_done, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
-  __threadfence();
-  // ---- grid parameters (one thread) ----
+}
+// grid parameters from the merged box (ONE thread, after every block has published); re-arms the control block
+__device__ __forceinline__ void db_grid_derive(const DbArgs& a) {
+  DbCtrl* c = a.ctrl;
   const unsigned long long ku0 = ld_relaxed_u64(&c->umin_k), ku1 = ld_relaxed_u64(&c->umax_k);
   const unsigned long long kv0 = ld_relaxed_u64(&c->vmin_k), kv1 = ld_relaxed_u64(&c->vmax_k);
   // re-arm the control block for the next invocation
@@ -232,6 +211,45 @@ __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
   c->u0 = u0; c->v0 = v0; c->h = h; c->inv_h = 1.0 / h; c->E = E;
   c->ncu = ncu; c->ncv = ncv; c->ncells = ncu * ncv; c->ncells_p1 = ncu * ncv + 1;
   c->clique = (a.seg_off != nullptr) ? 0 : clique;   // cells may mix segments: test every pair
+}
+
+// ---- k_db_bounds: (u, v) bounding box; the last block derives the grid ------------------------
+__global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
+  const bool eps_ok = (a.eps >= 0.0);
+  DbBox b;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  db_bounds_rearm(a, tid, nth);
+  if ((((unsigned long long)a.x | (unsigned long long)a.y) & 15ull) == 0) {   // 128-bit loads, two points each
+    const double2* x2 = reinterpret_cast<const double2*>(a.x);
+    const double2* y2 = reinterpret_cast<const double2*>(a.y);
+    const long long n2 = a.n >> 1;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (long long i = tid; i < n2; i += 4 * nth) {      // eight 128-bit loads in flight per thread (NaN = not there)
+      double2 xv[4], yv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool in = i + k * nth < n2;
+        xv[k] = in ? __ldg(x2 + i + k * nth) : make_double2(nan, nan);
+        yv[k] = in ? __ldg(y2 + i + k * nth) : make_double2(nan, nan);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { db_box_take(b, xv[k].x, yv[k].x, eps_ok); db_box_take(b, xv[k].y, yv[k].y, eps_ok); }
+    }
+    if (tid == 0 && (a.n & 1)) db_box_take(b, __ldg(a.x + a.n - 1), __ldg(a.y + a.n - 1), eps_ok);
+  } else {
+    for (long long i = tid; i < a.n; i += nth) db_box_take(b, __ldg(a.x + i), __ldg(a.y + i), eps_ok);
+  }
+  db_box_publish(a.ctrl, b);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&a.ctrl->blocks_done, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  db_grid_derive(a);
 }
 
 // cell coordinate of a (possibly out-of-box) u or v value; monotone non-decreasing in t
@@ -606,7 +624,8 @@ __global__ void __launch_bounds__(kDbBlock) k_db_flatten(DbArgs a) {
 
 // ---- k_db_resolve: component key per point, in ORIGINAL order ----------------------------------
 // Core points read their root's key; the non-core minority (border rule) is compacted per block.
-__global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
+template <class OnCore>
+__device__ __forceinline__ void db_resolve_body(const DbArgs& a, OnCore&& on_core) {
   __shared__ int s_list[kDbBlock];
   __shared__ int s_cnt[kDbBlock / kWarp];
   const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -622,6 +641,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
       else { a.is_key[me_i] = 1; a.compkey[me_i] = key; }
       // the minimum core index of a cluster heads it: cluster numbering ranks these (DBImproved.cs:93-110)
       if (!a.gidx && key == me_i) atomicOr(&a.headbits[me_i >> 5], 1u << (me_i & 31));
+      on_core(me_i, key);             // slab step: heads are marked in the bitmap of the index's home rank (slab.cuh)
     } else {
       border = true;
     }
@@ -683,6 +703,9 @@ __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
   }
   if (!a.cluster_id) a.is_key[me_i] = 0;
   a.compkey[me_i] = key;
+}
+__global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
+  db_resolve_body(a, [](int, int) {});
 }
 
 // number of cluster heads with an original index below idx (idx may be n)

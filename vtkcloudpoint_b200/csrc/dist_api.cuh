@@ -60,14 +60,26 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
   const int W = a.P.world;
   const int g_own = blocks_for(a.n_own, kDbBlock);
   const int g_stride = std::min(g_own, ctx->sm_count * 8);          // grid-stride kernels that end in a ticket: few, fat blocks
+  const bool lean = precut;               // the halo kernels also take the bounding box, derive the grid, clear the merge tables
   switch (phase) {
     case 0:
-      if (precut) VPC_LAUNCH(ctx, k_slb_halo_pack, g_stride, kDbBlock, s, a);
+      if (lean) {
+        int rc = dbscan_prepare(ctx, a.lx, a.ly, n_local, eps, min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg, nullptr, &ctx->db_pre);
+        if (rc) return rc;
+        ctx->db_pre_valid = true;
+        VPC_LAUNCH(ctx, k_slb_halo_pack, g_stride, kDbBlock, s, a, ctx->db_pre, static_cast<int4*>(table), (long long)(table_bytes / 16));
+      }
       break;
     case 1: {
-      if (precut) VPC_LAUNCH(ctx, k_slb_halo_pull, blocks_for(2ll * a.cap, kDbBlock), kDbBlock, s, a);
-      int rc = dbscan_enqueue(ctx, a.lx, a.ly, n_local, eps, min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg,
-                              nullptr, true);
+      int rc;
+      if (lean) {
+        if (!ctx->db_pre_valid || ctx->db_pre.n != n_local) return fail(ctx, VPC_E_STATE, "phase 0 must be the previous DBSCAN call on this context");
+        ctx->db_pre_valid = false;
+        VPC_LAUNCH(ctx, k_slb_halo_pull, blocks_for(2ll * a.cap, kDbBlock), kDbBlock, s, a, ctx->db_pre);
+        rc = dbscan_run(ctx, ctx->db_pre, s, true, true);
+      } else {
+        rc = dbscan_enqueue(ctx, a.lx, a.ly, n_local, eps, min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg, nullptr, true);
+      }
       if (rc) return rc;
       if (W > 1) {
         if (precut && !ctx->db_slab.banded) VPC_LAUNCH(ctx, k_slb_pairs_small, std::min(blocks_for(4ll * a.cap, kDbBlock), ctx->sm_count * 4), kDbBlock, s, a, ctx->db_slab);
@@ -80,23 +92,22 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
       DbArgs d = ctx->db_slab;
       d.compkey = a.gkey;
       const int gl = blocks_for(n_local, kDbBlock);
-      VPC_CUDA(ctx, cudaMemsetAsync(a.gkey, 0xff, 4ull * n_local, s));      // points outside the grid (NaN padding, non-finite input): noise
+      // points outside the grid (NaN padding, non-finite input) are noise: the halo kernels wrote their keys in the lean mode
+      if (!lean) VPC_CUDA(ctx, cudaMemsetAsync(a.gkey, 0xff, 4ull * n_local, s));
       if (W > 1) {
         MergeTables t{};
         t.g_key = static_cast<int*>(table); t.g_val = t.g_key + table_slots; t.k_key = t.g_val + table_slots; t.k_par = t.k_key + table_slots;
         t.mask = (unsigned)(table_slots - 1);
-        VPC_CUDA(ctx, cudaMemsetAsync(table, 0xff, table_bytes, s));
+        if (!lean) VPC_CUDA(ctx, cudaMemsetAsync(table, 0xff, table_bytes, s));
         VPC_LAUNCH(ctx, k_slb_merge, blocks_for((long long)W * a.cap_pairs, kDbBlock), kDbBlock, s, a, t);
         VPC_LAUNCH(ctx, k_slb_rekey, blocks_for(a.cap_pairs, kDbBlock), kDbBlock, s, a, d, t);
       }
-      VPC_LAUNCH(ctx, k_db_resolve, gl, kDbBlock, s, d);
+      VPC_LAUNCH(ctx, k_slb_resolve_heads, gl, kDbBlock, s, a, d);
       ctx->db_slab_valid = false;
-      VPC_LAUNCH(ctx, k_slb_heads, g_stride, kDbBlock, s, a);
       break;
     }
     case 3:
       VPC_LAUNCH(ctx, k_slb_heads_scan, scan_tiles(a.nwords), kScanBlock, s, a);
-      VPC_LAUNCH(ctx, k_slb_heads_publish, 1, 32, s, a);
       break;
     case 4:
       VPC_LAUNCH(ctx, k_slb_ids, g_stride, kDbBlock, s, a);
@@ -291,6 +302,7 @@ int vpc_slab_plan_create(vpc_ctx* ctx, vpc_comm* comm, const int64_t* n_per_rank
   a.scan_state = w.take<unsigned long long>(scan_tiles(a.nwords) + 1); a.scan_counter = w.take<int>(4);
   p->table = w.take<char>(p->table_bytes);
   k_slb_iota<<<blocks_for(a.n_own, kDbBlock), kDbBlock, 0, ctx->own_stream>>>(a.lg, a.n_own, a.gstart[me]);
+  a.lg_iota = 1;
   if (cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) { cudaFree(base); comm->bump = p->heap_mark; delete p; return fail(ctx, VPC_E_CUDA, "slab plan initialisation failed"); }
   *out = p;
   return VPC_OK;

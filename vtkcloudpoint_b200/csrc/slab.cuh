@@ -8,10 +8,10 @@
 //   [local DBSCAN]     dbscan.cuh on owned + halo points, component keys = minimum GLOBAL core index
 //   k_slb_pairs_pack   (global index, local key) of the core points that also live on another rank -> own heap; flag to everybody
 //   k_slb_merge        wait for everybody, pull all pairs, union the keys reported for the same point (hash tables of dbscan.cuh)
-//   [remap + resolve]  dbscan.cuh: local roots take the merged key, border rule with global keys (DBImproved.cs:87)
-//   k_slb_heads        owned core points that head their cluster set their bit in the bitmap of the rank that is HOME to that
-//                      global index (peer atomicOr when remote); flag to everybody
-//   k_slb_heads_scan   wait for everybody, popc-scan of the own bitmap; k_slb_heads_publish: the head count to everybody
+//   k_slb_rekey        local roots take the merged key; the border rule then runs with global keys (DBImproved.cs:87)
+//   k_slb_resolve_heads  the resolve pass, in which owned core points that head their cluster set their bit in the bitmap of the rank
+//                      that is HOME to that global index (peer atomicOr when remote); flag to everybody
+//   k_slb_heads_scan   wait for everybody, popc-scan of the own bitmap; its last block publishes the head count to everybody
 //   k_slb_ids          wait for everybody; id = first + 1 + (heads on lower homes) + rank inside the home's bitmap (DBImproved.cs:93-110)
 // A kernel waits only as its FIRST action and signals as its LAST, so the ranks can also be emulated one after the other on a single
 // GPU (phase by phase, vpc_api: lockstep mode) -- that is how the single-GPU test-suite exercises this file.
@@ -38,6 +38,7 @@ struct SlabArgs {
   double s_lo, s_hi, H;
   int has_left, has_right;
   int first_cluster_id;
+  int lg_iota;                              // 1: lg[i] == gstart[rank] + i for the owned points (pre-cut mode), no load needed
   // local buffers
   double* lx; double* ly; int* lg;          // local cloud: n_own owned points, then halo slots
   unsigned char* is_key_l; int* gkey;       // per local point: core flag, merged cluster key
@@ -53,31 +54,102 @@ struct SlabArgs {
 __device__ __forceinline__ bool slb_finite(double x, double y) { return finite_d(x) && finite_d(y) && finite_d(x + y) && finite_d(x - y); }
 
 // ---- halo strips: pack locally, tell the neighbours -----------------------------------------------------------------
-__global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a) {
+// The one pass over the owned points of the step's front end: it also takes their (u, v) bounding box for the local DBSCAN's grid
+// (k_db_bounds is not launched in pre-cut mode; k_slb_halo_pull adds the halo points and derives the grid), gives the points outside
+// the grid their key (noise), and clears the merge tables of phase 2.
+__global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a, DbArgs d, int4* table, long long table_int4) {
   __shared__ bool s_last;
   const int me = a.P.rank;
-  for (int base = blockIdx.x * blockDim.x; base < a.n_own; base += gridDim.x * blockDim.x) {   // block-uniform trip count (warp ballots inside)
-    const int i = base + threadIdx.x;
-    bool toL = false, toR = false;
-    double xi = 0, yi = 0;
-    if (i < a.n_own) {
-      xi = a.lx[i]; yi = a.ly[i];
-      if (slb_finite(xi, yi)) {
-        const double u = xi + yi;
-        toL = a.has_left && (u - a.H < a.s_lo);
-        toR = a.has_right && (u + a.H >= a.s_hi);
-      }
+  const bool eps_ok = (d.eps >= 0.0);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  db_bounds_rearm(d, tid, nth);
+  for (long long w = tid; w < table_int4; w += nth) table[w] = make_int4(-1, -1, -1, -1);
+  DbBox box;
+  // Boundary points are rare (~1 %): each block lists its own in shared memory and reserves strip slots with THREE global atomics per
+  // pass (a warp-aggregated atomic per warp and list put ~25k atomics on one 32-byte sector: 15 us of this kernel).
+  constexpr int kPer = 4;                                   // points per thread and pass
+  __shared__ int s_ent[kDbBlock * kPer];                    // local index of a listed point
+  __shared__ unsigned char s_fl[kDbBlock * kPer];           // toR << 1 | toL
+  __shared__ int s_n, s_cnt[3], s_base[3];
+  if (threadIdx.x == 0) { s_n = 0; s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
+  __syncthreads();
+  // one owned point: box, key of a point outside the grid, boundary list
+  auto take = [&](bool in, int i, double xi, double yi) {
+    if (!in) return;
+    if (db_valid(xi, yi, eps_ok)) {
+      const double u = xi + yi;
+      const bool toL = a.has_left && (u - a.H < a.s_lo);
+      const bool toR = a.has_right && (u + a.H >= a.s_hi);
+      db_box_take(box, xi, yi, true);
+      if (toL || toR) { const int t = atomicAdd(&s_n, 1); s_ent[t] = i; s_fl[t] = (unsigned char)((toR ? 2 : 0) | (toL ? 1 : 0)); }
+    } else {
+      a.gkey[i] = -1;                                                // never enters the grid: the resolve pass does not see it
     }
-    const int sl = db_append_slot(toL, a.counters + 0);
-    const int sr = db_append_slot(toR, a.counters + 1);
-    const int sb = db_append_slot(toL || toR, a.counters + 4);      // the same points are this rank's own pair candidates later
-    if (sl >= 0 && sl < a.cap) { a.P.at<double>(me, a.L.pack_x[0])[sl] = xi; a.P.at<double>(me, a.L.pack_y[0])[sl] = yi; a.P.at<int>(me, a.L.pack_g[0])[sl] = a.lg[i]; }
-    if (sr >= 0 && sr < a.cap) { a.P.at<double>(me, a.L.pack_x[1])[sr] = xi; a.P.at<double>(me, a.L.pack_y[1])[sr] = yi; a.P.at<int>(me, a.L.pack_g[1])[sr] = a.lg[i]; }
-    if (sb >= 0 && sb < 2 * a.cap) a.bidx[sb] = i;
+  };
+  // after a pass (block-uniform): reserve global slots, copy the listed points into the strips and the candidate list
+  auto flush = [&]() {
+    __syncthreads();
+    const int n_ent = s_n;
+    if (n_ent > 0) {                                                 // block-uniform
+      for (int t = threadIdx.x; t < n_ent; t += blockDim.x) {
+        const int e = s_fl[t];
+        if (e & 1) atomicAdd(&s_cnt[0], 1);
+        if (e & 2) atomicAdd(&s_cnt[1], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        const int c = threadIdx.x == 2 ? n_ent : s_cnt[threadIdx.x];
+        s_base[threadIdx.x] = c ? atomicAdd(a.counters + (threadIdx.x == 2 ? 4 : threadIdx.x), c) : 0;
+      }
+      __syncthreads();
+      if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;                   // now cursors inside the reserved ranges
+      __syncthreads();
+      for (int t = threadIdx.x; t < n_ent; t += blockDim.x) {
+        const int e = s_fl[t], i = s_ent[t];
+        const double xi = a.lx[i], yi = a.ly[i];
+        const int g = a.lg[i];
+        if (e & 1) { const int sl = s_base[0] + atomicAdd(&s_cnt[0], 1); if (sl < a.cap) { a.P.at<double>(me, a.L.pack_x[0])[sl] = xi; a.P.at<double>(me, a.L.pack_y[0])[sl] = yi; a.P.at<int>(me, a.L.pack_g[0])[sl] = g; } }
+        if (e & 2) { const int sr = s_base[1] + atomicAdd(&s_cnt[1], 1); if (sr < a.cap) { a.P.at<double>(me, a.L.pack_x[1])[sr] = xi; a.P.at<double>(me, a.L.pack_y[1])[sr] = yi; a.P.at<int>(me, a.L.pack_g[1])[sr] = g; } }
+        const int sb = s_base[2] + t;                                // the same points are this rank's own pair candidates later
+        if (sb < 2 * a.cap) a.bidx[sb] = i;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { s_n = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
+      __syncthreads();
+    }
+  };
+  const int span = gridDim.x * blockDim.x;
+  if ((((unsigned long long)a.lx | (unsigned long long)a.ly) & 15ull) == 0) {      // 128-bit loads, two points each, four in flight per thread
+    const double2* x2 = reinterpret_cast<const double2*>(a.lx);
+    const double2* y2 = reinterpret_cast<const double2*>(a.ly);
+    const int n2 = a.n_own >> 1;
+    for (int base = blockIdx.x * blockDim.x; base < n2; base += 2 * span) {         // block-uniform trip count
+      double2 xv[2], yv[2]; int p[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        p[k] = base + k * span + threadIdx.x;
+        const bool in = p[k] < n2;
+        xv[k] = in ? x2[p[k]] : make_double2(0.0, 0.0);
+        yv[k] = in ? y2[p[k]] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { take(p[k] < n2, 2 * p[k], xv[k].x, yv[k].x); take(p[k] < n2, 2 * p[k] + 1, xv[k].y, yv[k].y); }
+      flush();
+    }
+    if (blockIdx.x == 0) {                                                          // odd tail
+      if ((a.n_own & 1) && threadIdx.x == 0) take(true, a.n_own - 1, a.lx[a.n_own - 1], a.ly[a.n_own - 1]);
+      flush();
+    }
+  } else {
+    for (int base = blockIdx.x * blockDim.x; base < a.n_own; base += span) {
+      const int i = base + threadIdx.x;
+      if (i < a.n_own) take(true, i, a.lx[i], a.ly[i]);
+      flush();
+    }
   }
-  __syncthreads();                  // the block's stores happen-before thread 0's fence (the grid.sync pattern): ONE fence per block.
+  db_box_publish(d.ctrl, box);      // ends in __syncthreads(): the block's stores happen-before thread 0's fence (the grid.sync pattern)
   if (threadIdx.x == 0) {           // The stores are to the OWN heap (peers pull them through this GPU's L2): device scope is enough
-    __threadfence();                // here; the last block's system fence + st.release.sys publish.
+    __threadfence();                // here; the last block's system fence + the flag stores publish.
     s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
@@ -94,33 +166,49 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a) {
 }
 
 // ---- halo strips: wait for the neighbours, pull their strips, pad with NaN (= points outside the grid, DBImproved.cs:41) ------
-__global__ void __launch_bounds__(kDbBlock) k_slb_halo_pull(SlabArgs a) {
+// adds the pulled points to the bounding box; the last block derives the local DBSCAN's grid (the tail of k_db_bounds)
+__global__ void __launch_bounds__(kDbBlock) k_slb_halo_pull(SlabArgs a, DbArgs d) {
+  __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
   if (threadIdx.x == 0 && a.has_left) comm_wait(a.P, me - 1, kPhHalo, E);
   if (threadIdx.x == 1 && a.has_right) comm_wait(a.P, me + 1, kPhHalo, E);
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * a.cap) return;
-  const int side = j >= a.cap ? 1 : 0, k = side ? j - a.cap : j;     // side 0: strip from the left neighbour (its RIGHT strip)
-  const int src = side ? me + 1 : me - 1;
-  const bool have = side ? a.has_right : a.has_left;
-  int cnt = 0;
-  if (have) cnt = min((int)comm_payload(a.P, src, kPhHalo), a.cap);
-  const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  double x = nan, y = nan; int g = -1;
-  if (k < cnt) {
-    const int s = side ? 0 : 1;
-    x = ld_relaxed_sys_f64(a.P.at<double>(src, a.L.pack_x[s]) + k);
-    y = ld_relaxed_sys_f64(a.P.at<double>(src, a.L.pack_y[s]) + k);
-    g = ld_relaxed_sys_s32(a.P.at<int>(src, a.L.pack_g[s]) + k);
+  DbBox box;
+  if (j < 2 * a.cap) {
+    const int side = j >= a.cap ? 1 : 0, k = side ? j - a.cap : j;     // side 0: strip from the left neighbour (its RIGHT strip)
+    const int src = side ? me + 1 : me - 1;
+    const bool have = side ? a.has_right : a.has_left;
+    int cnt = 0;
+    if (have) cnt = min((int)comm_payload(a.P, src, kPhHalo), a.cap);
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    double x = nan, y = nan; int g = -1;
+    if (k < cnt) {
+      const int s = side ? 0 : 1;
+      x = ld_relaxed_sys_f64(a.P.at<double>(src, a.L.pack_x[s]) + k);
+      y = ld_relaxed_sys_f64(a.P.at<double>(src, a.L.pack_y[s]) + k);
+      g = ld_relaxed_sys_s32(a.P.at<int>(src, a.L.pack_g[s]) + k);
+      db_box_take(box, x, y, d.eps >= 0.0);
+    } else {
+      a.gkey[a.n_own + j] = -1;                                        // padding: outside the grid
+    }
+    a.lx[a.n_own + j] = x; a.ly[a.n_own + j] = y; a.lg[a.n_own + j] = g;
+    if (j == 0) {   // largest incoming strip (calibration of the capacities)
+      const int c0 = a.has_left ? (int)comm_payload(a.P, me - 1, kPhHalo) : 0, c1 = a.has_right ? (int)comm_payload(a.P, me + 1, kPhHalo) : 0;
+      a.status[2] = max(c0, c1);
+      a.status[6] = min(c0, a.cap) + min(c1, a.cap);      // halo points pulled over NVLink this step
+    }
   }
-  a.lx[a.n_own + j] = x; a.ly[a.n_own + j] = y; a.lg[a.n_own + j] = g;
-  if (j == 0) {   // largest incoming strip (calibration of the capacities)
-    const int c0 = a.has_left ? (int)comm_payload(a.P, me - 1, kPhHalo) : 0, c1 = a.has_right ? (int)comm_payload(a.P, me + 1, kPhHalo) : 0;
-    a.status[2] = max(c0, c1);
-    a.status[6] = min(c0, a.cap) + min(c1, a.cap);      // halo points pulled over NVLink this step
+  db_box_publish(d.ctrl, box);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&d.ctrl->blocks_done, 1u) == gridDim.x - 1);
   }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  db_grid_derive(d);
 }
 
 // ---- boundary pairs: (global index, local component key) of locally-core points that also live on another rank ---------------
@@ -225,32 +313,34 @@ __device__ __forceinline__ int slb_home_of(const SlabArgs& a, int g) {   // rank
   return q;
 }
 
-// ---- cluster heads: owned core points whose global index IS their cluster's key set their bit at the index's home ---------
-// also clears the bitmap of the other parity (nobody touches it during this step) and re-arms the scan of k_slb_heads_scan
-__global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
+// ---- cluster keys in local order + cluster heads: k_db_resolve's pass (dbscan.cuh) with the head marking folded in: an owned core
+// point whose global index IS its cluster's key sets its bit in the bitmap of the index's home rank.  Also clears the bitmap of
+// the other parity (nobody touches it during this step) and re-arms the scan of k_slb_heads_scan.
+__global__ void __launch_bounds__(kDbBlock) k_slb_resolve_heads(SlabArgs a, DbArgs d) {
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
   unsigned* other = a.P.at<unsigned>(me, a.L.bits[(E + 1) & 1]);
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < a.nwords; w += gridDim.x * blockDim.x) other[w] = 0u;
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < (a.nwords + kScanTile - 1) / kScanTile; w += gridDim.x * blockDim.x) a.scan_state[w] = 0ull;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.scan_counter = 0;
-  int remote = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_own; i += gridDim.x * blockDim.x) {
-    if (!a.is_key_l[i]) continue;
-    const int g = a.lg[i];
-    if (g >= 0 && a.gkey[i] == g) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.scan_counter[0] = 0; a.scan_counter[1] = 0; }
+  // The bits are the only stores of this kernel another rank reads.  Every marking thread CONSUMES the atomic's return value, i.e.
+  // waits until the atomic has been performed at its home L2 (over NVLink when remote), before the block's barrier; the ticket below
+  // therefore needs no fence of its own, and the blocks do not wait for their (many, scattered) key stores to drain: a
+  // __threadfence() per block here cost 13 us at 1M points.  The last block's system fence orders its flag stores behind the ticket.
+  int seen = 0;
+  db_resolve_body(d, [&](int i, int key) {
+    if (i >= a.n_own) return;
+    const int g = a.lg_iota ? a.gstart[me] + i : a.lg[i];           // (a scattered load here: this pass runs in sorted order)
+    if (g >= 0 && key == g) {
       const int home = slb_home_of(a, g);
       const int w = g - a.gstart[home];
-      remote |= home != me;
-      atomicOr_system(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5), 1u << (w & 31));
+      const unsigned old = atomicOr_system(a.P.at<unsigned>(home, a.L.bits[E & 1]) + (w >> 5), 1u << (w & 31));
+      seen |= (old == 0xffffffffu) ? 1 : 0;
     }
-  }
-  const int any_remote = __syncthreads_or(remote);   // blocks that touched a peer's bitmap order those atomics at system scope
-  if (threadIdx.x == 0) {
-    if (any_remote) __threadfence_system(); else __threadfence();
-    s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
-  }
+  });
+  (void)__syncthreads_or(seen);
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.counters + 3, 1) == (int)gridDim.x - 1);
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
   __threadfence_system();
@@ -258,21 +348,22 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_heads(SlabArgs a) {
   for (int q = 0; q < a.P.world; ++q) comm_signal(a.P, q, kPhHeads, E, 0ull);
 }
 
-// ---- wait for everybody's bits, popc-scan the own bitmap (multi-tile look-back scan: a single block took 58 us for 31k words), then
-// publish the own head count (and error bits)
+// ---- wait for everybody's bits, popc-scan the own bitmap (multi-tile look-back scan: a single block took 58 us for 31k words); the
+// block that finishes last publishes the own head count (and error bits) to everybody
 __global__ void __launch_bounds__(kScanBlock) k_slb_heads_scan(SlabArgs a) {
+  __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   comm_wait_all_block(a.P, kPhHeads, E);
   const int me = a.P.rank;
   scan_exclusive_body<true>(reinterpret_cast<const int*>(a.P.at<unsigned>(me, a.L.bits[E & 1])), a.P.at<int>(me, a.L.rank), nullptr, a.nwords, a.scan_state,
                             a.scan_counter, a.status + 4);
-}
-__global__ void __launch_bounds__(32) k_slb_heads_publish(SlabArgs a) {
-  const unsigned long long E = *a.epoch;
-  const int me = a.P.rank;
-  if (threadIdx.x == 0) __threadfence_system();
-  __syncwarp();
-  const int total = a.status[4];
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(a.scan_counter + 1, 1) == (int)gridDim.x - 1); }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) __threadfence_system();        // the ranks (own heap) precede the flags
+  __syncthreads();
+  const int total = ld_relaxed_s32(a.status + 4);
   const unsigned long long err = (unsigned long long)(unsigned)atomicOr(&a.P.hdr(me)->error, 0);
   if ((int)threadIdx.x < a.P.world) comm_signal(a.P, (int)threadIdx.x, kPhGather, E, ((unsigned long long)(unsigned)total & 0x0fffffffull) | ((err & 0xfull) << 28));
 }

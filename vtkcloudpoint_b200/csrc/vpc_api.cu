@@ -39,12 +39,15 @@ inline int blocks_for(long long n, int block) { return (int)std::max<long long>(
 // ---------------------------------------------------------------------------------------
 // DBSCAN
 // ---------------------------------------------------------------------------------------
-int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, double eps, int32_t min_pts,
+// dbscan_prepare lays the workspace out (and initialises a fresh one); dbscan_run enqueues the kernels.  The slab step's pre-cut mode
+// calls them separately: its halo kernels (slab.cuh) take the bounding box and derive the grid, so k_db_bounds is skipped there.
+int dbscan_prepare(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, double eps, int32_t min_pts,
                    int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
-                   int32_t* d_cluster_amount, cudaStream_t s, const int32_t* d_seg_off = nullptr, int32_t n_seg = 0,
-                   int32_t* d_seg_amount = nullptr, const int32_t* d_gidx = nullptr, int32_t* d_local_keys = nullptr, bool slab = false) {
+                   int32_t* d_cluster_amount, cudaStream_t s, const int32_t* d_seg_off, int32_t n_seg,
+                   int32_t* d_seg_amount, const int32_t* d_gidx, int32_t* d_local_keys, DbArgs* out) {
   const int ni = (int)n;
   ctx->db_slab_valid = false;
+  ctx->db_pre_valid = false;
   // (u, v) cells of side ~eps: about 4 x (bounding area / eps^2); 8 per point covers clustered clouds,
   // anything sparser is coarsened on the device (exactness is unaffected).
   const long long cap_ll = std::min<long long>(8ll * n + 4096, 2147483000ll);
@@ -92,8 +95,6 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   }
   a.cluster_id = d_cluster_id; a.is_key = d_is_key; a.is_classed = d_is_classed; a.cluster_amount = d_cluster_amount;
 
-  const int gpts = blocks_for(n, kDbBlock);
-  const int gstride = std::min(gpts, ctx->sm_count * 2);   // k_db_bounds: two resident blocks per SM (88 registers), each thread keeps 8 loads in flight
   // The control block and the cell counters clean up after themselves (k_db_bounds / k_db_scatter); they
   // are initialised only when the workspace is new or its layout (n) changed.
   if (d_seg_off && d_seg_amount) VPC_CUDA(ctx, cudaMemsetAsync(d_seg_amount, 0, 4ull * n_seg, s));
@@ -101,8 +102,20 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
     ctx->db_ws_n = -1;
     VPC_LAUNCH(ctx, k_db_ws_init, std::min(blocks_for((long long)cell_cap + 1, kDbBlock), ctx->sm_count * 16), kDbBlock, s, a);
   }
+  ctx->db_ws_n = -1;  // stays invalid until dbscan_run has enqueued everything
+  *out = a;
+  return VPC_OK;
+}
+
+int dbscan_run(vpc_ctx* ctx, const DbArgs& a, cudaStream_t s, bool slab, bool have_grid) {
+  const int64_t n = a.n;
+  const bool banded = a.banded != 0;
+  const int band_tiles = a.band_tiles, tiles0 = a.tiles0, tiles1 = a.tiles1, tiles2 = a.tiles2;
+  const long long nwords = (n >> 5) + 1;
+  const int gpts = blocks_for(n, kDbBlock);
+  const int gstride = std::min(gpts, ctx->sm_count * 2);   // k_db_bounds: two resident blocks per SM (88 registers), each thread keeps 8 loads in flight
   ctx->db_ws_n = -1;  // stays invalid if any launch below fails
-  VPC_LAUNCH(ctx, k_db_bounds, gstride, kDbBlock, s, a);
+  if (!have_grid) VPC_LAUNCH(ctx, k_db_bounds, gstride, kDbBlock, s, a);
   if (banded) {
     VPC_LAUNCH(ctx, k_db_band_hist, band_tiles, kDbBlock, s, a);
     VPC_LAUNCH(ctx, k_scan_exclusive<false>, tiles2, kScanBlock, s, a.band_hist, a.band_hist, (const int*)nullptr, kBands * band_tiles,
@@ -121,7 +134,7 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   VPC_LAUNCH(ctx, k_db_union, gpts, kDbBlock, s, a);
   VPC_LAUNCH(ctx, k_db_flatten, gpts, kDbBlock, s, a);
   if (slab) {   // slab phase 1 ends here; vpc_dbscan_slab_finish*_dev continues from the kept workspace
-    if (d_local_keys) VPC_LAUNCH(ctx, k_db_export_core, gpts, kDbBlock, s, a);
+    if (a.slab_export) VPC_LAUNCH(ctx, k_db_export_core, gpts, kDbBlock, s, a);
     ctx->db_slab = a;
     ctx->db_slab_valid = true;
     ctx->db_ws_n = n;
@@ -133,6 +146,17 @@ int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   VPC_LAUNCH(ctx, k_db_label, gpts, kDbBlock, s, a);
   ctx->db_ws_n = n;
   return VPC_OK;
+}
+
+int dbscan_enqueue(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n, double eps, int32_t min_pts,
+                   int32_t first_cluster_id, int32_t* d_cluster_id, uint8_t* d_is_key, uint8_t* d_is_classed,
+                   int32_t* d_cluster_amount, cudaStream_t s, const int32_t* d_seg_off = nullptr, int32_t n_seg = 0,
+                   int32_t* d_seg_amount = nullptr, const int32_t* d_gidx = nullptr, int32_t* d_local_keys = nullptr, bool slab = false) {
+  DbArgs a{};
+  const int rc = dbscan_prepare(ctx, d_x, d_y, n, eps, min_pts, first_cluster_id, d_cluster_id, d_is_key, d_is_classed, d_cluster_amount, s, d_seg_off, n_seg,
+                                d_seg_amount, d_gidx, d_local_keys, &a);
+  if (rc) return rc;
+  return dbscan_run(ctx, a, s, slab, false);
 }
 
 int dbscan_check(vpc_ctx* ctx, const void* mx, const void* my, int64_t n, double eps, const void* cid, const void* key,
