@@ -89,6 +89,15 @@ constexpr int kScanTile = kScanBlock * kScanItems;  // 4096 items per tile
 constexpr unsigned long long kTileAggregate = 1ull << 32;
 constexpr unsigned long long kTilePrefix = 2ull << 32;
 
+// Programmatic dependent launch: FIRST statement of a kernel launched with VPC_LAUNCH_PDL (before any early return, so that the grid
+// cannot complete ahead of its predecessor).  Waits until the preceding kernel of the stream has completed and its stores are
+// visible, then lets the next kernel's blocks move into the SMs this grid leaves free (they block in their own pdl_enter()).
+// A no-op in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // kPopc: the scanned value of item i is popc(in[i]) instead of in[i] (ranks inside a bitmap).
 template <bool kPopc>
 __device__ __forceinline__ void scan_exclusive_body(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr,
@@ -198,6 +207,7 @@ template <bool kPopc>
 __global__ void __launch_bounds__(kScanBlock)
 k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr,
                  int n_static, unsigned long long* tile_state, int* tile_counter, int* total_out) {
+  pdl_enter();
   scan_exclusive_body<kPopc>(in, out, n_ptr, n_static, tile_state, tile_counter, total_out);
 }
 

@@ -10,6 +10,7 @@
 #include <new>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "dbscan.cuh"
@@ -66,6 +67,7 @@ struct vpc_ctx {
   bool db_ws_banded = false;
   // optional per-kernel CUDA-event timing (bench.py's roofline leg)
   bool profile = false;
+  bool pdl = true;        // programmatic dependent launch between the kernels of a chain (VPC_PDL=0: off)
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   // pageable caller memory: worker threads + a page-locked ring (host/staging.hpp); created on first use
@@ -87,13 +89,26 @@ namespace {
     }                                                                                        \
   } while (0)
 
-#define VPC_LAUNCH(ctx, kernel, grid, block, stream, ...)                                    \
+// pdl: the kernel begins with pdl_enter() (common.cuh) and may be launched while its predecessor in the stream is still draining
+// (programmatic dependent launch; the edge survives stream capture into a CUDA graph).  VPC_PDL=0 switches it off.
+template <class... KArgs, class... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+#define VPC_LAUNCH_IMPL(ctx, use_pdl, kernel, grid, block, stream, ...)                          \
   do {                                                                                       \
     cudaEvent_t _ea = nullptr, _eb = nullptr;                                                \
     if ((ctx)->profile) {                                                                    \
       cudaEventCreate(&_ea); cudaEventCreate(&_eb); cudaEventRecord(_ea, (stream));          \
     }                                                                                        \
-    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                   \
+    launch_kernel(kernel, dim3(grid), dim3(block), (stream), (use_pdl) && (ctx)->pdl && !(ctx)->profile, __VA_ARGS__); \
     if ((ctx)->profile) {                                                                    \
       cudaEventRecord(_eb, (stream)); (ctx)->prof.push_back({#kernel, _ea, _eb});            \
     }                                                                                        \
@@ -104,6 +119,8 @@ namespace {
       return VPC_E_CUDA;                                                                     \
     }                                                                                        \
   } while (0)
+#define VPC_LAUNCH(ctx, kernel, grid, block, stream, ...) VPC_LAUNCH_IMPL(ctx, false, kernel, grid, block, stream, __VA_ARGS__)
+#define VPC_LAUNCH_PDL(ctx, kernel, grid, block, stream, ...) VPC_LAUNCH_IMPL(ctx, true, kernel, grid, block, stream, __VA_ARGS__)
 
 // worker threads for pageable host memory: VPC_COPY_THREADS (0 = plain cudaMemcpyAsync), default 2
 vpc_host::CopyPool* ctx_pool(vpc_ctx* ctx) {

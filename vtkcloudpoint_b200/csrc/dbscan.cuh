@@ -215,6 +215,7 @@ __device__ __forceinline__ void db_grid_derive(const DbArgs& a) {
 
 // ---- k_db_bounds: (u, v) bounding box; the last block derives the grid ------------------------
 __global__ void __launch_bounds__(kDbBlock) k_db_bounds(DbArgs a) {
+  pdl_enter();
   const bool eps_ok = (a.eps >= 0.0);
   DbBox b;
   const long long nth = (long long)gridDim.x * blockDim.x;
@@ -281,6 +282,7 @@ constexpr int kBands = 256;
 __device__ __forceinline__ int db_band_of(const DbCtrl& c, int key) { return (int)(((long long)key * kBands) / c.ncells); }
 
 __global__ void __launch_bounds__(kDbBlock) k_db_band_hist(DbArgs a) {
+  pdl_enter();
   __shared__ int s_cnt[kBands];
   s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_band_hist(DbArgs a) {
 // + running per-band slots).  (A variant ranking with shared-memory atomics and a separate key array was slower: the
 // extra 8-byte scattered stores cost more than the barriers saved.)
 __global__ void __launch_bounds__(kDbBlock) k_db_band_scatter(DbArgs a) {
+  pdl_enter();
   __shared__ int s_run[kBands];
   __shared__ int s_warp[kDbBlock / kWarp][kBands];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_band_scatter(DbArgs a) {
 // kBanded: thread t handles staging record t (the band partition already dropped the points outside the grid)
 template <bool kBanded>
 __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (kBanded) {
     if (i >= a.ctrl->n_banded) return;
@@ -380,6 +384,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_hist(DbArgs a) {
 // ---- k_db_scatter: physical reorder by cell; classifies dense cells on the way ------------------
 template <bool kBanded>
 __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
+  pdl_enter();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (kBanded ? (long long)a.ctrl->n_banded : (long long)a.n)) return;
   const int2 ks = a.keyslot[t];
@@ -471,6 +476,7 @@ __device__ __forceinline__ int db_block_compact(bool want, int item, int* s_list
 // ---- k_db_count: region query -> core flag (isKeyPoint, DBImproved.cs:33-54) ------------------
 // Only points outside dense cells (core[] == 2) still need a count; they are compacted per block.
 __global__ void __launch_bounds__(kDbBlock, VPC_COUNT_MINB) k_db_count(DbArgs a) {
+  pdl_enter();
   __shared__ int s_list[kDbBlock];
   __shared__ int s_cnt[kDbBlock / kWarp];
   const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -551,6 +557,7 @@ __device__ __forceinline__ int uf_unite_roots(PA parent, int ra, int rb) {
 
 // ---- k_db_union: core-core connectivity (expandCluster's reachability, DBImproved.cs:56-90) ----
 __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
+  pdl_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const DbCtrl c = *a.ctrl;
   if (p >= c.n_valid) return;
@@ -604,6 +611,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
 
 // ---- k_db_flatten: every core point learns its root; every root learns its minimum original index
 __global__ void __launch_bounds__(kDbBlock) k_db_flatten(DbArgs a) {
+  pdl_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_valid = a.ctrl->n_valid;
   const bool active = (p < n_valid) && a.core[p] == 1;
@@ -705,6 +713,7 @@ __device__ __forceinline__ void db_resolve_body(const DbArgs& a, OnCore&& on_cor
   a.compkey[me_i] = key;
 }
 __global__ void __launch_bounds__(kDbBlock) k_db_resolve(DbArgs a) {
+  pdl_enter();
   db_resolve_body(a, [](int, int) {});
 }
 
@@ -716,6 +725,7 @@ __device__ __forceinline__ int db_rank_of(const DbArgs& a, int idx) {
 
 // ---- k_db_label: cluster ids in the reference's numbering ---------------------------------------
 __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && a.cluster_amount) *a.cluster_amount = a.first_cluster_id + a.ctrl->n_roots;  // :112
   if (i >= a.n) return;
@@ -742,6 +752,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_label(DbArgs a) {
 // ---- distributed mode (one slab per GPU, vtkcloudpoint_b200/distributed.py) ----------------------
 // after k_db_flatten: per local point, its core flag and the key of its LOCAL component
 __global__ void __launch_bounds__(kDbBlock) k_db_export_core(DbArgs a) {
+  pdl_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.ctrl->n_valid) return;
   const int i = a.rec[p].sidx;

@@ -67,7 +67,7 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
         int rc = dbscan_prepare(ctx, a.lx, a.ly, n_local, eps, min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg, nullptr, &ctx->db_pre);
         if (rc) return rc;
         ctx->db_pre_valid = true;
-        VPC_LAUNCH(ctx, k_slb_halo_pack, g_stride, kDbBlock, s, a, ctx->db_pre, static_cast<int4*>(table), (long long)(table_bytes / 16));
+        VPC_LAUNCH_PDL(ctx, k_slb_halo_pack, g_stride, kDbBlock, s, a, ctx->db_pre, static_cast<int4*>(table), (long long)(table_bytes / 16));
       }
       break;
     case 1: {
@@ -75,15 +75,15 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
       if (lean) {
         if (!ctx->db_pre_valid || ctx->db_pre.n != n_local) return fail(ctx, VPC_E_STATE, "phase 0 must be the previous DBSCAN call on this context");
         ctx->db_pre_valid = false;
-        VPC_LAUNCH(ctx, k_slb_halo_pull, blocks_for(2ll * a.cap, kDbBlock), kDbBlock, s, a, ctx->db_pre);
+        VPC_LAUNCH_PDL(ctx, k_slb_halo_pull, blocks_for(2ll * a.cap, kDbBlock), kDbBlock, s, a, ctx->db_pre);
         rc = dbscan_run(ctx, ctx->db_pre, s, true, true);
       } else {
         rc = dbscan_enqueue(ctx, a.lx, a.ly, n_local, eps, min_pts, 0, nullptr, a.is_key_l, nullptr, nullptr, s, nullptr, 0, nullptr, a.lg, nullptr, true);
       }
       if (rc) return rc;
       if (W > 1) {
-        if (precut && !ctx->db_slab.banded) VPC_LAUNCH(ctx, k_slb_pairs_small, std::min(blocks_for(4ll * a.cap, kDbBlock), ctx->sm_count * 4), kDbBlock, s, a, ctx->db_slab);
-        else VPC_LAUNCH(ctx, k_slb_pairs_pack, blocks_for(n_local, kDbBlock), kDbBlock, s, a, ctx->db_slab);
+        if (precut && !ctx->db_slab.banded) VPC_LAUNCH_PDL(ctx, k_slb_pairs_small, std::min(blocks_for(4ll * a.cap, kDbBlock), ctx->sm_count * 4), kDbBlock, s, a, ctx->db_slab);
+        else VPC_LAUNCH_PDL(ctx, k_slb_pairs_pack, blocks_for(n_local, kDbBlock), kDbBlock, s, a, ctx->db_slab);
       }
       break;
     }
@@ -91,6 +91,7 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
       if (!ctx->db_slab_valid || ctx->db_slab.n != n_local) return fail(ctx, VPC_E_STATE, "phase 1 must be the previous DBSCAN call on this context");
       DbArgs d = ctx->db_slab;
       d.compkey = a.gkey;
+      d.cluster_id = a.cid;        // = "fold the core flag into the key" (core: -2 - key), as in the single-GPU pipeline: one scattered store per point
       const int gl = blocks_for(n_local, kDbBlock);
       // points outside the grid (NaN padding, non-finite input) are noise: the halo kernels wrote their keys in the lean mode
       if (!lean) VPC_CUDA(ctx, cudaMemsetAsync(a.gkey, 0xff, 4ull * n_local, s));
@@ -99,18 +100,18 @@ int slab_phase_enqueue(vpc_ctx* ctx, const SlabArgs& a, int n_local, double eps,
         t.g_key = static_cast<int*>(table); t.g_val = t.g_key + table_slots; t.k_key = t.g_val + table_slots; t.k_par = t.k_key + table_slots;
         t.mask = (unsigned)(table_slots - 1);
         if (!lean) VPC_CUDA(ctx, cudaMemsetAsync(table, 0xff, table_bytes, s));
-        VPC_LAUNCH(ctx, k_slb_merge, blocks_for((long long)W * a.cap_pairs, kDbBlock), kDbBlock, s, a, t);
-        VPC_LAUNCH(ctx, k_slb_rekey, blocks_for(a.cap_pairs, kDbBlock), kDbBlock, s, a, d, t);
+        VPC_LAUNCH_PDL(ctx, k_slb_merge, blocks_for((long long)W * a.cap_pairs, kDbBlock), kDbBlock, s, a, t);
+        VPC_LAUNCH_PDL(ctx, k_slb_rekey, blocks_for(a.cap_pairs, kDbBlock), kDbBlock, s, a, d, t);
       }
-      VPC_LAUNCH(ctx, k_slb_resolve_heads, gl, kDbBlock, s, a, d);
+      VPC_LAUNCH_PDL(ctx, k_slb_resolve_heads, gl, kDbBlock, s, a, d);
       ctx->db_slab_valid = false;
       break;
     }
     case 3:
-      VPC_LAUNCH(ctx, k_slb_heads_scan, scan_tiles(a.nwords), kScanBlock, s, a);
+      VPC_LAUNCH_PDL(ctx, k_slb_heads_scan, scan_tiles(a.nwords), kScanBlock, s, a);
       break;
     case 4:
-      VPC_LAUNCH(ctx, k_slb_ids, g_stride, kDbBlock, s, a);
+      VPC_LAUNCH_PDL(ctx, k_slb_ids, g_stride, kDbBlock, s, a);
       break;
   }
   return VPC_OK;
@@ -401,12 +402,12 @@ int vpc_icp_dist_round_phase_dev(vpc_icp_dist* p, int32_t phase, double e, int32
   IcpDistArgs a = p->a;
   a.e = e; a.max_iters = max_iters; a.st = ctx->icp_state; a.partial = ctx->icp_partial; a.ticket = ctx->icp_ticket;
   if (p->mode == 0) {
-    if (phase == 0) VPC_LAUNCH(ctx, k_icpd_nn_local, blocks_for(a.n, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
-    if (phase == 1) VPC_LAUNCH(ctx, k_icpd_reduce, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, p->d_data, a);
+    if (phase == 0) VPC_LAUNCH_PDL(ctx, k_icpd_nn_local, blocks_for(a.n, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
+    if (phase == 1) VPC_LAUNCH_PDL(ctx, k_icpd_reduce, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, p->d_data, a);
   } else {
-    if (phase == 0) VPC_LAUNCH(ctx, k_icpd_iter_local, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
+    if (phase == 0) VPC_LAUNCH_PDL(ctx, k_icpd_iter_local, blocks_for(a.slice_cap, kIterBlock), kIterBlock, s, ctx->model, p->d_data, a);
   }
-  if (phase == 2) VPC_LAUNCH(ctx, k_icpd_solve, 1, 32, s, a);
+  if (phase == 2) VPC_LAUNCH_PDL(ctx, k_icpd_solve, 1, 32, s, a);
   return VPC_OK;
 }
 

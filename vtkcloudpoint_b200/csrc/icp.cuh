@@ -595,6 +595,7 @@ constexpr int kIterBlock = VPC_ICP_ITER_BLOCK;
 __global__ void __launch_bounds__(kIterBlock)
 k_icp_iter(IcpModel g, const double* __restrict__ data, int n, double e, int max_iters, IcpState* st,
            int* __restrict__ order, double* __restrict__ partial, unsigned* ticket) {
+  pdl_enter();
   if (st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double s[kIcpSums];

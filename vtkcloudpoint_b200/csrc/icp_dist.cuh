@@ -99,6 +99,7 @@ __device__ __forceinline__ void icpd_publish_sums(const IcpDistArgs& a, const do
 
 // ---- target sharded, step 1: this shard's candidate for every data point, into the own heap ------------------------------------
 __global__ void __launch_bounds__(kIterBlock) k_icpd_nn_local(IcpModel g, const double* __restrict__ data, IcpDistArgs a) {
+  pdl_enter();
   if (a.st->done) return;
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch + 1;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(kIterBlock) k_icpd_nn_local(IcpModel g, const 
 
 // ---- target sharded, step 2: my slice of the data points, candidates pulled from every shard ---------------------------------------
 __global__ void __launch_bounds__(kIterBlock) k_icpd_reduce(const double* __restrict__ data, IcpDistArgs a) {
+  pdl_enter();
   if (a.st->done) return;
   __shared__ double S[kIcpSums];
   const unsigned long long E = *a.epoch + 1;
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(kIterBlock) k_icpd_reduce(const double* __rest
 
 // ---- source sharded: my slice of the data against the whole (replicated) model ---------------------------------------------
 __global__ void __launch_bounds__(kIterBlock) k_icpd_iter_local(IcpModel g, const double* __restrict__ data, IcpDistArgs a) {
+  pdl_enter();
   if (a.st->done) return;
   __shared__ double S[kIcpSums];
   const unsigned long long E = *a.epoch + 1;
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(kIterBlock) k_icpd_iter_local(IcpModel g, cons
 
 // ---- every rank: the `world` partial sums in rank order -> the rigid step (replicated, bit-identical on all ranks) -------------
 __global__ void __launch_bounds__(32) k_icpd_solve(IcpDistArgs a) {
+  pdl_enter();
   if (a.st->done) return;
   __shared__ double S[kIcpSums];
   const unsigned long long E = *a.epoch + 1;

@@ -58,6 +58,7 @@ __device__ __forceinline__ bool slb_finite(double x, double y) { return finite_d
 // (k_db_bounds is not launched in pre-cut mode; k_slb_halo_pull adds the halo points and derives the grid), gives the points outside
 // the grid their key (noise), and clears the merge tables of phase 2.
 __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a, DbArgs d, int4* table, long long table_int4) {
+  pdl_enter();
   __shared__ bool s_last;
   const int me = a.P.rank;
   const bool eps_ok = (d.eps >= 0.0);
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pack(SlabArgs a, DbArgs d
 // ---- halo strips: wait for the neighbours, pull their strips, pad with NaN (= points outside the grid, DBImproved.cs:41) ------
 // adds the pulled points to the bounding box; the last block derives the local DBSCAN's grid (the tail of k_db_bounds)
 __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pull(SlabArgs a, DbArgs d) {
+  pdl_enter();
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_halo_pull(SlabArgs a, DbArgs d
 // walks the SORTED positions of the workspace the local DBSCAN kept (valid for the direct and the banded layout): coordinates, local
 // index, parent and core flag of a point sit together there
 __global__ void __launch_bounds__(kDbBlock) k_slb_pairs_pack(SlabArgs a, DbArgs d) {
+  pdl_enter();
   __shared__ bool s_last;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   bool want = false;
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_pairs_pack(SlabArgs a, DbArgs 
 // the same for the direct (non-banded) layout in pre-cut mode, without a pass over the whole cloud: the candidates are the halo slots
 // and the own boundary points k_slb_halo_pack listed; core flag and key come from the workspace through keyslot (by local index)
 __global__ void __launch_bounds__(kDbBlock) k_slb_pairs_small(SlabArgs a, DbArgs d) {
+  pdl_enter();
   __shared__ bool s_last;
   const int me = a.P.rank;
   const int n_cand = 2 * a.cap + a.status[7];
@@ -281,10 +285,11 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_pairs_small(SlabArgs a, DbArgs
 
 // ---- cross-slab merge: pull everybody's pairs, union the keys that name the same point -----------------------------------
 __global__ void __launch_bounds__(kDbBlock) k_slb_merge(SlabArgs a, MergeTables t) {
+  pdl_enter();
   const unsigned long long E = *a.epoch;
   comm_wait_all_block(a.P, kPhPairs, E);
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= (long long)a.P.world * a.cap_pairs) return;
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (few, fat blocks lose here: 23 us instead of 17, the hash
+  if (j >= (long long)a.P.world * a.cap_pairs) return;                        // inserts are latency chains and want the parallelism)
   const int r = (int)(j / a.cap_pairs), q = (int)(j % a.cap_pairs);
   if (q >= min((int)comm_payload(a.P, r, kPhPairs), a.cap_pairs)) return;
   const unsigned long long raw = ld_relaxed_sys_u64(a.P.at<unsigned long long>(r, a.L.pairs) + q);
@@ -299,6 +304,7 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_merge(SlabArgs a, MergeTables 
 // every local root behind a pair this rank reported takes the minimum key of its merged set (the other roots kept theirs: their
 // components touch no slab boundary).  Pairs of one component store the same value: benign.
 __global__ void __launch_bounds__(kDbBlock) k_slb_rekey(SlabArgs a, DbArgs d, MergeTables t) {
+  pdl_enter();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= min(a.status[3], a.cap_pairs)) return;
   const int2 gk = a.P.at<int2>(a.P.rank, a.L.pairs)[q];
@@ -317,6 +323,7 @@ __device__ __forceinline__ int slb_home_of(const SlabArgs& a, int g) {   // rank
 // point whose global index IS its cluster's key sets its bit in the bitmap of the index's home rank.  Also clears the bitmap of
 // the other parity (nobody touches it during this step) and re-arms the scan of k_slb_heads_scan.
 __global__ void __launch_bounds__(kDbBlock) k_slb_resolve_heads(SlabArgs a, DbArgs d) {
+  pdl_enter();
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   const int me = a.P.rank;
@@ -351,6 +358,7 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_resolve_heads(SlabArgs a, DbAr
 // ---- wait for everybody's bits, popc-scan the own bitmap (multi-tile look-back scan: a single block took 58 us for 31k words); the
 // block that finishes last publishes the own head count (and error bits) to everybody
 __global__ void __launch_bounds__(kScanBlock) k_slb_heads_scan(SlabArgs a) {
+  pdl_enter();
   __shared__ bool s_last;
   const unsigned long long E = *a.epoch;
   comm_wait_all_block(a.P, kPhHeads, E);
@@ -370,6 +378,7 @@ __global__ void __launch_bounds__(kScanBlock) k_slb_heads_scan(SlabArgs a) {
 
 // ---- ids in the reference's numbering: clusters ranked by their minimum core index (DBImproved.cs:93-110) -----------------------
 __global__ void __launch_bounds__(kDbBlock) k_slb_ids(SlabArgs a) {
+  pdl_enter();
   __shared__ int s_base[kMaxWorld + 1];
   __shared__ int s_err;
   const unsigned long long E = *a.epoch;
@@ -386,7 +395,9 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_ids(SlabArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.status[0] = a.first_cluster_id + s_base[a.P.world]; a.status[1] = s_err; a.status[5] = (int)E; }
   // few, fat blocks: the wait above ends in a system-scope fence per block (3906 of them cost ~20 us at 1M points)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_own; i += gridDim.x * blockDim.x) {
-  const int k = a.gkey[i];
+  const int kk = a.gkey[i];                      // core points: -2 - key (the resolve pass folds the flag in), others: key or -1
+  const bool core = kk < -1;
+  const int k = core ? -2 - kk : kk;
   int id = 0;
   if (k >= 0) {
     const int home = slb_home_of(a, k);
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(kDbBlock) k_slb_ids(SlabArgs a) {
     id = a.first_cluster_id + 1 + s_base[home] + r;
   }
   a.cid[i] = id;
-  a.is_key[i] = a.is_key_l[i];
+  a.is_key[i] = core ? 1 : 0;
   a.is_classed[i] = id != 0;      // min_pts > 0 in the slab path: a labelled point was taken from a nei list (DBImproved.cs:65)
   }
 }

@@ -115,35 +115,35 @@ int dbscan_run(vpc_ctx* ctx, const DbArgs& a, cudaStream_t s, bool slab, bool ha
   const int gpts = blocks_for(n, kDbBlock);
   const int gstride = std::min(gpts, ctx->sm_count * 2);   // k_db_bounds: two resident blocks per SM (88 registers), each thread keeps 8 loads in flight
   ctx->db_ws_n = -1;  // stays invalid if any launch below fails
-  if (!have_grid) VPC_LAUNCH(ctx, k_db_bounds, gstride, kDbBlock, s, a);
+  if (!have_grid) VPC_LAUNCH_PDL(ctx, k_db_bounds, gstride, kDbBlock, s, a);
   if (banded) {
-    VPC_LAUNCH(ctx, k_db_band_hist, band_tiles, kDbBlock, s, a);
-    VPC_LAUNCH(ctx, k_scan_exclusive<false>, tiles2, kScanBlock, s, a.band_hist, a.band_hist, (const int*)nullptr, kBands * band_tiles,
+    VPC_LAUNCH_PDL(ctx, k_db_band_hist, band_tiles, kDbBlock, s, a);
+    VPC_LAUNCH_PDL(ctx, k_scan_exclusive<false>, tiles2, kScanBlock, s, a.band_hist, a.band_hist, (const int*)nullptr, kBands * band_tiles,
                a.tile_state2, &a.ctrl->scan_counter[2], &a.ctrl->n_banded);
-    VPC_LAUNCH(ctx, k_db_band_scatter, band_tiles, kDbBlock, s, a);
-    VPC_LAUNCH(ctx, k_db_hist<true>, gpts, kDbBlock, s, a);
+    VPC_LAUNCH_PDL(ctx, k_db_band_scatter, band_tiles, kDbBlock, s, a);
+    VPC_LAUNCH_PDL(ctx, k_db_hist<true>, gpts, kDbBlock, s, a);
   } else {
-    VPC_LAUNCH(ctx, k_db_hist<false>, gpts, kDbBlock, s, a);
+    VPC_LAUNCH_PDL(ctx, k_db_hist<false>, gpts, kDbBlock, s, a);
   }
-  VPC_LAUNCH(ctx, k_scan_exclusive<false>, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0,
+  VPC_LAUNCH_PDL(ctx, k_scan_exclusive<false>, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0,
              a.tile_state0, &a.ctrl->scan_counter[0], &a.ctrl->n_valid);
-  if (banded) VPC_LAUNCH(ctx, k_db_scatter<true>, gpts, kDbBlock, s, a);
-  else VPC_LAUNCH(ctx, k_db_scatter<false>, gpts, kDbBlock, s, a);
+  if (banded) VPC_LAUNCH_PDL(ctx, k_db_scatter<true>, gpts, kDbBlock, s, a);
+  else VPC_LAUNCH_PDL(ctx, k_db_scatter<false>, gpts, kDbBlock, s, a);
   ctx->db_ws_banded = banded;
-  VPC_LAUNCH(ctx, k_db_count, gpts, kDbBlock, s, a);
-  VPC_LAUNCH(ctx, k_db_union, gpts, kDbBlock, s, a);
-  VPC_LAUNCH(ctx, k_db_flatten, gpts, kDbBlock, s, a);
+  VPC_LAUNCH_PDL(ctx, k_db_count, gpts, kDbBlock, s, a);
+  VPC_LAUNCH_PDL(ctx, k_db_union, gpts, kDbBlock, s, a);
+  VPC_LAUNCH_PDL(ctx, k_db_flatten, gpts, kDbBlock, s, a);
   if (slab) {   // slab phase 1 ends here; vpc_dbscan_slab_finish*_dev continues from the kept workspace
-    if (a.slab_export) VPC_LAUNCH(ctx, k_db_export_core, gpts, kDbBlock, s, a);
+    if (a.slab_export) VPC_LAUNCH_PDL(ctx, k_db_export_core, gpts, kDbBlock, s, a);
     ctx->db_slab = a;
     ctx->db_slab_valid = true;
     ctx->db_ws_n = n;
     return VPC_OK;
   }
-  VPC_LAUNCH(ctx, k_db_resolve, gpts, kDbBlock, s, a);
-  VPC_LAUNCH(ctx, k_scan_exclusive<true>, tiles1, kScanBlock, s, reinterpret_cast<const int*>(a.headbits), a.rank, (const int*)nullptr, (int)nwords, a.tile_state1,
+  VPC_LAUNCH_PDL(ctx, k_db_resolve, gpts, kDbBlock, s, a);
+  VPC_LAUNCH_PDL(ctx, k_scan_exclusive<true>, tiles1, kScanBlock, s, reinterpret_cast<const int*>(a.headbits), a.rank, (const int*)nullptr, (int)nwords, a.tile_state1,
              &a.ctrl->scan_counter[1], &a.ctrl->n_roots);
-  VPC_LAUNCH(ctx, k_db_label, gpts, kDbBlock, s, a);
+  VPC_LAUNCH_PDL(ctx, k_db_label, gpts, kDbBlock, s, a);
   ctx->db_ws_n = n;
   return VPC_OK;
 }
@@ -219,7 +219,7 @@ int icp_enqueue_rounds(vpc_ctx* ctx, const double* d_data, int64_t n, double e, 
                        int32_t* d_order, cudaStream_t s) {
   const int nb = ctx->icp_partial_blocks;
   for (int r = 0; r < rounds; ++r) {
-    VPC_LAUNCH(ctx, k_icp_iter, nb, kIterBlock, s, ctx->model, d_data, (int)n, e, max_iters, ctx->icp_state, d_order,
+    VPC_LAUNCH_PDL(ctx, k_icp_iter, nb, kIterBlock, s, ctx->model, d_data, (int)n, e, max_iters, ctx->icp_state, d_order,
                ctx->icp_partial, ctx->icp_ticket);
   }
   return VPC_OK;
@@ -316,6 +316,7 @@ int vpc_create(vpc_ctx** out, const int* device_ids, int n_devices) {
   if (!ctx) return VPC_E_NOMEM;
   ctx->device = dev;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = std::getenv("VPC_PDL")) ctx->pdl = std::atoi(e) != 0;
   DeviceGuard g(dev);
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VPC_E_CUDA; }
   if (n_devices > 1) {                         // one process, several GPUs: a sub-context per rank (group_api.cuh)
