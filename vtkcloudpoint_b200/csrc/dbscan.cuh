@@ -110,6 +110,9 @@ struct DbArgs {
 #ifndef VPC_COUNT_MINB
 #define VPC_COUNT_MINB 1
 #endif
+#ifndef VPC_UNION_MINB
+#define VPC_UNION_MINB 8   // k_db_union wants every warp slot: 32 registers 46 us, 46 registers (5 blocks per SM) 57 us at 1M points
+#endif
 constexpr int kDbBlock = VPC_DB_BLOCK;
 constexpr int kNbrCap = 8;   // one 32-byte sector of neighbour positions per non-core point
 constexpr int kNone = 0x7fffffff;
@@ -556,7 +559,7 @@ __device__ __forceinline__ int uf_unite_roots(PA parent, int ra, int rb) {
 }
 
 // ---- k_db_union: core-core connectivity (expandCluster's reachability, DBImproved.cs:56-90) ----
-__global__ void __launch_bounds__(kDbBlock) k_db_union(DbArgs a) {
+__global__ void __launch_bounds__(kDbBlock, VPC_UNION_MINB) k_db_union(DbArgs a) {
   pdl_enter();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const DbCtrl c = *a.ctrl;
