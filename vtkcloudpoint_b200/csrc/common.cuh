@@ -82,8 +82,14 @@ __device__ __forceinline__ double warp_max_d(double v) {
 // Scans `count` int32 items (count read from *n_ptr when n_ptr != nullptr, else n_static).
 // tile_state: one u64 per tile, zeroed before the launch; tile_counter: one int, zeroed.
 // total_out (nullable) receives the grand total.  in == out is allowed.
-constexpr int kScanBlock = 256;
-constexpr int kScanItems = 16;
+#ifndef VPC_SCAN_BLOCK
+#define VPC_SCAN_BLOCK 256
+#endif
+#ifndef VPC_SCAN_ITEMS
+#define VPC_SCAN_ITEMS 16
+#endif
+constexpr int kScanBlock = VPC_SCAN_BLOCK;
+constexpr int kScanItems = VPC_SCAN_ITEMS;
 constexpr int kScanTile = kScanBlock * kScanItems;  // 4096 items per tile
 
 constexpr unsigned long long kTileAggregate = 1ull << 32;
