@@ -73,6 +73,7 @@ struct vpc_ctx {
   // pageable caller memory: worker threads + a page-locked ring (host/staging.hpp); created on first use
   vpc_host::CopyPool* pool = nullptr;
   bool pool_tried = false;
+  int copy_workers_forced = 0;   // VPC_COPY_THREADS: every copy uses this many workers (0 = chosen by size)
   vpc_host::Stager stager;
   // single-process multi-GPU mode (vpc_create with n_devices > 1): one sub-context per rank, see group_api.cuh
   struct vpc_group* group = nullptr;
@@ -122,15 +123,16 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaS
 #define VPC_LAUNCH(ctx, kernel, grid, block, stream, ...) VPC_LAUNCH_IMPL(ctx, false, kernel, grid, block, stream, __VA_ARGS__)
 #define VPC_LAUNCH_PDL(ctx, kernel, grid, block, stream, ...) VPC_LAUNCH_IMPL(ctx, true, kernel, grid, block, stream, __VA_ARGS__)
 
-// worker threads for pageable host memory: VPC_COPY_THREADS (0 = plain cudaMemcpyAsync), default 2
+// worker threads for pageable host memory: VPC_COPY_THREADS (0 = plain cudaMemcpyAsync).  The pool holds up to eight; a copy engages
+// two of them below 24 MiB and more above (host/staging.hpp).  With VPC_COPY_THREADS set, every copy may use all of them.
 vpc_host::CopyPool* ctx_pool(vpc_ctx* ctx) {
   if (!ctx->pool_tried) {
     ctx->pool_tried = true;
-    // two workers + the caller saturate the host's copy bandwidth (measured on the B200 box, 16 cores: 1 / 2 / 4 / 8 workers give
-    // 0.77 / 1.00 / 0.98 / 0.95 Gpts/s end to end at 1M points, the driver's own pageable path 0.71)
-    int t = std::thread::hardware_concurrency() >= 4 ? 2 : 1;
-    if (const char* e = std::getenv("VPC_COPY_THREADS")) t = std::atoi(e);
+    const unsigned hw = std::thread::hardware_concurrency();
+    int t = hw >= 12 ? 8 : (hw >= 6 ? 4 : (hw >= 4 ? 2 : 1));
+    if (const char* e = std::getenv("VPC_COPY_THREADS")) { t = std::atoi(e); ctx->copy_workers_forced = t; }
     if (t > 0) ctx->pool = new (std::nothrow) vpc_host::CopyPool(t);
+    ctx->stager.forced_workers = ctx->copy_workers_forced;
   }
   return ctx->pool;
 }

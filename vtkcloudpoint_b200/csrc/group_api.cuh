@@ -68,6 +68,8 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
   vpc_group* G = top->group;
   const int W = G->world;
   vpc_host::CopyPool* pool = ctx_pool(top);
+  // the copies of a call are many small ones (a chunk per device): the worker count follows the CALL's size (host/staging.hpp)
+  const int copy_workers = top->copy_workers_forced > 0 ? top->copy_workers_forced : (16ull * (size_t)n < (24u << 20) ? 2 : 8);
   static const bool trace = std::getenv("VPC_GROUP_TRACE") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
   auto mark = [&](const char* what) {
@@ -99,8 +101,8 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     cudaStream_t s = G->stream[c];
     const size_t nc = (size_t)(lo[c + 1] - lo[c]);
     if (pool) VPC_CUDA(top, sc->stager.reserve(16ull * nc));
-    VPC_CUDA(top, sc->stager.h2d(pool, in[c].x, mx + lo[c], 8 * nc, s));
-    VPC_CUDA(top, sc->stager.h2d(pool, in[c].y, my + lo[c], 8 * nc, s));
+    VPC_CUDA(top, sc->stager.h2d(pool, in[c].x, mx + lo[c], 8 * nc, s, -1, copy_workers));
+    VPC_CUDA(top, sc->stager.h2d(pool, in[c].y, my + lo[c], 8 * nc, s, -1, copy_workers));
     const unsigned long long init[4] = {~0ull, 0ull, 0ull, 0ull};
     VPC_CUDA(top, cudaMemcpyAsync(in[c].range, init, 32, cudaMemcpyHostToDevice, s));
     VPC_CUDA(top, cudaMemsetAsync(in[c].counts, 0, 4 * kMaxWorld * 3, s));
@@ -257,9 +259,9 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     DeviceGuard g(sc->device);
     cudaStream_t s = G->stream[c];
     const size_t nc = (size_t)(lo[c + 1] - lo[c]);
-    VPC_CUDA(top, sc->stager.d2h(pool, cluster_id + lo[c], in[c].cid, 4 * nc, s));
-    VPC_CUDA(top, sc->stager.d2h(pool, is_key + lo[c], in[c].key, nc, s));
-    VPC_CUDA(top, sc->stager.d2h(pool, is_classed + lo[c], in[c].cls, nc, s));
+    VPC_CUDA(top, sc->stager.d2h(pool, cluster_id + lo[c], in[c].cid, 4 * nc, s, -1, copy_workers));
+    VPC_CUDA(top, sc->stager.d2h(pool, is_key + lo[c], in[c].key, nc, s, -1, copy_workers));
+    VPC_CUDA(top, sc->stager.d2h(pool, is_classed + lo[c], in[c].cls, nc, s, -1, copy_workers));
     if (c == 0) VPC_CUDA(top, cudaMemcpyAsync(status, sa[0].status, 64, cudaMemcpyDeviceToHost, s));
   }
   for (int c = 0; c < W; ++c) {
