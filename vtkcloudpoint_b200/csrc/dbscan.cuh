@@ -108,7 +108,7 @@ struct DbArgs {
 #define VPC_DB_BLOCK 256
 #endif
 #ifndef VPC_COUNT_MINB
-#define VPC_COUNT_MINB 1
+#define VPC_COUNT_MINB 4   // 64 registers: above that the step loses more than k_db_count gains (profiles/r02_experiments.md)
 #endif
 #ifndef VPC_UNION_MINB
 #define VPC_UNION_MINB 8   // k_db_union wants every warp slot: 32 registers 46 us, 46 registers (5 blocks per SM) 57 us at 1M points
@@ -457,6 +457,37 @@ __device__ __forceinline__ int db_count_range(const DbRec* __restrict__ rec, int
   return cnt;
 }
 
+// The same over FOUR row ranges treated as one candidate sequence, VPC_COUNT_ILP loads in flight: a fringe point's ~40 candidates
+// take 5 dependent round trips instead of ~3 per row.  Stops after a batch once `need` is reached (the list of a core point is unused).
+#ifndef VPC_COUNT_ILP
+#define VPC_COUNT_ILP 6
+#endif
+#ifndef VPC_COUNT_PRELOAD
+#define VPC_COUNT_PRELOAD 1
+#endif
+__device__ __forceinline__ int db_count_rows(const DbRec* __restrict__ rec, const int (&j0)[4], const int (&j1)[4], int s, int e, double2 me, double eps,
+                                             const int* __restrict__ sseg, int myseg, int self, int* __restrict__ list, int& n_list, int cnt, int need) {
+  constexpr int K = VPC_COUNT_ILP > 0 ? VPC_COUNT_ILP : 1;
+  const int p1 = j1[0] - j0[0], p2 = p1 + (j1[1] - j0[1]), p3 = p2 + (j1[2] - j0[2]), tot = p3 + (j1[3] - j0[3]);
+  for (int t = 0; t < tot && cnt < need; t += K) {
+    int jj[K];
+    double2 q[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int tt = min(t + k, tot - 1);
+      jj[k] = tt < p1 ? j0[0] + tt : (tt < p2 ? j0[1] + (tt - p1) : (tt < p3 ? j0[2] + (tt - p2) : j0[3] + (tt - p3)));
+      q[k] = db_xy(rec, jj[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const bool hit = t + k < tot && !(jj[k] >= s && jj[k] < e) && db_near(me, q[k], eps) && (!sseg || sseg[jj[k]] == myseg);
+      cnt += hit ? 1 : 0;
+      if (hit && jj[k] != self) { if (n_list < kNbrCap) list[n_list] = jj[k]; ++n_list; }
+    }
+  }
+  return cnt;
+}
+
 // Block-level stream compaction: threads with `want` append `item` to a shared list in thread order.
 // Returns the list length (same for every thread).  Needs kDbBlock ints of shared memory.
 __device__ __forceinline__ int db_block_compact(bool want, int item, int* s_list, int* s_warp_cnt) {
@@ -494,6 +525,19 @@ __global__ void __launch_bounds__(kDbBlock, VPC_COUNT_MINB) k_db_count(DbArgs a)
   const int need = a.min_pts;
   const int own = st.cv * c.ncu + st.cu;
   const int s = __ldg(a.cell_start + own), e = __ldg(a.cell_start + own + 1);
+  int j0[4], j1[4];
+  auto load_rows = [&](int rb) {       // all row ranges of a group of four rows: independent loads
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = rb + r;
+      const bool ok = row <= st.vhi;
+      j0[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.ulo) : 0;
+      j1[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.uhi + 1) : 0;
+    }
+  };
+#if VPC_COUNT_PRELOAD
+  load_rows(st.vlo);                   // in flight together with the own cell's range
+#endif
   const int myseg = a.seg_off ? a.sseg[p] : 0;
   int cnt = 0, es = 0, ee = 0;         // [es, ee): range excluded from the tests because it is already counted
   int* list = a.nbr + (long long)p * kNbrCap;   // streamed out as found: one 32-byte sector per point
@@ -504,17 +548,14 @@ __global__ void __launch_bounds__(kDbBlock, VPC_COUNT_MINB) k_db_count(DbArgs a)
       if (j != p) { if (n_list < kNbrCap) list[n_list] = j; ++n_list; }
   }
   for (int rb = st.vlo; rb <= st.vhi && cnt < need; rb += 4) {
-    int j0[4], j1[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {      // all row ranges first: independent loads
-      const int row = rb + r;
-      const bool ok = row <= st.vhi;
-      j0[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.ulo) : 0;
-      j1[r] = ok ? __ldg(a.cell_start + row * c.ncu + st.uhi + 1) : 0;
-    }
+    if (!VPC_COUNT_PRELOAD || rb != st.vlo) load_rows(rb);
+#if VPC_COUNT_ILP > 0
+    cnt = db_count_rows(a.rec, j0, j1, es, ee, me, a.eps, a.sseg, myseg, p, list, n_list, cnt, need);
+#else
 #pragma unroll
     for (int r = 0; r < 4; ++r)
       if (cnt < need) cnt += db_count_range(a.rec, j0[r], j1[r], es, ee, me, a.eps, a.sseg, myseg, p, list, n_list);
+#endif
   }
   const bool core = cnt >= need;       // only 'count >= minPts' matters (:47)
   // a non-core point has seen ALL its neighbours (no early exit): its list is complete unless it overflowed
