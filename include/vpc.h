@@ -67,7 +67,8 @@ int64_t vpc_profile_report(vpc_ctx* ctx, char* buf, int64_t cap);
 
 /* Host memory.  The host-pointer exports accept ANY host memory.  Pageable arrays -- what the .NET marshaller passes for a
  * double[] argument: pinned against the GC for the call, but not page-locked -- are moved by worker threads through a page-locked
- * ring inside the context (csrc/host/staging.hpp; VPC_COPY_THREADS sets the thread count, 0 = plain cudaMemcpy).  Arrays that are
+ * ring inside the context (csrc/host/staging.hpp: two threads for copies below 24 MiB, up to eight above; VPC_COPY_THREADS fixes
+ * the count, 0 = plain cudaMemcpy).  Arrays that are
  * page-locked (allocated with vpc_host_alloc, or registered once with vpc_host_register) are copied directly at the PCIe rate:
  * a shim that keeps its flattened coordinate arrays between calls should use those. */
 int vpc_host_alloc(void** out, int64_t bytes);
