@@ -101,8 +101,8 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     cudaStream_t s = G->stream[c];
     const size_t nc = (size_t)(lo[c + 1] - lo[c]);
     if (pool) VPC_CUDA(top, sc->stager.reserve(16ull * nc));
-    VPC_CUDA(top, sc->stager.h2d(pool, in[c].x, mx + lo[c], 8 * nc, s, -1, copy_workers));
-    VPC_CUDA(top, sc->stager.h2d(pool, in[c].y, my + lo[c], 8 * nc, s, -1, copy_workers));
+    const vpc_host::Stager::Seg hin[2] = {{const_cast<double*>(mx + lo[c]), in[c].x, 8 * nc}, {const_cast<double*>(my + lo[c]), in[c].y, 8 * nc}};
+    VPC_CUDA(top, sc->stager.h2d_multi(pool, hin, 2, s, -1, copy_workers));
     const unsigned long long init[4] = {~0ull, 0ull, 0ull, 0ull};
     VPC_CUDA(top, cudaMemcpyAsync(in[c].range, init, 32, cudaMemcpyHostToDevice, s));
     VPC_CUDA(top, cudaMemsetAsync(in[c].counts, 0, 4 * kMaxWorld * 3, s));
@@ -259,9 +259,8 @@ int group_dbscan(vpc_ctx* top, const double* mx, const double* my, int64_t n, do
     DeviceGuard g(sc->device);
     cudaStream_t s = G->stream[c];
     const size_t nc = (size_t)(lo[c + 1] - lo[c]);
-    VPC_CUDA(top, sc->stager.d2h(pool, cluster_id + lo[c], in[c].cid, 4 * nc, s, -1, copy_workers));
-    VPC_CUDA(top, sc->stager.d2h(pool, is_key + lo[c], in[c].key, nc, s, -1, copy_workers));
-    VPC_CUDA(top, sc->stager.d2h(pool, is_classed + lo[c], in[c].cls, nc, s, -1, copy_workers));
+    const vpc_host::Stager::Seg hout[3] = {{cluster_id + lo[c], in[c].cid, 4 * nc}, {is_key + lo[c], in[c].key, nc}, {is_classed + lo[c], in[c].cls, nc}};
+    VPC_CUDA(top, sc->stager.d2h_multi(pool, hout, 3, s, -1, copy_workers));
     if (c == 0) VPC_CUDA(top, cudaMemcpyAsync(status, sa[0].status, 64, cudaMemcpyDeviceToHost, s));
   }
   for (int c = 0; c < W; ++c) {

@@ -413,14 +413,13 @@ int vpc_dbscan_l1_2d(vpc_ctx* ctx, const double* mx, const double* my, int64_t n
   // pageable arrays (what the P/Invoke marshaller passes) go through worker threads + a page-locked ring; page-locked ones directly
   vpc_host::CopyPool* pool = ctx_pool(ctx);
   if (pool) VPC_CUDA(ctx, ctx->stager.reserve(16ull * n));
-  VPC_CUDA(ctx, ctx->stager.h2d(pool, d_x, mx, 8ull * n, s));
-  VPC_CUDA(ctx, ctx->stager.h2d(pool, d_y, my, 8ull * n, s));
+  const vpc_host::Stager::Seg in[2] = {{const_cast<double*>(mx), d_x, 8ull * (size_t)n}, {const_cast<double*>(my), d_y, 8ull * (size_t)n}};
+  VPC_CUDA(ctx, ctx->stager.h2d_multi(pool, in, 2, s));
   rc = dbscan_enqueue(ctx, d_x, d_y, n, eps, min_pts, first_cluster_id, d_cid, d_key, d_cls, d_amount, s);
   if (rc) return rc;
   int amount = 0;
-  VPC_CUDA(ctx, ctx->stager.d2h(pool, cluster_id, d_cid, 4ull * n, s));
-  VPC_CUDA(ctx, ctx->stager.d2h(pool, is_key, d_key, (size_t)n, s));
-  VPC_CUDA(ctx, ctx->stager.d2h(pool, is_classed, d_cls, (size_t)n, s));
+  const vpc_host::Stager::Seg out[3] = {{cluster_id, d_cid, 4ull * (size_t)n}, {is_key, d_key, (size_t)n}, {is_classed, d_cls, (size_t)n}};
+  VPC_CUDA(ctx, ctx->stager.d2h_multi(pool, out, 3, s));
   VPC_CUDA(ctx, cudaMemcpyAsync(&amount, d_amount, 4, cudaMemcpyDeviceToHost, s));
   VPC_CUDA(ctx, ctx->stager.finish(pool));
   VPC_CUDA(ctx, cudaStreamSynchronize(s));
