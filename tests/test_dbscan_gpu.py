@@ -248,3 +248,22 @@ def test_big_adjacent_cells(ctx, oracle):
     g = rng.integers(0, 40, (6000, 2)) * 0.5
     _check(ctx, oracle, g[:, 0].copy(), g[:, 1].copy(), 1.0, 3)
     _check(ctx, oracle, g[:, 0].copy(), g[:, 1].copy(), 0.5, 2)
+
+
+def test_launch_and_staging_switches_do_not_change_results(oracle, monkeypatch):
+    # VPC_PDL=0 (plain launches), VPC_COPY_THREADS=0 (plain cudaMemcpy) and a forced worker count: contexts read the switches when
+    # they are created; every variant must give the oracle's result on a cloud large enough for several staging chunks
+    from vtkcloudpoint_b200 import Context
+    mx, my = synth.dbscan_cloud(0x5D, 60, n_total=200_003)
+    want = oracle.dbscan(mx, my, 0.07, 7, 3, variant="grid")
+    for env in ({"VPC_PDL": "0"}, {"VPC_COPY_THREADS": "0"}, {"VPC_COPY_THREADS": "5"}, {}):
+        for k in ("VPC_PDL", "VPC_COPY_THREADS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Context(0) as c:
+            got = c.dbscan(mx, my, 0.07, 7, 3)
+        assert got.cluster_amount == want[3], env
+        np.testing.assert_array_equal(got.cluster_id, want[0], err_msg=str(env))
+        np.testing.assert_array_equal(got.is_key, want[1], err_msg=str(env))
+        np.testing.assert_array_equal(got.is_classed, want[2], err_msg=str(env))
