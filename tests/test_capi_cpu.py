@@ -53,3 +53,16 @@ def test_product_never_imports_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.hpp")):
         s = f.read_text()
         assert "oracle_py" not in s and "vpc_oracle" not in s and "vpco_" not in s, f
+
+
+def test_copy_pool_runs_every_index_once(tmp_path):
+    # csrc/host/staging.hpp: the worker pool behind the pageable-memory staging (pure host code; the Stager itself needs a GPU)
+    import shutil
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    cuda_inc = Path(shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc").resolve().parent.parent / "include"
+    exe = tmp_path / "test_copy_pool"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", f"-I{cuda_inc}", "-o", str(exe), str(root / "tests" / "cpp" / "test_copy_pool.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "copy pool ok" in out.stdout, out.stdout + out.stderr
