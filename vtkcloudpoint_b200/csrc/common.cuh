@@ -95,6 +95,22 @@ constexpr int kScanTile = kScanBlock * kScanItems;  // 4096 items per tile
 constexpr unsigned long long kTileAggregate = 1ull << 32;
 constexpr unsigned long long kTilePrefix = 2ull << 32;
 
+// One 32-byte record in ONE store (sm_100: 256-bit global stores, STG.256): a scattered record write is one L2 operation instead of
+// two 128-bit ones.  p must be 32-byte aligned.  VPC_ST256=0: two 128-bit stores.
+#ifndef VPC_ST256
+#define VPC_ST256 1
+#endif
+__device__ __forceinline__ void st_sector(void* p, double a, double b, int c, int d, int e, int f) {
+#if VPC_ST256
+  const unsigned long long w2 = (unsigned long long)(unsigned)c | ((unsigned long long)(unsigned)d << 32);
+  const unsigned long long w3 = (unsigned long long)(unsigned)e | ((unsigned long long)(unsigned)f << 32);
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "l"(w2), "l"(w3) : "memory");
+#else
+  reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+  reinterpret_cast<int4*>(p)[1] = make_int4(c, d, e, f);
+#endif
+}
+
 // Programmatic dependent launch: FIRST statement of a kernel launched with VPC_LAUNCH_PDL (before any early return, so that the grid
 // cannot complete ahead of its predecessor).  Waits until the preceding kernel of the stream has completed and its stores are
 // visible, then lets the next kernel's blocks move into the SMs this grid leaves free (they block in their own pdl_enter()).

@@ -347,9 +347,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_band_scatter(DbArgs a) {
     }
     __syncthreads();
     if (band < kBands) {
-      double2* t2 = reinterpret_cast<double2*>(a.tmp + s_warp[warp][band] + rank_in_warp);
-      t2[0] = make_double2(x, y);
-      reinterpret_cast<int4*>(t2)[1] = make_int4((int)i, key, 0, 0);
+      st_sector(a.tmp + s_warp[warp][band] + rank_in_warp, x, y, (int)i, key, 0, 0);
     }
     __syncthreads();
   }
@@ -407,9 +405,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
   // dense clique cell (>= min_pts points): all core, one cluster, hung under the cell's first slot -- no test
   const bool dense = a.ctrl->clique && (e - s >= a.min_pts);
   a.core[pos] = dense ? 1 : 2;
-  double2* r2 = reinterpret_cast<double2*>(a.rec + pos);   // two 128-bit stores = one full sector
-  r2[0] = make_double2(x, y);
-  reinterpret_cast<int4*>(r2)[1] = make_int4(i, dense ? s : pos, (dense && pos == s) ? s : kNone, kNone);
+  st_sector(a.rec + pos, x, y, i, dense ? s : pos, (dense && pos == s) ? s : kNone, kNone);   // one full sector, one store
 }
 
 // exact reference predicate: Math.Abs(dx) + Math.Abs(dy) <= e   (DBImproved.cs:16-21, :41)
