@@ -153,6 +153,11 @@ __device__ __forceinline__ void db_bounds_rearm(const DbArgs& a, long long tid, 
   for (long long i = tid; i < a.tiles1; i += nth) a.tile_state1[i] = 0;
   if (a.banded) for (long long i = tid; i < a.tiles2; i += nth) a.tile_state2[i] = 0;
   for (long long i = tid; i <= (a.n >> 5); i += nth) a.headbits[i] = 0u;
+  // core[] starts as "dense cell: core" everywhere (coalesced, n bytes); k_db_scatter then stores only the minority outside dense
+  // cells -- a scattered 1-byte store per point was a third of that kernel's L2 store operations
+  uint4* c4 = reinterpret_cast<uint4*>(a.core);
+  const unsigned ones = 0x01010101u;
+  for (long long i = tid; i < (((long long)a.n + 15) >> 4); i += nth) c4[i] = make_uint4(ones, ones, ones, ones);
 }
 // block reduction of the boxes; thread 0 merges the block's box into the control block.  Ends in __syncthreads().
 __device__ __forceinline__ void db_box_publish(DbCtrl* c, DbBox b) {
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(kDbBlock) k_db_scatter(DbArgs a) {
   if (a.seg_off) a.sseg[pos] = a.segof[i];
   // dense clique cell (>= min_pts points): all core, one cluster, hung under the cell's first slot -- no test
   const bool dense = a.ctrl->clique && (e - s >= a.min_pts);
-  a.core[pos] = dense ? 1 : 2;
+  if (!dense) a.core[pos] = 2;                    // dense: 1, preset by the first kernel of the chain (db_bounds_rearm)
   st_sector(a.rec + pos, x, y, i, dense ? s : pos, (dense && pos == s) ? s : kNone, kNone);   // one full sector, one store
 }
 
