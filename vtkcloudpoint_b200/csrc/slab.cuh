@@ -44,7 +44,7 @@ struct SlabArgs {
   unsigned char* is_key_l; int* gkey;       // per local point: core flag, merged cluster key
   int* counters;                            // [0..1] halo strip counts, [2] pairs count, [3] ticket
   int* pair_root;                           // [cap_pairs] sorted position of the local root behind every pair this rank reported
-  unsigned long long* scan_state; int* scan_counter;   // look-back scan of the head bitmap (re-armed by k_slb_heads)
+  unsigned long long* scan_state; int* scan_counter;   // look-back scan of the head bitmap + its completion ticket (re-armed by k_slb_resolve_heads)
   int* bidx;                                // [2 * cap] pre-cut mode: local indices of the own points inside a halo strip (k_slb_halo_pack)
   unsigned long long* epoch;                // step counter (device resident: graph replays advance it)
   int* cid; unsigned char* is_key; unsigned char* is_classed;   // outputs per owned point
