@@ -235,4 +235,99 @@ k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, const int* _
 
 inline int scan_tiles(long long n) { return (int)((n + kScanTile - 1) / kScanTile); }
 
+// ---- the same scan without the look-back chain, for LONG inputs (the ~4M cell counters of a 1M-point DBSCAN are ~1000 tiles that
+// all start together: every tile then walks back over its predecessors' aggregates 32 at a time, ~30 dependent L2 round trips
+// for the last ones).  Three independent passes instead: tile sums, a scan of the tile sums (k_scan_exclusive on <= a few tiles),
+// local scans seeded with the tile's prefix.
+__global__ void __launch_bounds__(kScanBlock) k_scan_tile_sums(const int* __restrict__ in, const int* __restrict__ n_ptr, int n_static, int* __restrict__ tile_sum) {
+  pdl_enter();
+  __shared__ int s_w[kScanBlock / kWarp];
+  const int n = n_ptr ? *n_ptr : n_static;
+  const long long base = (long long)blockIdx.x * kScanTile;
+  int s = 0;
+  if (base < n) {                                           // block-uniform
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+      const long long e = base + 4ll * (k * kScanBlock + (int)threadIdx.x);      // coalesced 128-bit loads
+      if (e + 4 <= n) { const int4 q = *reinterpret_cast<const int4*>(in + e); s += (q.x + q.y) + (q.z + q.w); }
+      else { for (int j = 0; j < 4; ++j) if (e + j < n) s += in[e + j]; }
+    }
+  }
+  s = warp_sum_i(s);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kScanBlock / kWarp; ++w) t += s_w[w];
+    tile_sum[blockIdx.x] = t;
+  }
+}
+
+// tile_prefix[b] = exclusive prefix of tile b (the scanned tile sums)
+__global__ void __launch_bounds__(kScanBlock) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ n_ptr, int n_static,
+                                                           const int* __restrict__ tile_prefix, int* total_out) {
+  pdl_enter();
+  __shared__ int s_warp[kScanBlock / kWarp];
+  const int n = n_ptr ? *n_ptr : n_static;
+  const long long base = (long long)blockIdx.x * kScanTile;
+  if (base >= n) {
+    if (n <= 0 && blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pre = tile_prefix[blockIdx.x];
+  int v[kScanItems];                                        // blocked arrangement, as in scan_exclusive_body
+  const long long t0 = base + (long long)threadIdx.x * kScanItems;
+  if (t0 + kScanItems <= n) {
+    const int4* p = reinterpret_cast<const int4*>(in + t0);
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+      int4 q = p[k];
+      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v[k] = (t0 + k < n) ? in[t0 + k] : 0;
+  }
+  int tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) tsum += v[k];
+  int incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int warp_off = 0, block_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kScanBlock / kWarp; ++w) {
+    int sw = s_warp[w];
+    if (w < warp) warp_off += sw;
+    block_sum += sw;
+  }
+  int run = pre + warp_off + incl - tsum;
+  if (total_out && base + kScanTile >= n && threadIdx.x == kScanBlock - 1) *total_out = pre + block_sum;
+  if (t0 + kScanItems <= n) {
+    int4* p = reinterpret_cast<int4*>(out + t0);
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+      int4 q;
+      q.x = run; run += v[4 * k];
+      q.y = run; run += v[4 * k + 1];
+      q.z = run; run += v[4 * k + 2];
+      q.w = run; run += v[4 * k + 3];
+      p[k] = q;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (t0 + k < n) out[t0 + k] = run;
+      run += v[k];
+    }
+  }
+}
+
 }  // namespace vpc

@@ -107,6 +107,9 @@ int dbscan_prepare(vpc_ctx* ctx, const double* d_x, const double* d_y, int64_t n
   return VPC_OK;
 }
 
+#ifndef VPC_SCAN_THREE_PASS
+#define VPC_SCAN_THREE_PASS 1
+#endif
 int dbscan_run(vpc_ctx* ctx, const DbArgs& a, cudaStream_t s, bool slab, bool have_grid) {
   const int64_t n = a.n;
   const bool banded = a.banded != 0;
@@ -125,8 +128,20 @@ int dbscan_run(vpc_ctx* ctx, const DbArgs& a, cudaStream_t s, bool slab, bool ha
   } else {
     VPC_LAUNCH_PDL(ctx, k_db_hist<false>, gpts, kDbBlock, s, a);
   }
+#if VPC_SCAN_THREE_PASS
+  {  // cell offsets without a look-back chain (common.cuh): tile sums -> their scan -> local scans.  The tile sums and the small
+     // scan's states share the (re-armed) tile_state0 buffer: int[tiles0], then the states behind it
+    int* tile_sum = reinterpret_cast<int*>(a.tile_state0);
+    unsigned long long* st2 = reinterpret_cast<unsigned long long*>(tile_sum + ((tiles0 + 1) & ~1));
+    VPC_LAUNCH_PDL(ctx, k_scan_tile_sums, tiles0, kScanBlock, s, a.cell_count, &a.ctrl->ncells_p1, 0, tile_sum);
+    VPC_LAUNCH_PDL(ctx, k_scan_exclusive<false>, scan_tiles(tiles0), kScanBlock, s, tile_sum, tile_sum, (const int*)nullptr, tiles0, st2, &a.ctrl->scan_counter[0],
+                   (int*)nullptr);
+    VPC_LAUNCH_PDL(ctx, k_scan_tiles, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0, tile_sum, &a.ctrl->n_valid);
+  }
+#else
   VPC_LAUNCH_PDL(ctx, k_scan_exclusive<false>, tiles0, kScanBlock, s, a.cell_count, a.cell_start, &a.ctrl->ncells_p1, 0,
              a.tile_state0, &a.ctrl->scan_counter[0], &a.ctrl->n_valid);
+#endif
   if (banded) VPC_LAUNCH_PDL(ctx, k_db_scatter<true>, gpts, kDbBlock, s, a);
   else VPC_LAUNCH_PDL(ctx, k_db_scatter<false>, gpts, kDbBlock, s, a);
   ctx->db_ws_banded = banded;
